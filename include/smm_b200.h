@@ -1,0 +1,171 @@
+/* smm_b200.h -- C ABI of libsmm_b200.so: the B200 (sm_100a) implementation of SMM.jl's
+ * parallel-tempered BGP MCMC hot path.
+ *
+ * The reference has no FFI (it is pure Julia); each entry point below replaces a Julia-level
+ * function of /root/reference/src/mopt and is what a Julia `ccall` shim (julia/SMMB200.jl,
+ * INTEGRATION.md), Python ctypes (smm_jl_b200/_lib.py) or a C++ driver binds:
+ *
+ *   smm_bgp_create      <- MAlgoBGP(m::MProb, opts)            AlgoBGP.jl:505-538 (+ BGPChain :78-109)
+ *   smm_bgp_step        <- run!(algo) / computeNextIteration!  AlgoAbstract.jl:27-76, AlgoBGP.jl:589-640
+ *                          (proposal :424, evaluateObjective mprob.jl:175, objfunc_norm
+ *                          ObjExamples.jl:59, doAcceptReject! :324, set_eval! :220,
+ *                          exchangeMoves! :647, swap_ev_ij! :734)
+ *   smm_bgp_read_trace  <- BGPChain fields / history(c)        AlgoBGP.jl:42-61,138-160
+ *   smm_bgp_read_chain_state <- c.sigma, c.accept_rate         AlgoBGP.jl:253-257,381-390
+ *   smm_bgp_eval_batch  <- evaluateObjective(m, p; noseed)     mprob.jl:175-205 (batched)
+ *   smm_bgp_export_state / smm_bgp_import_state <- save / readMalgo / restart!
+ *                                                              AlgoAbstract.jl:83-102, AlgoBGP.jl:804
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 or a negative SMM_E_* code
+ * and leaves a message for smm_last_error() (thread local); no C++ exception crosses the boundary.
+ * Host buffers are caller-owned and touched only during the call.  The library owns all device
+ * memory, its CUDA stream and (world_size > 1) its NCCL communicator.  One process drives one GPU;
+ * a multi-GPU run is world_size processes that each create a handle with the same config, their
+ * own rank, and the same nccl_id (made by rank 0 with smm_nccl_unique_id and broadcast by the
+ * host language: torch.distributed in Python, Distributed/MPI in Julia).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with SMM_E_CUDA.
+ */
+#ifndef SMM_B200_H
+#define SMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMM_ABI_VERSION 1
+
+/* error codes */
+#define SMM_OK 0
+#define SMM_E_ARG (-1)
+#define SMM_E_CUDA (-2)
+#define SMM_E_NCCL (-3)
+#define SMM_E_UNSUPPORTED_SHAPE (-4)
+#define SMM_E_NEGATIVE_OBJECTIVE (-5) /* AlgoBGP.jl:341 `error("AlgoBGP assumes ... non-negative")` */
+#define SMM_E_SAMPLER_EXHAUSTED (-6)  /* AlgoBGP.jl:409 `error("no draw in support after ...")`   */
+#define SMM_E_STATE (-7)
+
+/* built-in objective functions (the device simulators selected by addEvalFunc!) */
+#define SMM_OBJ_NORM 0      /* objfunc_norm      ObjExamples.jl:59-116  (P == M: row means)          */
+#define SMM_OBJ_NORM_SLOW 1 /* objfunc_norm_slow ObjExamples.jl:124-184 (+ slow_seconds per eval)    */
+#define SMM_OBJ_NORM_MV 2   /* means + sample variances, M == 2P (generalises
+                               objfunc_norm2 ObjExamples.jl:191, which is broken upstream)           */
+#define SMM_OBJ_PANEL 3     /* dynamic panel, P == 2K+4, M == 4K+8 (no upstream code)   */
+#define SMM_OBJ_FAILS 4     /* Testobj_fails     ObjExamples.jl:27-32: every evaluation throws ->
+                               status -2, value stays -1.0 (mprob.jl:183-186)                        */
+
+#define SMM_MAX_PARAMS 64
+#define SMM_MAX_MOMENTS 128
+#define SMM_NCCL_ID_BYTES 128
+
+typedef struct smm_bgp smm_bgp; /* opaque */
+
+typedef struct smm_bgp_config {
+  int32_t abi_version; /* SMM_ABI_VERSION */
+  /* problem (MProb, mprob.jl:29-53) */
+  int32_t n_params;      /* P: sampled parameters, in params_to_sample order                       */
+  int32_t n_moments;     /* M: data moments, in moments order                                       */
+  const double *lb;      /* [P] lower bounds                                                        */
+  const double *ub;      /* [P] upper bounds                                                        */
+  const double *init;    /* [P] initial_value                                                       */
+  const double *data_mom; /* [M] data moment values                                                 */
+  const double *data_w;   /* [M] data moment weights (divide, as an s.d.: ObjExamples.jl:97)        */
+  /* objective */
+  int32_t objective_id;  /* SMM_OBJ_*                                                               */
+  int32_t n_sim;         /* S simulation draws per evaluation (10000 at ObjExamples.jl:76)          */
+  uint64_t seed_sim;     /* 1234 at ObjExamples.jl:74                                               */
+  int32_t noseed;        /* ev.options[:noseed] (ObjExamples.jl:71): fresh draws per evaluation     */
+  double slow_seconds;   /* SMM_OBJ_NORM_SLOW: sleep(0.1) at ObjExamples.jl:130                     */
+  int32_t panel_T;       /* SMM_OBJ_PANEL                                                           */
+  int32_t panel_N;
+  int32_t panel_K;
+  /* algorithm (opts of MAlgoBGP, AlgoBGP.jl:505-538) */
+  int32_t n_chains;            /* opts["N"] (total over all ranks)                                   */
+  int32_t max_iter;            /* opts["maxiter"]: trace capacity                                    */
+  const double *sigma0;        /* [N] sigma * temps[i]                                               */
+  const double *acc_tuner;     /* [N] opts["acc_tuners"]                                             */
+  const double *min_improve;   /* [N] opts["min_improve"]                                            */
+  int32_t sigma_update_steps;  /* 10                                                                 */
+  double sigma_adjust_by;      /* 0.01                                                               */
+  int32_t smpl_iters;          /* 1000                                                               */
+  int32_t batch_size;          /* P by default; must divide P (see DESIGN.md on the upstream bug)    */
+  uint64_t seed_algo;          /* seeds Zprop, Uacc, Pairs                                           */
+  /* placement */
+  int32_t device;      /* CUDA device ordinal of this process                                        */
+  int32_t world_size;  /* number of processes/GPUs sharing the chains (1, 2, 4, 8)                   */
+  int32_t rank;        /* this process: owns chains [rank*N/world, (rank+1)*N/world)                  */
+  uint8_t nccl_id[SMM_NCCL_ID_BYTES]; /* from smm_nccl_unique_id on rank 0 (ignored if world == 1)   */
+  int32_t exchange_mode; /* 0 = ncclAllGather + exchange kernel; 1 = fused peer-store all-gather       */
+  int32_t n_split;       /* CTAs per chain evaluation; 0 = choose from the SM count                    */
+} smm_bgp_config;
+
+/* Host-side SoA view of iterations [iter_lo, iter_hi] (1-based, inclusive) of the chains this rank
+ * owns.  n = iter_hi - iter_lo + 1, L = local chains.  Row-major [n][L] (+[P] / [M]).  Any pointer
+ * may be NULL to skip that column.  Mirrors the BGPChain vectors and the Eval fields history() reads. */
+typedef struct smm_trace_view {
+  double *value;       /* [n][L]     evals[it].value                                                */
+  double *prob;        /* [n][L]     evals[it].prob                                                 */
+  double *curr_val;    /* [n][L]     curr_val[it]                                                   */
+  double *best_val;    /* [n][L]     best_val[it]                                                   */
+  double *params;      /* [n][L][P]  evals[it].params                                               */
+  double *sim_moments; /* [n][L][M]  evals[it].simMoments                                           */
+  uint8_t *accepted;   /* [n][L]     accepted[it]                                                   */
+  int32_t *status;     /* [n][L]     evals[it].status                                               */
+  int32_t *exchanged;  /* [n][L]     exchanged[it] (1-based partner id, 0 = none)                   */
+  int32_t *best_id;    /* [n][L]     best_id[it] (1-based iteration)                                */
+} smm_trace_view;
+
+typedef struct smm_counters {
+  int64_t iterations;       /* iterations completed                                                  */
+  int64_t evaluations;      /* objective evaluations done by this rank (iterations * local chains)  */
+  int64_t kernel_launches;  /* this library's kernel launches (all kinds)                            */
+  int64_t collectives;      /* NCCL collectives enqueued                                             */
+  int64_t accepted;         /* Metropolis accepts over local chains                                  */
+  int64_t swaps;            /* exchange moves that swapped (counted once per pair, all chains)       */
+  int64_t proposal_attempts; /* rejection-loop attempts used by local chains                         */
+} smm_counters;
+
+int smm_abi_version(void);
+const char *smm_last_error(void);
+int smm_device_count(void);
+int smm_nccl_unique_id(uint8_t out[SMM_NCCL_ID_BYTES]);
+
+int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out);
+void smm_bgp_destroy(smm_bgp *h);
+
+/* run iterations i+1 .. i+n_iters; blocking (returns after the device finished and the sticky
+ * device error flag was checked).  elapsed_ms (may be NULL) receives the CUDA-event time of the
+ * region on the library's stream. */
+int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms);
+int smm_bgp_iteration(const smm_bgp *h); /* iterations completed so far (algo.i) */
+int smm_bgp_local_chains(const smm_bgp *h);
+void *smm_bgp_stream(smm_bgp *h); /* cudaStream_t the kernels run on */
+
+int smm_bgp_read_trace(smm_bgp *h, int32_t iter_lo, int32_t iter_hi, const smm_trace_view *out);
+int smm_bgp_read_chain_state(smm_bgp *h, double *sigma, double *accept_rate); /* [L] each */
+int smm_bgp_get_counters(smm_bgp *h, smm_counters *out);
+
+/* batched bare objective: value[B], moments[B][M], status[B] at params[B][P] (host pointers).
+ * noseed != 0 draws fresh shocks indexed by (entry b, rep0 + b). */
+int smm_bgp_eval_batch(smm_bgp *h, const double *params, int32_t B, int32_t noseed, uint32_t rep0,
+                       double *value, double *moments, int32_t *status);
+
+/* checkpoint: the per-chain algorithm state (sigma, accept counters, last-accepted record) plus the
+ * trace are enough to resume; all randomness is counter-indexed so there is no RNG state. */
+int64_t smm_bgp_state_bytes(const smm_bgp *h);
+int smm_bgp_export_state(smm_bgp *h, void *buf, int64_t nbytes);
+int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes);
+
+/* test/diagnostic entry points (device implementations of the stream definitions) */
+int smm_debug_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_pairs,
+                      double *out /* [2*n_pairs] */);
+int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij /* [n_pairs][2] in execution order */,
+                    int32_t *level_offsets /* [n_pairs+1] */, int32_t *n_levels);
+int smm_debug_rng_throughput(int32_t device, int64_t n_pairs_per_thread, int32_t blocks, int32_t threads,
+                             float *elapsed_ms, double *checksum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMM_B200_H */

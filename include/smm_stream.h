@@ -1,0 +1,265 @@
+/* smm_stream.h -- NORMATIVE definition of the counter-indexed random streams of the BGP hot path.
+ *
+ * The reference draws its randomness from Julia's global RNG and an unseedable RandomDevice
+ * (/root/reference/src/SMM.jl:59-60, src/mopt/AlgoBGP.jl:85,404,656, src/mopt/ObjExamples.jl:74-79),
+ * none of which is reproducible outside one Julia build.  Parity is therefore defined on the
+ * reference's ALGORITHM as a pure function of four injected streams:
+ *
+ *   Zsim [row k, draw s]                 standard normals of the model simulator
+ *   Zprop[chain, iter, attempt, param k] standard normals of the truncated random-walk proposal
+ *   Uacc [chain, iter]                   the pre-drawn Metropolis uniforms  (BGPChain.probs_acc)
+ *   Pairs[iter][t]                       the exchange-move pair sample
+ *
+ * Every element is a pure function of (seed, indices): Philox4x32-10 keyed by the seed, the indices in
+ * the 128-bit counter, then a fixed fp64 transform that uses only + - * fma / sqrt and therefore
+ * yields BIT-IDENTICAL doubles on the host (oracle, Julia CPU objfunc) and on the device (kernels).
+ * This header is included by the CUDA kernels (smm_jl_b200/csrc) and by the CPU oracle (oracle/);
+ * it contains no algorithm of the BGP sampler itself.
+ *
+ * Compile host code with -ffp-contract=off (and -mfma for speed); device code uses the _rn
+ * intrinsics so nvcc's -fmad setting cannot change results.
+ */
+#ifndef SMM_STREAM_H
+#define SMM_STREAM_H
+
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+#include "smm_stream_tables.h"
+
+#if defined(__CUDACC__)
+#define SMM_HD __host__ __device__ __forceinline__
+#else
+#define SMM_HD static inline
+#endif
+
+/* stream ids: the top 4 bits of counter word 3; the low 28 bits carry the iteration */
+#define SMM_STREAM_SIM 1u
+#define SMM_STREAM_PROP 2u
+#define SMM_STREAM_ACC 3u
+#define SMM_STREAM_PAIR 4u
+#define SMM_ITER_MASK 0x0FFFFFFFu
+
+/* ---- exactly-rounded primitive ops (never contracted) ------------------------------------ */
+#if defined(__CUDA_ARCH__)
+#define SMM_MUL(a, b) __dmul_rn((a), (b))
+#define SMM_ADD(a, b) __dadd_rn((a), (b))
+#define SMM_SUB(a, b) __dsub_rn((a), (b))
+#define SMM_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define SMM_SQRT(a) __dsqrt_rn((a))
+#else
+#define SMM_MUL(a, b) ((a) * (b))
+#define SMM_ADD(a, b) ((a) + (b))
+#define SMM_SUB(a, b) ((a) - (b))
+#define SMM_FMA(a, b, c) fma((a), (b), (c))
+#define SMM_SQRT(a) sqrt((a))
+#endif
+
+/* ---- Philox4x32-10 (Salmon et al., SC'11; same constants as Random123 / cuRAND) ---------- */
+typedef struct smm_u32x4 {
+  uint32_t x, y, z, w;
+} smm_u32x4;
+
+#define SMM_PHILOX_M0 0xD2511F53u
+#define SMM_PHILOX_M1 0xCD9E8D57u
+#define SMM_PHILOX_W0 0x9E3779B9u
+#define SMM_PHILOX_W1 0xBB67AE85u
+
+SMM_HD void smm_mulhilo(uint32_t a, uint32_t b, uint32_t *hi, uint32_t *lo) {
+#if defined(__CUDA_ARCH__)
+  *lo = a * b;
+  *hi = __umulhi(a, b);
+#else
+  uint64_t p = (uint64_t)a * (uint64_t)b;
+  *lo = (uint32_t)p;
+  *hi = (uint32_t)(p >> 32);
+#endif
+}
+
+SMM_HD smm_u32x4 smm_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                   uint32_t k1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    smm_mulhilo(SMM_PHILOX_M0, c0, &hi0, &lo0);
+    smm_mulhilo(SMM_PHILOX_M1, c2, &hi1, &lo1);
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += SMM_PHILOX_W0;
+    k1 += SMM_PHILOX_W1;
+  }
+  smm_u32x4 out;
+  out.x = c0;
+  out.y = c1;
+  out.z = c2;
+  out.w = c3;
+  return out;
+}
+
+/* ---- bit casts --------------------------------------------------------------------------- */
+SMM_HD double smm_bits_to_double(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)b);
+#else
+  double d;
+  memcpy(&d, &b, sizeof d);
+  return d;
+#endif
+}
+SMM_HD uint64_t smm_double_to_bits(double d) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(d);
+#else
+  uint64_t b;
+  memcpy(&b, &d, sizeof b);
+  return b;
+#endif
+}
+
+/* 52 random mantissa bits from two words: a supplies the high 32, b its top 20 */
+SMM_HD uint64_t smm_mant52(uint32_t a, uint32_t b) { return ((uint64_t)a << 20) | (uint64_t)(b >> 12); }
+
+/* uniform on [0,1) with 52-bit resolution (Julia's rand(Float64) convention) */
+SMM_HD double smm_u01(uint32_t a, uint32_t b) {
+  return SMM_SUB(smm_bits_to_double(0x3FF0000000000000ull | smm_mant52(a, b)), 1.0);
+}
+
+/* ---- log table ---------------------------------------------------------------------------- */
+typedef struct smm_logent {
+  double inv, lnc;
+} smm_logent;
+
+static const smm_logent SMM_LOGTAB_HOST[1 << SMM_LOG_BITS] = SMM_LOG_TABLE;
+#if defined(__CUDACC__)
+static __device__ const smm_logent SMM_LOGTAB_DEV[1 << SMM_LOG_BITS] = SMM_LOG_TABLE;
+#endif
+
+SMM_HD const smm_logent *smm_logtab(void) {
+#if defined(__CUDA_ARCH__)
+  return SMM_LOGTAB_DEV;
+#else
+  return SMM_LOGTAB_HOST;
+#endif
+}
+
+/* natural log of a normal, positive double u in (0,1]; abs error ~1e-16 (tests/test_stream.py) */
+SMM_HD double smm_log01(double u, const smm_logent *tab) {
+  const uint64_t b = smm_double_to_bits(u);
+  const int e = (int)((b >> 52) & 0x7FFu) - 1023;
+  const uint32_t j = (uint32_t)(b >> (52 - SMM_LOG_BITS)) & ((1u << SMM_LOG_BITS) - 1u);
+  const double m = smm_bits_to_double((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+  const smm_logent t = tab[j];
+  const double r = SMM_FMA(m, t.inv, -1.0); /* exact for the end buckets, |r| <= 2^-7 */
+  const double q[SMM_LOGQ_DEG + 1] = SMM_LOGQ_COEFS;
+  double p = q[SMM_LOGQ_DEG];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = SMM_LOGQ_DEG - 1; i >= 0; --i) p = SMM_FMA(p, r, q[i]);
+  const double r2 = SMM_MUL(r, r);
+  const double l1p = SMM_FMA(r2, p, r);                   /* log(1+r) */
+  const double base = SMM_FMA((double)e, SMM_LN2, t.lnc); /* e*ln2 + ln(c_j); 0 near u=1 */
+  return SMM_ADD(base, l1p);
+}
+
+/* cos and sin of 2*pi*B/2^52 for a 52-bit integer B: octant from the top 3 bits, the remaining
+ * 49 bits are the (exact) position inside the octant */
+SMM_HD void smm_sincos_turn52(uint64_t B, double *c_out, double *s_out) {
+  const uint32_t oct = (uint32_t)(B >> 49) & 7u;
+  const uint64_t rem = B & ((1ull << 49) - 1ull);
+  const double d = smm_bits_to_double(0x3FF0000000000000ull | (rem << 3)); /* 1 + f */
+  const double g = (oct & 1u) ? SMM_SUB(2.0, d) : SMM_SUB(d, 1.0);         /* f or 1-f, exact */
+  const double w = SMM_MUL(g, g);
+  const double cs[SMM_SIN_DEG + 1] = SMM_SIN_COEFS;
+  const double cc[SMM_COS_DEG + 1] = SMM_COS_COEFS;
+  double ps = cs[SMM_SIN_DEG];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = SMM_SIN_DEG - 1; i >= 0; --i) ps = SMM_FMA(ps, w, cs[i]);
+  double pc = cc[SMM_COS_DEG];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = SMM_COS_DEG - 1; i >= 0; --i) pc = SMM_FMA(pc, w, cc[i]);
+  const double sn = SMM_MUL(g, ps); /* sin(pi/4 * g) */
+  const double cn = pc;             /* cos(pi/4 * g) */
+  const int swap = ((oct + 1u) >> 1) & 1u;
+  double c = swap ? sn : cn;
+  double s = swap ? cn : sn;
+  if (((oct + 2u) >> 2) & 1u) c = -c;
+  if (oct >> 2) s = -s;
+  *c_out = c;
+  *s_out = s;
+}
+
+/* Box-Muller on one Philox block: words x,y -> radius uniform in (0,1], words z,w -> angle */
+SMM_HD void smm_normal_pair_tab(smm_u32x4 r, const smm_logent *tab, double *z0, double *z1) {
+  const double d1 = smm_bits_to_double(0x3FF0000000000000ull | smm_mant52(r.x, r.y));
+  const double u1 = SMM_SUB(2.0, d1); /* (0,1], exact */
+  const double l = smm_log01(u1, tab);
+  const double rad = SMM_SQRT(SMM_MUL(-2.0, l));
+  double c, s;
+  smm_sincos_turn52(smm_mant52(r.z, r.w), &c, &s);
+  *z0 = SMM_MUL(rad, c);
+  *z1 = SMM_MUL(rad, s);
+}
+SMM_HD void smm_normal_pair(smm_u32x4 r, double *z0, double *z1) {
+  smm_normal_pair_tab(r, smm_logtab(), z0, z1);
+}
+
+/* ---- the four streams ----------------------------------------------------------------------- */
+
+/* Zsim[k, 2j] and Zsim[k, 2j+1].  With common random numbers (noseed == 0, the reference's
+ * Random.seed!(1234) at ObjExamples.jl:74) every evaluation sees the same block; with noseed the
+ * block is additionally indexed by (eval_uid, rep). */
+SMM_HD smm_u32x4 smm_sim_block(uint64_t seed_sim, uint32_t j, uint32_t k, int noseed, uint32_t eval_uid,
+                               uint32_t rep) {
+  const uint32_t c2 = noseed ? eval_uid : 0u;
+  const uint32_t c3 = (SMM_STREAM_SIM << 28) | (noseed ? (rep & SMM_ITER_MASK) : 0u);
+  return smm_philox4x32_10(j, k, c2, c3, (uint32_t)seed_sim, (uint32_t)(seed_sim >> 32));
+}
+
+/* Zprop[chain, iter, attempt, 2*kpair] and [.., 2*kpair+1]  (chain 0-based global id, iter 1-based) */
+SMM_HD smm_u32x4 smm_prop_block(uint64_t seed_algo, uint32_t chain, uint32_t iter, uint32_t attempt,
+                                uint32_t kpair) {
+  return smm_philox4x32_10(attempt, kpair, chain, (SMM_STREAM_PROP << 28) | (iter & SMM_ITER_MASK),
+                           (uint32_t)seed_algo, (uint32_t)(seed_algo >> 32));
+}
+
+/* Uacc[chain, iter] in [0,1) */
+SMM_HD double smm_acc_uniform(uint64_t seed_algo, uint32_t chain, uint32_t iter) {
+  const smm_u32x4 r = smm_philox4x32_10(0u, 0u, chain, (SMM_STREAM_ACC << 28) | (iter & SMM_ITER_MASK),
+                                        (uint32_t)seed_algo, (uint32_t)(seed_algo >> 32));
+  return smm_u01(r.x, r.y);
+}
+
+/* candidate rank in [0, n_pairs) for slot t of Pairs[iter], redraw number `attempt` */
+SMM_HD uint32_t smm_pair_candidate(uint64_t seed_algo, uint32_t iter, uint32_t t, uint32_t attempt,
+                                   uint32_t n_pairs) {
+  const smm_u32x4 r = smm_philox4x32_10(t, attempt, 0u, (SMM_STREAM_PAIR << 28) | (iter & SMM_ITER_MASK),
+                                        (uint32_t)seed_algo, (uint32_t)(seed_algo >> 32));
+  const uint64_t v = ((uint64_t)r.x << 32) | (uint64_t)r.y;
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__umul64hi(v, (uint64_t)n_pairs);
+#else
+  return (uint32_t)(((unsigned __int128)v * (unsigned __int128)n_pairs) >> 64);
+#endif
+}
+
+/* rank q (0-based) -> pair (i<j), 0-based, in the order of the reference's comprehension
+ * `[(i,j) for i in 1:N, j in 1:N if i<j]` (AlgoBGP.jl:653): i runs fastest, so rank = j(j-1)/2 + i */
+SMM_HD void smm_pair_unrank(uint32_t q, uint32_t *i, uint32_t *j) {
+  /* j = floor((1+sqrt(1+8q))/2), fixed up with integer arithmetic */
+  uint32_t jj = (uint32_t)((1.0 + SMM_SQRT((double)(1.0 + 8.0 * (double)q))) * 0.5);
+  while ((uint64_t)jj * (jj - 1u) / 2u > q) --jj;
+  while ((uint64_t)(jj + 1u) * jj / 2u <= q) ++jj;
+  *j = jj;
+  *i = q - (uint32_t)((uint64_t)jj * (jj - 1u) / 2u);
+}
+
+#endif /* SMM_STREAM_H */

@@ -1,0 +1,186 @@
+"""ctypes binding of libsmm_b200.so -- the C ABI declared in include/smm_b200.h.
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc
+(smm_jl_b200/build.py); if that fails, or no CUDA device is present, compute calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from ._abi import (BGPConfig, ERROR_NAMES, SMM_NCCL_ID_BYTES, Trace, smm_bgp_config, smm_counters, smm_trace_view)
+
+_lib = None
+
+EXPORTS = [
+    "smm_abi_version", "smm_last_error", "smm_device_count", "smm_nccl_unique_id", "smm_bgp_create",
+    "smm_bgp_destroy", "smm_bgp_step", "smm_bgp_iteration", "smm_bgp_local_chains", "smm_bgp_stream",
+    "smm_bgp_read_trace", "smm_bgp_read_chain_state", "smm_bgp_get_counters", "smm_bgp_eval_batch",
+    "smm_bgp_state_bytes", "smm_bgp_export_state", "smm_bgp_import_state", "smm_debug_normals",
+    "smm_debug_pairs", "smm_debug_rng_throughput",
+]
+
+
+class SMMError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return _build.SO
+
+
+def lib():
+    """Load (building first if needed) libsmm_b200.so."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.SO):
+        _build.build()
+    L = C.CDLL(_build.SO, mode=C.RTLD_GLOBAL)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    vp = C.c_void_p
+    L.smm_abi_version.restype = C.c_int
+    L.smm_last_error.restype = C.c_char_p
+    L.smm_device_count.restype = C.c_int
+    L.smm_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    L.smm_bgp_create.argtypes = [C.POINTER(smm_bgp_config), C.POINTER(vp)]
+    L.smm_bgp_destroy.argtypes = [vp]
+    L.smm_bgp_destroy.restype = None
+    L.smm_bgp_step.argtypes = [vp, C.c_int32, C.POINTER(C.c_float)]
+    L.smm_bgp_iteration.argtypes = [vp]
+    L.smm_bgp_local_chains.argtypes = [vp]
+    L.smm_bgp_stream.argtypes = [vp]
+    L.smm_bgp_stream.restype = vp
+    L.smm_bgp_read_trace.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(smm_trace_view)]
+    L.smm_bgp_read_chain_state.argtypes = [vp, dp, dp]
+    L.smm_bgp_get_counters.argtypes = [vp, C.POINTER(smm_counters)]
+    L.smm_bgp_eval_batch.argtypes = [vp, dp, C.c_int32, C.c_int32, C.c_uint32, dp, dp, ip]
+    L.smm_bgp_state_bytes.argtypes = [vp]
+    L.smm_bgp_state_bytes.restype = C.c_int64
+    L.smm_bgp_export_state.argtypes = [vp, vp, C.c_int64]
+    L.smm_bgp_import_state.argtypes = [vp, vp, C.c_int64]
+    L.smm_debug_normals.argtypes = [C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, dp]
+    L.smm_debug_pairs.argtypes = [vp, C.c_int32, ip, ip, ip]
+    L.smm_debug_rng_throughput.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float), dp]
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise SMMError(rc, lib().smm_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    return lib().smm_device_count()
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * SMM_NCCL_ID_BYTES)()
+    check(lib().smm_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+class BGPHandle:
+    """Thin owner of an `smm_bgp*`: create / step / read_trace / destroy."""
+
+    def __init__(self, cfg: BGPConfig):
+        self.cfg = cfg
+        self._cs = cfg.c_struct()
+        self._h = C.c_void_p()
+        check(lib().smm_bgp_create(C.byref(self._cs), C.byref(self._h)))
+        self.L = lib().smm_bgp_local_chains(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().smm_bgp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def iteration(self) -> int:
+        return lib().smm_bgp_iteration(self._h)
+
+    @property
+    def stream(self) -> int:
+        return lib().smm_bgp_stream(self._h) or 0
+
+    def step(self, n_iters: int) -> float:
+        """Run n_iters iterations; returns the CUDA-event time of the region in ms."""
+        ms = C.c_float(0.0)
+        check(lib().smm_bgp_step(self._h, n_iters, C.byref(ms)))
+        return ms.value
+
+    def read_trace(self, iter_lo: int = 1, iter_hi: int | None = None, into: Trace | None = None) -> Trace:
+        hi = self.iteration if iter_hi is None else iter_hi
+        n = hi - iter_lo + 1
+        tr = into if into is not None else Trace(n, self.L, self.cfg.n_params, self.cfg.n_moments)
+        v = tr.view()
+        check(lib().smm_bgp_read_trace(self._h, iter_lo, hi, C.byref(v)))
+        return tr
+
+    def chain_state(self):
+        sigma, acc = np.zeros(self.L), np.zeros(self.L)
+        dp = C.POINTER(C.c_double)
+        check(lib().smm_bgp_read_chain_state(self._h, sigma.ctypes.data_as(dp), acc.ctypes.data_as(dp)))
+        return sigma, acc
+
+    def counters(self) -> dict:
+        c = smm_counters()
+        check(lib().smm_bgp_get_counters(self._h, C.byref(c)))
+        return {f: getattr(c, f) for f, _ in smm_counters._fields_}
+
+    def eval_batch(self, params, noseed: int = 0, rep0: int = 0):
+        P, M = self.cfg.n_params, self.cfg.n_moments
+        params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1, P))
+        B = params.shape[0]
+        value, mom, status = np.zeros(B), np.zeros((B, M)), np.zeros(B, dtype=np.int32)
+        dp = C.POINTER(C.c_double)
+        check(lib().smm_bgp_eval_batch(self._h, params.ctypes.data_as(dp), B, noseed, rep0, value.ctypes.data_as(dp),
+                                       mom.ctypes.data_as(dp), status.ctypes.data_as(C.POINTER(C.c_int32))))
+        return value, mom, status
+
+    def export_state(self) -> bytes:
+        n = lib().smm_bgp_state_bytes(self._h)
+        buf = C.create_string_buffer(n)
+        check(lib().smm_bgp_export_state(self._h, C.cast(buf, C.c_void_p), n))
+        return buf.raw
+
+    def import_state(self, blob: bytes):
+        buf = C.create_string_buffer(blob, len(blob))
+        check(lib().smm_bgp_import_state(self._h, C.cast(buf, C.c_void_p), len(blob)))
+
+    def debug_pairs(self, it: int):
+        n_s = self.cfg.n_chains if self.cfg.n_chains >= 3 else self.cfg.n_chains - 1
+        ij = np.zeros((n_s, 2), dtype=np.int32)
+        off = np.zeros(n_s + 1, dtype=np.int32)
+        nlev = C.c_int32(0)
+        ip = C.POINTER(C.c_int32)
+        check(lib().smm_debug_pairs(self._h, it, ij.ctypes.data_as(ip), off.ctypes.data_as(ip), C.byref(nlev)))
+        return ij, off[: nlev.value + 1], nlev.value
+
+
+def debug_normals(seed: int, k: int, c2: int, c3: int, n_pairs: int, device: int = 0) -> np.ndarray:
+    out = np.zeros(2 * n_pairs)
+    check(lib().smm_debug_normals(device, seed, k, c2, c3, n_pairs, out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def rng_throughput(n_pairs_per_thread: int, blocks: int, device: int = 0):
+    """RNG-only micro-kernel (Philox + Box-Muller + 2 accumulations): returns (ms, normals/s)."""
+    ms, cs = C.c_float(0.0), C.c_double(0.0)
+    check(lib().smm_debug_rng_throughput(device, n_pairs_per_thread, blocks, 128, C.byref(ms), C.byref(cs)))
+    normals = 2.0 * n_pairs_per_thread * blocks * 128
+    return ms.value, normals / (ms.value * 1e-3)

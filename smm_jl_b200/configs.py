@@ -1,0 +1,72 @@
+"""The BASELINE.json configurations as `BGPConfig`s (shapes from /root/reference/src/mopt/Examples.jl
+and SURVEY.md section 8d).  Pure host-side data; used by bench.py and the tests."""
+from __future__ import annotations
+
+import numpy as np
+
+from ._abi import BGPConfig, SMM_OBJ_NORM, SMM_OBJ_NORM_MV, SMM_OBJ_NORM_SLOW, SMM_OBJ_PANEL
+
+
+def temperature_ladder(n_chains: int, maxtemp: float) -> np.ndarray:
+    """`temps = range(1.0, stop=maxtemp, length=N)` (AlgoBGP.jl:508); a single chain has no ladder (:526)."""
+    if n_chains == 1:
+        return np.ones(1)
+    return np.linspace(1.0, float(maxtemp), n_chains)
+
+
+def c1_serial_normal(niter: int = 200, slow: bool = False, slow_seconds: float = 0.1, **kw) -> BGPConfig:
+    """`SMM.serialNormal(2, niter)` (Examples.jl:118-153 -> snorm_impl :373-446): 3 chains, 2 params."""
+    n = 3
+    temps = temperature_ladder(n, 5.0)
+    args = dict(
+        lb=[-3.0, -20.0], ub=[3.0, 20.0], init=[0.2, -0.2],
+        data_mom=[-1.0, 10.0], data_w=[1.0, 1.0],
+        n_chains=n, max_iter=niter,
+        sigma0=0.05 * temps, acc_tuner=[20.0, 2.0, 1.0], min_improve=[0.0] * n,
+        objective_id=SMM_OBJ_NORM_SLOW if slow else SMM_OBJ_NORM, slow_seconds=slow_seconds,
+        n_sim=10000, seed_sim=1234, seed_algo=12,
+    )
+    args.update(kw)
+    return BGPConfig(**args)
+
+
+def mvnormal(n_chains: int = 256, niter: int = 1000, n_params: int = 8, **kw) -> BGPConfig:
+    """C2/C3: MvNormal SMM with 2P moments (P means + P variances), S = 10 000 draws per evaluation."""
+    P = n_params
+    base_means = [-1.0, 1.0, 0.5, -0.5, 0.7, -0.7, 0.3, -0.3]
+    means = [base_means[k % 8] for k in range(P)]
+    temps = temperature_ladder(n_chains, 5.0)
+    tuners = np.geomspace(20.0, 1.0, n_chains) if n_chains > 1 else np.array([20.0])
+    args = dict(
+        lb=[-3.0] * P, ub=[3.0] * P, init=[0.2 * (-1.0) ** (k + 1) for k in range(P)],
+        data_mom=means + [1.0] * P, data_w=[1.0] * (2 * P),
+        n_chains=n_chains, max_iter=niter,
+        sigma0=0.05 * temps, acc_tuner=tuners, min_improve=[0.0] * n_chains,
+        objective_id=SMM_OBJ_NORM_MV, n_sim=10000, seed_sim=1234, seed_algo=20261017,
+    )
+    args.update(kw)
+    return BGPConfig(**args)
+
+
+def normal_means(n_chains: int = 256, niter: int = 1000, n_params: int = 8, **kw) -> BGPConfig:
+    """`objfunc_norm` itself (P == M, means only) at the C2 chain count, for a like-for-like."""
+    cfg = mvnormal(n_chains, niter, n_params, **kw)
+    P = n_params
+    cfg.data_mom = list(cfg.data_mom[:P])
+    cfg.data_w = [1.0] * P
+    cfg.objective_id = kw.get("objective_id", SMM_OBJ_NORM)
+    return cfg
+
+
+def slow_normal(n_chains: int = 64, niter: int = 2000, slow_seconds: float = 0.1, **kw) -> BGPConfig:
+    """C5: `objfunc_norm_slow` (C1's problem + slow_seconds per evaluation) on n_chains chains."""
+    temps = temperature_ladder(n_chains, 5.0)
+    args = dict(
+        lb=[-3.0, -20.0], ub=[3.0, 20.0], init=[0.2, -0.2],
+        data_mom=[-1.0, 10.0], data_w=[1.0, 1.0],
+        n_chains=n_chains, max_iter=niter,
+        sigma0=0.05 * temps, acc_tuner=np.geomspace(20.0, 1.0, n_chains), min_improve=[0.0] * n_chains,
+        objective_id=SMM_OBJ_NORM_SLOW, slow_seconds=slow_seconds, n_sim=10000, seed_sim=1234, seed_algo=12,
+    )
+    args.update(kw)
+    return BGPConfig(**args)

@@ -1,0 +1,641 @@
+// smm_api.cu -- C ABI of libsmm_b200.so (include/smm_b200.h): handle management, the iteration
+// loop of run! (AlgoAbstract.jl:27-76) as a stream of kernel launches, NCCL plumbing, host copies.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "smm_device.cuh"
+
+namespace smm {
+// launchers defined in smm_kernels.cu
+size_t pairs_smem_bytes(int N, int n_s);
+size_t exch_smem_bytes(int N);
+cudaError_t configure_kernels(int N, int n_s);
+int eval_max_blocks_per_sm();
+void launch_eval(const DevProblem &pb, const DevState &st, int iter, int n_split, int part_len, cudaStream_t s);
+void launch_pairs(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int n_s, cudaStream_t s);
+void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sched_idx, int n_s, cudaStream_t s);
+void launch_objective(const DevProblem &pb, const double *params, int B, int noseed, uint32_t rep0, int n_split,
+                      int part_len, double *partials, unsigned *arrive, double *value, double *moments, int *status,
+                      cudaStream_t s);
+void launch_debug_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, double *out,
+                          cudaStream_t s);
+void launch_rng_throughput(long long n_per_thread, int blocks, double *out, cudaStream_t s);
+}  // namespace smm
+
+using namespace smm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(SMM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+  } while (0)
+
+#define NCCL_TRY(expr)                                                                          \
+  do {                                                                                          \
+    ncclResult_t r__ = (expr);                                                                  \
+    if (r__ != ncclSuccess)                                                                     \
+      return fail(SMM_E_NCCL, std::string(#expr) + ": " + ncclGetErrorString(r__));             \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    n = count;
+    return cudaMalloc((void **)&p, sizeof(T) * (count ? count : 1));
+  }
+  void free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+};
+
+}  // namespace
+
+struct smm_bgp {
+  int device = 0;
+  int P = 0, M = 0, N = 0, L = 0, chain0 = 0, R = 0, max_iter = 0, world = 1, rank = 0;
+  int n_s = 0;       // pairs per iteration
+  int n_split = 1, part_len = 0;
+  int iter = 0;      // iterations completed (algo.i)
+  int sched_iter0 = -1, sched_n = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ncclComm_t comm = nullptr;
+  DevProblem pb{};
+  DevState st{};
+  smm_counters ctr{};
+  // owned device memory
+  DevBuf<double> lb, ub, init, data, w, acc_tuner, min_improve;
+  DevBuf<double> sigma, accept_rate, la_cur, la_pub, la_all;
+  DevBuf<int> n_noex, n_acc;
+  DevBuf<double> t_value, t_prob, t_curr, t_best, t_params, t_mom;
+  DevBuf<uint8_t> t_acc;
+  DevBuf<int> t_status, t_exch, t_bestid;
+  DevBuf<double> partials;
+  DevBuf<unsigned> arrive;
+  DevBuf<int> sched_ij, sched_off, sched_nlev, err;
+  DevBuf<unsigned long long> counters;
+
+  void release() {
+    if (comm) ncclCommDestroy(comm);
+    comm = nullptr;
+    lb.free(); ub.free(); init.free(); data.free(); w.free(); acc_tuner.free(); min_improve.free();
+    sigma.free(); accept_rate.free(); la_cur.free(); la_pub.free(); la_all.free();
+    n_noex.free(); n_acc.free();
+    t_value.free(); t_prob.free(); t_curr.free(); t_best.free(); t_params.free(); t_mom.free();
+    t_acc.free(); t_status.free(); t_exch.free(); t_bestid.free();
+    partials.free(); arrive.free(); sched_ij.free(); sched_off.free(); sched_nlev.free(); err.free();
+    counters.free();
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+    ev0 = ev1 = nullptr;
+    stream = nullptr;
+  }
+};
+
+namespace {
+
+int check_config(const smm_bgp_config *cfg) {
+  if (!cfg) return fail(SMM_E_ARG, "null config");
+  if (cfg->abi_version != SMM_ABI_VERSION) return fail(SMM_E_ARG, "abi_version mismatch");
+  if (cfg->n_params < 1 || cfg->n_params > SMM_MAX_PARAMS) return fail(SMM_E_ARG, "n_params out of range");
+  if (cfg->n_moments < 1 || cfg->n_moments > SMM_MAX_MOMENTS) return fail(SMM_E_ARG, "n_moments out of range");
+  if (cfg->n_chains < 1 || cfg->max_iter < 1) return fail(SMM_E_ARG, "n_chains / max_iter must be positive");
+  if (cfg->max_iter > (int)SMM_ITER_MASK) return fail(SMM_E_ARG, "max_iter exceeds the 28-bit iteration index");
+  if (!cfg->lb || !cfg->ub || !cfg->init || !cfg->data_mom || !cfg->data_w || !cfg->sigma0 || !cfg->acc_tuner ||
+      !cfg->min_improve)
+    return fail(SMM_E_ARG, "null array in config");
+  if (cfg->batch_size < 1 || cfg->n_params % cfg->batch_size != 0)
+    return fail(SMM_E_UNSUPPORTED_SHAPE,
+                "batch_size must divide n_params (upstream's batches are ill-formed otherwise, AlgoBGP.jl:95-103)");
+  const int P = cfg->n_params, M = cfg->n_moments;
+  switch (cfg->objective_id) {
+    case SMM_OBJ_NORM:
+    case SMM_OBJ_NORM_SLOW:
+      if (P != M)
+        return fail(SMM_E_UNSUPPORTED_SHAPE, "objfunc_norm needs n_params == n_moments (ObjExamples.jl:77-78)");
+      break;
+    case SMM_OBJ_NORM_MV:
+      if (M != 2 * P) return fail(SMM_E_UNSUPPORTED_SHAPE, "norm_mv needs n_moments == 2*n_params");
+      break;
+    case SMM_OBJ_PANEL:
+      return fail(SMM_E_UNSUPPORTED_SHAPE, "panel objective not built yet");
+    case SMM_OBJ_FAILS:
+      break;
+    default:
+      return fail(SMM_E_ARG, "unknown objective_id");
+  }
+  if (cfg->n_sim < 2) return fail(SMM_E_ARG, "n_sim must be >= 2");
+  if (cfg->sigma_update_steps < 1) return fail(SMM_E_ARG, "sigma_update_steps must be >= 1");
+  if (cfg->smpl_iters < 1) return fail(SMM_E_ARG, "smpl_iters must be >= 1");
+  for (int k = 0; k < P; ++k)
+    if (!(cfg->ub[k] > cfg->lb[k])) return fail(SMM_E_ARG, "need ub > lb (mprob.jl:82)");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+    return fail(SMM_E_ARG, "bad rank / world_size");
+  if (cfg->n_chains % cfg->world_size != 0)
+    return fail(SMM_E_UNSUPPORTED_SHAPE, "n_chains must be a multiple of world_size");
+  if (cfg->n_chains > 8192) return fail(SMM_E_UNSUPPORTED_SHAPE, "n_chains > 8192 not supported");
+  return 0;
+}
+
+template <typename T>
+int upload(DevBuf<T> &buf, const T *src, size_t n) {
+  CUDA_TRY(buf.alloc(n));
+  CUDA_TRY(cudaMemcpy(buf.p, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+template <typename T>
+int fill(DevBuf<T> &buf, size_t n, T v) {
+  CUDA_TRY(buf.alloc(n));
+  std::vector<T> h(n, v);
+  CUDA_TRY(cudaMemcpy(buf.p, h.data(), sizeof(T) * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int choose_split(int L, int n_sm, int blocks_per_sm, int n_blocks_philox, int requested) {
+  if (requested > 0) return requested > kMaxSplit ? kMaxSplit : requested;
+  // one wave: L * n_split CTAs <= resident capacity, as even as possible over the SMs
+  const int cap = n_sm * (blocks_per_sm > 0 ? blocks_per_sm : 1);
+  int best = 1;
+  double best_score = -1.0;
+  for (int s = 1; s <= kMaxSplit; ++s) {
+    if ((long long)L * s > cap && s > 1) break;
+    if (n_blocks_philox / s < 8) break;
+    const double per_sm = (double)L * s / n_sm;
+    const double balance = per_sm / std::ceil(per_sm);  // tail efficiency of the busiest SM
+    const double score = balance + 1e-3 * s;            // prefer finer splits on ties
+    if (score > best_score) {
+      best_score = score;
+      best = s;
+    }
+  }
+  return best;
+}
+
+int device_error_to_rc(int flags) {
+  if (flags & kErrNegative)
+    return fail(SMM_E_NEGATIVE_OBJECTIVE,
+                "AlgoBGP assumes that your objective function returns a non-negative number (AlgoBGP.jl:341)");
+  if (flags & kErrExhausted)
+    return fail(SMM_E_SAMPLER_EXHAUSTED, "no draw in support after smpl_iters trials (AlgoBGP.jl:409)");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smm_abi_version(void) { return SMM_ABI_VERSION; }
+
+const char *smm_last_error(void) { return g_err.c_str(); }
+
+int smm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int smm_nccl_unique_id(uint8_t out[SMM_NCCL_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) <= SMM_NCCL_ID_BYTES, "ncclUniqueId does not fit");
+  if (!out) return fail(SMM_E_ARG, "null output");
+  ncclUniqueId id;
+  NCCL_TRY(ncclGetUniqueId(&id));
+  memset(out, 0, SMM_NCCL_ID_BYTES);
+  memcpy(out, &id, sizeof id);
+  return 0;
+}
+
+void smm_bgp_destroy(smm_bgp *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  h->release();
+  delete h;
+}
+
+int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
+  if (!out) return fail(SMM_E_ARG, "null output handle");
+  *out = nullptr;
+  if (int rc = check_config(cfg)) return rc;
+  if (smm_device_count() <= cfg->device || cfg->device < 0)
+    return fail(SMM_E_CUDA, "no such CUDA device (this library has no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  smm_bgp *h = new smm_bgp();
+  struct Guard {
+    smm_bgp *h;
+    bool ok = false;
+    ~Guard() {
+      if (!ok) {
+        h->release();
+        delete h;
+      }
+    }
+  } guard{h};
+  h->device = cfg->device;
+  h->P = cfg->n_params;
+  h->M = cfg->n_moments;
+  h->N = cfg->n_chains;
+  h->world = cfg->world_size;
+  h->rank = cfg->rank;
+  h->L = h->N / h->world;
+  h->chain0 = h->rank * h->L;
+  h->R = rec_len(h->P, h->M);
+  h->max_iter = cfg->max_iter;
+  h->n_s = h->N < 3 ? h->N - 1 : h->N;
+  const int P = h->P, M = h->M, N = h->N, L = h->L, R = h->R, I = h->max_iter;
+
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&h->ev0));
+  CUDA_TRY(cudaEventCreate(&h->ev1));
+
+  if (int rc = upload(h->lb, cfg->lb, P)) return rc;
+  if (int rc = upload(h->ub, cfg->ub, P)) return rc;
+  if (int rc = upload(h->init, cfg->init, P)) return rc;
+  if (int rc = upload(h->data, cfg->data_mom, M)) return rc;
+  if (int rc = upload(h->w, cfg->data_w, M)) return rc;
+  if (int rc = upload(h->acc_tuner, cfg->acc_tuner, N)) return rc;
+  if (int rc = upload(h->min_improve, cfg->min_improve, N)) return rc;
+  if (int rc = upload(h->sigma, cfg->sigma0 + h->chain0, L)) return rc;
+  if (int rc = fill(h->accept_rate, (size_t)L, 0.0)) return rc;
+  if (int rc = fill(h->n_noex, (size_t)L, 0)) return rc;
+  if (int rc = fill(h->n_acc, (size_t)L, 0)) return rc;
+  const double nan = std::numeric_limits<double>::quiet_NaN(), inf = std::numeric_limits<double>::infinity();
+  if (int rc = fill(h->la_cur, (size_t)L * R, nan)) return rc;
+  if (int rc = fill(h->la_pub, (size_t)L * R, nan)) return rc;
+  if (h->world > 1) {
+    if (int rc = fill(h->la_all, (size_t)N * R, nan)) return rc;
+  }
+  // trace: unrun slots look like a fresh BGPChain (AlgoBGP.jl:81-89); Eval slots are `undef` -> NaN
+  const size_t IL = (size_t)I * L;
+  if (int rc = fill(h->t_value, IL, nan)) return rc;
+  if (int rc = fill(h->t_prob, IL, nan)) return rc;
+  if (int rc = fill(h->t_curr, IL, inf)) return rc;
+  if (int rc = fill(h->t_best, IL, inf)) return rc;
+  if (int rc = fill(h->t_params, IL * P, nan)) return rc;
+  if (int rc = fill(h->t_mom, IL * M, nan)) return rc;
+  if (int rc = fill(h->t_acc, IL, (uint8_t)0)) return rc;
+  if (int rc = fill(h->t_status, IL, 0)) return rc;
+  if (int rc = fill(h->t_exch, IL, 0)) return rc;
+  if (int rc = fill(h->t_bestid, IL, -1)) return rc;
+
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  h->part_len = 2 * P;
+  const int n_blocks_philox = (cfg->n_sim + 1) / 2;
+  h->n_split = choose_split(L, prop.multiProcessorCount, eval_max_blocks_per_sm(), n_blocks_philox, cfg->n_split);
+  if (cfg->objective_id == SMM_OBJ_FAILS) h->n_split = 1;
+  if (int rc = fill(h->partials, (size_t)L * h->n_split * h->part_len, 0.0)) return rc;
+  if (int rc = fill(h->arrive, (size_t)L, 0u)) return rc;
+  if (h->N > 1) {
+    if (int rc = fill(h->sched_ij, (size_t)kPairChunk * h->n_s * 2, 0)) return rc;
+    if (int rc = fill(h->sched_off, (size_t)kPairChunk * (h->n_s + 1), 0)) return rc;
+    if (int rc = fill(h->sched_nlev, (size_t)kPairChunk, 0)) return rc;
+    CUDA_TRY(configure_kernels(N, h->n_s));
+  }
+  if (int rc = fill(h->err, 1, 0)) return rc;
+  if (int rc = fill(h->counters, 4, 0ull)) return rc;
+
+  DevProblem &pb = h->pb;
+  pb.P = P; pb.M = M; pb.S = cfg->n_sim; pb.obj = cfg->objective_id; pb.noseed = cfg->noseed;
+  pb.N = N; pb.L = L; pb.chain0 = h->chain0; pb.max_iter = I; pb.world = h->world;
+  pb.sigma_update_steps = cfg->sigma_update_steps; pb.smpl_iters = cfg->smpl_iters; pb.batch_size = cfg->batch_size;
+  pb.panel_T = cfg->panel_T; pb.panel_N = cfg->panel_N; pb.panel_K = cfg->panel_K;
+  pb.sigma_adjust_by = cfg->sigma_adjust_by; pb.slow_seconds = cfg->slow_seconds;
+  pb.seed_sim = cfg->seed_sim; pb.seed_algo = cfg->seed_algo;
+  pb.lb = h->lb.p; pb.ub = h->ub.p; pb.init = h->init.p; pb.data = h->data.p; pb.w = h->w.p;
+  pb.acc_tuner = h->acc_tuner.p; pb.min_improve = h->min_improve.p;
+
+  DevState &st = h->st;
+  st.sigma = h->sigma.p; st.accept_rate = h->accept_rate.p; st.n_noex = h->n_noex.p; st.n_acc = h->n_acc.p;
+  st.la_cur = h->la_cur.p; st.la_pub = h->la_pub.p; st.la_all = h->world > 1 ? h->la_all.p : h->la_pub.p;
+  st.t_value = h->t_value.p; st.t_prob = h->t_prob.p; st.t_curr = h->t_curr.p; st.t_best = h->t_best.p;
+  st.t_params = h->t_params.p; st.t_mom = h->t_mom.p; st.t_acc = h->t_acc.p; st.t_status = h->t_status.p;
+  st.t_exch = h->t_exch.p; st.t_bestid = h->t_bestid.p;
+  st.partials = h->partials.p; st.arrive = h->arrive.p;
+  st.sched_ij = h->sched_ij.p; st.sched_off = h->sched_off.p; st.sched_nlev = h->sched_nlev.p;
+  st.err = h->err.p; st.counters = h->counters.p;
+
+  if (h->world > 1) {
+    ncclUniqueId id;
+    memcpy(&id, cfg->nccl_id, sizeof id);
+    NCCL_TRY(ncclCommInitRank(&h->comm, h->world, id, h->rank));
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  guard.ok = true;
+  *out = h;
+  return 0;
+}
+
+int smm_bgp_iteration(const smm_bgp *h) { return h ? h->iter : -1; }
+int smm_bgp_local_chains(const smm_bgp *h) { return h ? h->L : -1; }
+void *smm_bgp_stream(smm_bgp *h) { return h ? (void *)h->stream : nullptr; }
+
+int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
+  if (!h) return fail(SMM_E_ARG, "null handle");
+  if (n_iters < 0 || h->iter + n_iters > h->max_iter)
+    return fail(SMM_E_ARG, "step would exceed max_iter (use restart!/extend to grow the chains)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaEventRecord(h->ev0, s));
+  const bool exchange = h->N > 1;
+  for (int k = 0; k < n_iters; ++k) {
+    const int it = h->iter + 1;
+    if (exchange && it >= 2 && (h->sched_iter0 < 0 || it >= h->sched_iter0 + h->sched_n)) {
+      // precompute Pairs[it .. it+chunk) and their level schedules
+      int n = h->max_iter - it + 1;
+      if (n > kPairChunk) n = kPairChunk;
+      launch_pairs(h->pb, h->st, it, n, h->n_s, s);
+      h->sched_iter0 = it;
+      h->sched_n = n;
+      h->ctr.kernel_launches++;
+    }
+    launch_eval(h->pb, h->st, it, h->n_split, h->part_len, s);
+    h->ctr.kernel_launches++;
+    if (exchange && it >= 2) {  // AlgoBGP.jl:637
+      if (h->world > 1) {
+        NCCL_TRY(ncclAllGather(h->st.la_pub, h->st.la_all, (size_t)h->L * h->R, ncclDouble, h->comm, s));
+        h->ctr.collectives++;
+      }
+      launch_exchange(h->pb, h->st, it, it - h->sched_iter0, h->n_s, s);
+      h->ctr.kernel_launches++;
+    }
+    h->iter = it;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev1, s));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  h->ctr.iterations = h->iter;
+  h->ctr.evaluations = (int64_t)h->iter * h->L;
+  int flags = 0;
+  CUDA_TRY(cudaMemcpy(&flags, h->st.err, sizeof flags, cudaMemcpyDeviceToHost));
+  return device_error_to_rc(flags);
+}
+
+int smm_bgp_read_trace(smm_bgp *h, int32_t iter_lo, int32_t iter_hi, const smm_trace_view *out) {
+  if (!h || !out) return fail(SMM_E_ARG, "null argument");
+  if (iter_lo < 1 || iter_hi < iter_lo || iter_hi > h->max_iter) return fail(SMM_E_ARG, "bad iteration range");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t L = h->L, off = (size_t)(iter_lo - 1) * L, n = (size_t)(iter_hi - iter_lo + 1) * L;
+  cudaStream_t s = h->stream;
+#define COPY(dst, src, T, mult)                                                                              \
+  if (out->dst)                                                                                              \
+    CUDA_TRY(cudaMemcpyAsync(out->dst, h->st.src + off * (mult), sizeof(T) * n * (mult), cudaMemcpyDeviceToHost, s))
+  COPY(value, t_value, double, 1);
+  COPY(prob, t_prob, double, 1);
+  COPY(curr_val, t_curr, double, 1);
+  COPY(best_val, t_best, double, 1);
+  COPY(params, t_params, double, (size_t)h->P);
+  COPY(sim_moments, t_mom, double, (size_t)h->M);
+  COPY(accepted, t_acc, uint8_t, 1);
+  COPY(status, t_status, int32_t, 1);
+  COPY(exchanged, t_exch, int32_t, 1);
+  COPY(best_id, t_bestid, int32_t, 1);
+#undef COPY
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int smm_bgp_read_chain_state(smm_bgp *h, double *sigma, double *accept_rate) {
+  if (!h) return fail(SMM_E_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (sigma) CUDA_TRY(cudaMemcpy(sigma, h->st.sigma, sizeof(double) * h->L, cudaMemcpyDeviceToHost));
+  if (accept_rate)
+    CUDA_TRY(cudaMemcpy(accept_rate, h->st.accept_rate, sizeof(double) * h->L, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int smm_bgp_get_counters(smm_bgp *h, smm_counters *out) {
+  if (!h || !out) return fail(SMM_E_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  unsigned long long c[4];
+  CUDA_TRY(cudaMemcpy(c, h->st.counters, sizeof c, cudaMemcpyDeviceToHost));
+  h->ctr.accepted = (int64_t)c[0];
+  h->ctr.swaps = (int64_t)c[1];
+  h->ctr.proposal_attempts = (int64_t)c[2];
+  *out = h->ctr;
+  return 0;
+}
+
+int smm_bgp_eval_batch(smm_bgp *h, const double *params, int32_t B, int32_t noseed, uint32_t rep0, double *value,
+                       double *moments, int32_t *status) {
+  if (!h || !params) return fail(SMM_E_ARG, "null argument");
+  if (B < 1) return fail(SMM_E_ARG, "B must be positive");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int P = h->P, M = h->M;
+  int n_split = h->n_split;
+  DevBuf<double> d_params, d_value, d_mom, d_part;
+  DevBuf<int> d_status;
+  DevBuf<unsigned> d_arrive;
+  struct Free {
+    DevBuf<double> &a, &b, &c, &d;
+    DevBuf<int> &e;
+    DevBuf<unsigned> &f;
+    ~Free() { a.free(); b.free(); c.free(); d.free(); e.free(); f.free(); }
+  } fr{d_params, d_value, d_mom, d_part, d_status, d_arrive};
+  CUDA_TRY(d_params.alloc((size_t)B * P));
+  CUDA_TRY(d_value.alloc(B));
+  CUDA_TRY(d_mom.alloc((size_t)B * M));
+  CUDA_TRY(d_part.alloc((size_t)B * n_split * h->part_len));
+  CUDA_TRY(d_status.alloc(B));
+  CUDA_TRY(d_arrive.alloc(B));
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaMemcpyAsync(d_params.p, params, sizeof(double) * B * P, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(d_arrive.p, 0, sizeof(unsigned) * B, s));
+  // grid.y is limited to 65535
+  for (int b0 = 0; b0 < B; b0 += 32768) {
+    const int nb = (B - b0) < 32768 ? (B - b0) : 32768;
+    launch_objective(h->pb, d_params.p + (size_t)b0 * P, nb, noseed, rep0 + (uint32_t)b0, n_split, h->part_len,
+                     d_part.p + (size_t)b0 * n_split * h->part_len, d_arrive.p + b0, d_value.p + b0,
+                     d_mom.p + (size_t)b0 * M, d_status.p + b0, s);
+    h->ctr.kernel_launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (value) CUDA_TRY(cudaMemcpyAsync(value, d_value.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+  if (moments) CUDA_TRY(cudaMemcpyAsync(moments, d_mom.p, sizeof(double) * B * M, cudaMemcpyDeviceToHost, s));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, d_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ---- checkpoint ----------------------------------------------------------------------------------
+// layout: header {magic, P, M, L, R, iter} (6 x int64) | sigma[L] accept_rate[L] | n_noex[L] n_acc[L] (int32)
+//         | la_cur[L][R] | trace rows 1..iter of every column
+namespace {
+struct StateHeader {
+  int64_t magic, P, M, L, R, iter;
+};
+const int64_t kMagic = 0x534d4d4232303031ll;  // "SMMB2001"
+}  // namespace
+
+int64_t smm_bgp_state_bytes(const smm_bgp *h) {
+  if (!h) return -1;
+  const int64_t L = h->L, R = h->R, it = h->iter, P = h->P, M = h->M;
+  return (int64_t)sizeof(StateHeader) + 8 * 2 * L + 4 * 2 * L + 8 * L * R + it * L * (8 * (4 + P + M) + 1 + 4 * 3);
+}
+
+int smm_bgp_export_state(smm_bgp *h, void *buf, int64_t nbytes) {
+  if (!h || !buf) return fail(SMM_E_ARG, "null argument");
+  if (nbytes < smm_bgp_state_bytes(h)) return fail(SMM_E_ARG, "buffer too small");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  char *p = (char *)buf;
+  StateHeader hd{kMagic, h->P, h->M, h->L, h->R, h->iter};
+  memcpy(p, &hd, sizeof hd);
+  p += sizeof hd;
+  const size_t L = h->L, n = (size_t)h->iter * L;
+#define OUT(src, T, count)                                                               \
+  do {                                                                                   \
+    CUDA_TRY(cudaMemcpy(p, src, sizeof(T) * (count), cudaMemcpyDeviceToHost));           \
+    p += sizeof(T) * (count);                                                            \
+  } while (0)
+  OUT(h->st.sigma, double, L);
+  OUT(h->st.accept_rate, double, L);
+  OUT(h->st.n_noex, int, L);
+  OUT(h->st.n_acc, int, L);
+  OUT(h->st.la_cur, double, L * h->R);
+  OUT(h->st.t_value, double, n);
+  OUT(h->st.t_prob, double, n);
+  OUT(h->st.t_curr, double, n);
+  OUT(h->st.t_best, double, n);
+  OUT(h->st.t_params, double, n * h->P);
+  OUT(h->st.t_mom, double, n * h->M);
+  OUT(h->st.t_acc, uint8_t, n);
+  OUT(h->st.t_status, int, n);
+  OUT(h->st.t_exch, int, n);
+  OUT(h->st.t_bestid, int, n);
+#undef OUT
+  return 0;
+}
+
+int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes) {
+  if (!h || !buf) return fail(SMM_E_ARG, "null argument");
+  if (nbytes < (int64_t)sizeof(StateHeader)) return fail(SMM_E_ARG, "buffer too small");
+  const char *p = (const char *)buf;
+  StateHeader hd;
+  memcpy(&hd, p, sizeof hd);
+  p += sizeof hd;
+  if (hd.magic != kMagic || hd.P != h->P || hd.M != h->M || hd.L != h->L || hd.R != h->R)
+    return fail(SMM_E_STATE, "checkpoint does not match this handle's shape");
+  if (hd.iter < 0 || hd.iter > h->max_iter) return fail(SMM_E_STATE, "checkpoint has more iterations than max_iter");
+  const size_t L = h->L, n = (size_t)hd.iter * L;
+  const int64_t need = (int64_t)sizeof(StateHeader) + 8 * 2 * (int64_t)L + 4 * 2 * (int64_t)L + 8 * (int64_t)L * h->R +
+                       (int64_t)n * (8 * (4 + h->P + h->M) + 1 + 4 * 3);
+  if (nbytes < need) return fail(SMM_E_ARG, "truncated checkpoint");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+#define IN(dst, T, count)                                                                \
+  do {                                                                                   \
+    CUDA_TRY(cudaMemcpy(dst, p, sizeof(T) * (count), cudaMemcpyHostToDevice));           \
+    p += sizeof(T) * (count);                                                            \
+  } while (0)
+  IN(h->st.sigma, double, L);
+  IN(h->st.accept_rate, double, L);
+  IN(h->st.n_noex, int, L);
+  IN(h->st.n_acc, int, L);
+  IN(h->st.la_cur, double, L * h->R);
+  IN(h->st.t_value, double, n);
+  IN(h->st.t_prob, double, n);
+  IN(h->st.t_curr, double, n);
+  IN(h->st.t_best, double, n);
+  IN(h->st.t_params, double, n * h->P);
+  IN(h->st.t_mom, double, n * h->M);
+  IN(h->st.t_acc, uint8_t, n);
+  IN(h->st.t_status, int, n);
+  IN(h->st.t_exch, int, n);
+  IN(h->st.t_bestid, int, n);
+#undef IN
+  h->iter = (int)hd.iter;
+  h->sched_iter0 = -1;
+  h->sched_n = 0;
+  return 0;
+}
+
+// ---- diagnostics ---------------------------------------------------------------------------------
+int smm_debug_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_pairs,
+                      double *out) {
+  if (!out || n_pairs < 1) return fail(SMM_E_ARG, "bad argument");
+  if (smm_device_count() <= device) return fail(SMM_E_CUDA, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  DevBuf<double> d;
+  CUDA_TRY(d.alloc((size_t)2 * n_pairs));
+  launch_debug_normals(seed, k, c2, c3, n_pairs, d.p, 0);
+  cudaError_t e = cudaMemcpy(out, d.p, sizeof(double) * 2 * n_pairs, cudaMemcpyDeviceToHost);
+  d.free();
+  CUDA_TRY(e);
+  return 0;
+}
+
+int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij, int32_t *level_offsets, int32_t *n_levels) {
+  if (!h || !ij || !level_offsets || !n_levels) return fail(SMM_E_ARG, "null argument");
+  if (h->N < 2) return fail(SMM_E_ARG, "no exchange with a single chain");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  launch_pairs(h->pb, h->st, iter, 1, h->n_s, h->stream);
+  h->sched_iter0 = -1;  // the cached schedule was overwritten
+  h->sched_n = 0;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(ij, h->st.sched_ij, sizeof(int) * 2 * h->n_s, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(level_offsets, h->st.sched_off, sizeof(int) * (h->n_s + 1), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(n_levels, h->st.sched_nlev, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int smm_debug_rng_throughput(int32_t device, int64_t n_pairs_per_thread, int32_t blocks, int32_t threads,
+                             float *elapsed_ms, double *checksum) {
+  (void)threads;
+  if (smm_device_count() <= device) return fail(SMM_E_CUDA, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  DevBuf<double> d;
+  const size_t n = (size_t)blocks * kEvalThreads * 2;
+  CUDA_TRY(d.alloc(n));
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  launch_rng_throughput(n_pairs_per_thread, blocks, d.p, 0);  // warm-up
+  CUDA_TRY(cudaEventRecord(a, 0));
+  launch_rng_throughput(n_pairs_per_thread, blocks, d.p, 0);
+  CUDA_TRY(cudaEventRecord(b, 0));
+  CUDA_TRY(cudaEventSynchronize(b));
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, a, b));
+  std::vector<double> hbuf(n);
+  cudaError_t e = cudaMemcpy(hbuf.data(), d.p, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  d.free();
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  CUDA_TRY(e);
+  if (checksum) {
+    double cs = 0.0;
+    for (double v : hbuf) cs += v;
+    *checksum = cs;
+  }
+  return 0;
+}
+
+}  // extern "C"
