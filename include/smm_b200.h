@@ -157,6 +157,16 @@ int64_t smm_bgp_state_bytes(const smm_bgp *h);
 int smm_bgp_export_state(smm_bgp *h, void *buf, int64_t nbytes);
 int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes);
 
+/* BGPChain.probs_acc[iter_lo..iter_hi] of a chain (0-based global id): the Uacc stream evaluated on the
+ * host (a pure function of the seed; replaces `rand(n)` at AlgoBGP.jl:85).  out[iter_hi-iter_lo+1]. */
+int smm_stream_acc_uniforms(uint64_t seed_algo, uint32_t chain, int32_t iter_lo, int32_t iter_hi, double *out);
+
+/* per-kernel device timing: when enabled, smm_bgp_step brackets every launch with CUDA events on the
+ * library's stream and accumulates the elapsed time per kernel kind (slows the step; off by default).
+ * kinds: 0 = evaluation kernel, 1 = exchange kernel, 2 = pair-schedule kernel, 3 = all-gather. */
+int smm_bgp_set_profiling(smm_bgp *h, int32_t enabled);
+int smm_bgp_kernel_times(smm_bgp *h, double ms_sum[4], int64_t launches[4]);
+
 /* test/diagnostic entry points (device implementations of the stream definitions) */
 int smm_debug_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_pairs,
                       double *out /* [2*n_pairs] */);

@@ -128,14 +128,30 @@ SMM_HD double smm_u01(uint32_t a, uint32_t b) {
   return SMM_SUB(smm_bits_to_double(0x3FF0000000000000ull | smm_mant52(a, b)), 1.0);
 }
 
-/* ---- log table ---------------------------------------------------------------------------- */
+/* ---- constants: host arrays, and on the device the constant bank (so that DFMA takes the
+ * coefficient as a c[bank][offset] operand instead of materialising it in registers) ------------- */
 typedef struct smm_logent {
-  double inv, lnc;
+  double inv, nlnc;
 } smm_logent;
 
 static const smm_logent SMM_LOGTAB_HOST[1 << SMM_LOG_BITS] = SMM_LOG_TABLE;
+static const double SMM_SIN_HOST[SMM_SIN_DEG + 1] = SMM_SIN_COEFS;
+static const double SMM_COS_HOST[SMM_COS_DEG + 1] = SMM_COS_COEFS;
+static const double SMM_LOGQ_HOST[SMM_LOGQ_DEG + 1] = SMM_LOGQ_COEFS;
 #if defined(__CUDACC__)
 static __device__ const smm_logent SMM_LOGTAB_DEV[1 << SMM_LOG_BITS] = SMM_LOG_TABLE;
+static __constant__ double SMM_SIN_DEV[SMM_SIN_DEG + 1] = SMM_SIN_COEFS;
+static __constant__ double SMM_COS_DEV[SMM_COS_DEG + 1] = SMM_COS_COEFS;
+static __constant__ double SMM_LOGQ_DEV[SMM_LOGQ_DEG + 1] = SMM_LOGQ_COEFS;
+#endif
+#if defined(__CUDA_ARCH__)
+#define SMM_SIN_C(i) SMM_SIN_DEV[i]
+#define SMM_COS_C(i) SMM_COS_DEV[i]
+#define SMM_LOGQ_C(i) SMM_LOGQ_DEV[i]
+#else
+#define SMM_SIN_C(i) SMM_SIN_HOST[i]
+#define SMM_COS_C(i) SMM_COS_HOST[i]
+#define SMM_LOGQ_C(i) SMM_LOGQ_HOST[i]
 #endif
 
 SMM_HD const smm_logent *smm_logtab(void) {
@@ -146,67 +162,62 @@ SMM_HD const smm_logent *smm_logtab(void) {
 #endif
 }
 
-/* natural log of a normal, positive double u in (0,1]; abs error ~1e-16 (tests/test_stream.py) */
-SMM_HD double smm_log01(double u, const smm_logent *tab) {
+/* -log(u) of a normal double u in (0,1); abs error ~1e-16 (tests/test_stream.py).
+ * u = 2^e * m, m in [1,2); bucket j = top SMM_LOG_BITS bits of m; r = m*INV[j] - 1 (one fma);
+ * -log(u) = (e * -ln2 + NLNC[j]) + (r^2 * NQ(r) - r).  The end buckets have INV = 1 and 1/2 exactly,
+ * so the result is accurate to the last bits on both sides of u = 1. */
+SMM_HD double smm_neglog01(double u, const smm_logent *tab) {
   const uint64_t b = smm_double_to_bits(u);
-  const int e = (int)((b >> 52) & 0x7FFu) - 1023;
-  const uint32_t j = (uint32_t)(b >> (52 - SMM_LOG_BITS)) & ((1u << SMM_LOG_BITS) - 1u);
+  const uint32_t hi = (uint32_t)(b >> 32);
+  const int e = (int)((hi >> 20) & 0x7FFu) - 1023;
+  const uint32_t j = (hi >> (20 - SMM_LOG_BITS)) & ((1u << SMM_LOG_BITS) - 1u);
   const double m = smm_bits_to_double((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
   const smm_logent t = tab[j];
-  const double r = SMM_FMA(m, t.inv, -1.0); /* exact for the end buckets, |r| <= 2^-7 */
-  const double q[SMM_LOGQ_DEG + 1] = SMM_LOGQ_COEFS;
-  double p = q[SMM_LOGQ_DEG];
+  const double r = SMM_FMA(m, t.inv, -1.0);
+  double p = SMM_LOGQ_C(SMM_LOGQ_DEG);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = SMM_LOGQ_DEG - 1; i >= 0; --i) p = SMM_FMA(p, r, q[i]);
+  for (int i = SMM_LOGQ_DEG - 1; i >= 0; --i) p = SMM_FMA(p, r, SMM_LOGQ_C(i));
   const double r2 = SMM_MUL(r, r);
-  const double l1p = SMM_FMA(r2, p, r);                   /* log(1+r) */
-  const double base = SMM_FMA((double)e, SMM_LN2, t.lnc); /* e*ln2 + ln(c_j); 0 near u=1 */
-  return SMM_ADD(base, l1p);
+  const double nl1p = SMM_FMA(r2, p, -r);                     /* -log(1+r) */
+  const double base = SMM_FMA((double)e, SMM_NLN2, t.nlnc);   /* -(e ln2 + ln c_j); 0 near u = 1 */
+  return SMM_ADD(base, nl1p);
 }
 
-/* cos and sin of 2*pi*B/2^52 for a 52-bit integer B: octant from the top 3 bits, the remaining
- * 49 bits are the (exact) position inside the octant */
-SMM_HD void smm_sincos_turn52(uint64_t B, double *c_out, double *s_out) {
-  const uint32_t oct = (uint32_t)(B >> 49) & 7u;
-  const uint64_t rem = B & ((1ull << 49) - 1ull);
-  const double d = smm_bits_to_double(0x3FF0000000000000ull | (rem << 3)); /* 1 + f */
-  const double g = (oct & 1u) ? SMM_SUB(2.0, d) : SMM_SUB(d, 1.0);         /* f or 1-f, exact */
-  const double w = SMM_MUL(g, g);
-  const double cs[SMM_SIN_DEG + 1] = SMM_SIN_COEFS;
-  const double cc[SMM_COS_DEG + 1] = SMM_COS_COEFS;
-  double ps = cs[SMM_SIN_DEG];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = SMM_SIN_DEG - 1; i >= 0; --i) ps = SMM_FMA(ps, w, cs[i]);
-  double pc = cc[SMM_COS_DEG];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = SMM_COS_DEG - 1; i >= 0; --i) pc = SMM_FMA(pc, w, cc[i]);
-  const double sn = SMM_MUL(g, ps); /* sin(pi/4 * g) */
-  const double cn = pc;             /* cos(pi/4 * g) */
-  const int swap = ((oct + 1u) >> 1) & 1u;
-  double c = swap ? sn : cn;
-  double s = swap ? cn : sn;
-  if (((oct + 2u) >> 2) & 1u) c = -c;
-  if (oct >> 2) s = -s;
-  *c_out = c;
-  *s_out = s;
-}
-
-/* Box-Muller on one Philox block: words x,y -> radius uniform in (0,1], words z,w -> angle */
+/* Box-Muller on one Philox block r = (x, y, z, w):
+ *   A = 52 bits of (x, y) forced odd    -> u1 = 1 - A/2^52 in [2^-52, 1 - 2^-52]   (radius)
+ *   B = 52 bits of (z, w): low 49 bits  -> g in [0,1), first-octant angle (pi/4) g
+ *                          bits 49,50,51 -> a uniformly random symmetry of the octant tiling:
+ *                                           swap (x<->y), sign of z0, sign of z1
+ *   z0, z1 = sqrt(-log u1) * { sqrt2 cos, sqrt2 sin }((pi/4) g), swapped / negated as drawn.
+ * A uniform point of the first octant under a uniform element of the dihedral group is uniform on the
+ * circle, so (z0, z1) are independent standard normals. */
 SMM_HD void smm_normal_pair_tab(smm_u32x4 r, const smm_logent *tab, double *z0, double *z1) {
-  const double d1 = smm_bits_to_double(0x3FF0000000000000ull | smm_mant52(r.x, r.y));
-  const double u1 = SMM_SUB(2.0, d1); /* (0,1], exact */
-  const double l = smm_log01(u1, tab);
-  const double rad = SMM_SQRT(SMM_MUL(-2.0, l));
-  double c, s;
-  smm_sincos_turn52(smm_mant52(r.z, r.w), &c, &s);
-  *z0 = SMM_MUL(rad, c);
-  *z1 = SMM_MUL(rad, s);
+  const double d1 = smm_bits_to_double(0x3FF0000000000000ull | smm_mant52(r.x, r.y) | 1ull);
+  const double u1 = SMM_SUB(2.0, d1); /* exact */
+  const double rad = SMM_SQRT(smm_neglog01(u1, tab));
+  const uint64_t rem = smm_mant52(r.z, r.w) & ((1ull << 49) - 1ull);
+  const double g = SMM_SUB(smm_bits_to_double(0x3FF0000000000000ull | (rem << 3)), 1.0); /* exact */
+  const double w = SMM_MUL(g, g);
+  double ps = SMM_SIN_C(SMM_SIN_DEG);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = SMM_SIN_DEG - 1; i >= 0; --i) ps = SMM_FMA(ps, w, SMM_SIN_C(i));
+  double pc = SMM_COS_C(SMM_COS_DEG);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = SMM_COS_DEG - 1; i >= 0; --i) pc = SMM_FMA(pc, w, SMM_COS_C(i));
+  const double sn = SMM_MUL(g, ps);
+  const int swap = (r.z >> 29) & 1u;
+  uint64_t cb = smm_double_to_bits(swap ? sn : pc);
+  uint64_t sb = smm_double_to_bits(swap ? pc : sn);
+  cb ^= (uint64_t)((r.z << 1) & 0x80000000u) << 32; /* bit 30 of z -> sign of z0 */
+  sb ^= (uint64_t)(r.z & 0x80000000u) << 32;        /* bit 31 of z -> sign of z1 */
+  *z0 = SMM_MUL(rad, smm_bits_to_double(cb));
+  *z1 = SMM_MUL(rad, smm_bits_to_double(sb));
 }
 SMM_HD void smm_normal_pair(smm_u32x4 r, double *z0, double *z1) {
   smm_normal_pair_tab(r, smm_logtab(), z0, z1);

@@ -10,7 +10,7 @@ import subprocess
 
 import numpy as np
 
-from smm_jl_b200._abi import BGPConfig, Trace, smm_bgp_config, smm_trace_view, ERROR_NAMES
+from smm_jl_b200._abi import BGPConfig, Trace, smm_bgp_config, smm_trace_view, ERROR_NAMES  # interface only
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libsmm_oracle.so")
@@ -50,10 +50,8 @@ def lib():
     L.smm_oracle_normals.restype = None
     L.smm_oracle_normal_from_words.argtypes = [C.c_uint32] * 4 + [dp]
     L.smm_oracle_normal_from_words.restype = None
-    L.smm_oracle_log01.argtypes = [C.c_double]
-    L.smm_oracle_log01.restype = C.c_double
-    L.smm_oracle_sincos52.argtypes = [C.c_uint64, dp, dp]
-    L.smm_oracle_sincos52.restype = None
+    L.smm_oracle_neglog01.argtypes = [C.c_double]
+    L.smm_oracle_neglog01.restype = C.c_double
     L.smm_oracle_acc_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
     L.smm_oracle_acc_uniform.restype = C.c_double
     L.smm_oracle_pair_unrank.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -126,14 +124,8 @@ def normal_from_words(x, y, z, w):
     return out
 
 
-def log01(u: float) -> float:
-    return lib().smm_oracle_log01(u)
-
-
-def sincos52(B: int):
-    c, s = C.c_double(), C.c_double()
-    lib().smm_oracle_sincos52(B, C.byref(c), C.byref(s))
-    return c.value, s.value
+def neglog01(u: float) -> float:
+    return lib().smm_oracle_neglog01(u)
 
 
 def acc_uniform(seed, chain, it):

@@ -1,0 +1,177 @@
+"""Independent numpy/pure-Python re-derivation of the oracle -- TEST INFRASTRUCTURE.
+
+Purpose: pin oracle/smm_oracle.cpp (and the shared stream header it includes) against a second
+implementation that shares no code with it: Philox4x32-10 written in numpy integer arithmetic, the
+Box-Muller transform evaluated with libm (np.log / np.cos / np.sin, so it also checks the accuracy of the
+header's polynomial kernels), and the BGP algorithm written as plain Python loops following the same
+reference lines (AlgoBGP.jl:209-257, 272-471, 589-749; ObjExamples.jl:59-116; mprob.jl:246-272).
+Small cases only.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+M0, M1 = 0xD2511F53, 0xCD9E8D57
+W0, W1 = 0x9E3779B9, 0xBB67AE85
+MASK = 0xFFFFFFFF
+STREAM_SIM, STREAM_PROP, STREAM_ACC, STREAM_PAIR = 1, 2, 3, 4
+
+
+def philox(c0, c1, c2, c3, k0, k1):
+    """vectorised over numpy uint64 arrays holding 32-bit values"""
+    c0, c1, c2, c3 = [np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3)]
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    for _ in range(10):
+        p0 = np.uint64(M0) * c0
+        p1 = np.uint64(M1) * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & np.uint64(MASK)
+        hi1, lo1 = p1 >> np.uint64(32), p1 & np.uint64(MASK)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(W0)) & np.uint64(MASK)
+        k1 = (k1 + np.uint64(W1)) & np.uint64(MASK)
+    return c0, c1, c2, c3
+
+
+def normal_pairs(x, y, z, w):
+    """the transform of smm_stream.h, evaluated with libm in float64"""
+    x, y, z, w = [np.asarray(v, dtype=np.uint64) for v in (x, y, z, w)]
+    A = ((x << np.uint64(20)) | (y >> np.uint64(12))) | np.uint64(1)
+    u1 = (np.float64(2 ** 52) - A.astype(np.float64)) / np.float64(2 ** 52)
+    B = (z << np.uint64(20)) | (w >> np.uint64(12))
+    g = (B & np.uint64(2 ** 49 - 1)).astype(np.float64) / np.float64(2 ** 49)
+    rad = np.sqrt(-2.0 * np.log(u1))
+    c, s = np.cos(np.pi / 4 * g), np.sin(np.pi / 4 * g)
+    swap = ((z >> np.uint64(29)) & np.uint64(1)).astype(bool)
+    c, s = np.where(swap, s, c), np.where(swap, c, s)
+    c = np.where(((z >> np.uint64(30)) & np.uint64(1)).astype(bool), -c, c)
+    s = np.where(((z >> np.uint64(31)) & np.uint64(1)).astype(bool), -s, s)
+    return rad * c, rad * s
+
+
+def sim_normals(seed_sim, k, S, noseed=0, uid=0, rep=0):
+    nb = (S + 1) // 2
+    j = np.arange(nb, dtype=np.uint64)
+    c2 = uid if noseed else 0
+    c3 = (STREAM_SIM << 28) | ((rep & 0x0FFFFFFF) if noseed else 0)
+    r = philox(j, k, c2, c3, seed_sim & MASK, seed_sim >> 32)
+    z0, z1 = normal_pairs(*r)
+    return np.stack([z0, z1], axis=1).reshape(-1)[:S]
+
+
+def prop_normal(seed_algo, chain, it, attempt, k):
+    r = philox(attempt, k >> 1, chain, (STREAM_PROP << 28) | it, seed_algo & MASK, seed_algo >> 32)
+    z0, z1 = normal_pairs(*r)
+    return float(z1) if (k & 1) else float(z0)
+
+
+def acc_uniform(seed_algo, chain, it):
+    x, y, _, _ = philox(0, 0, chain, (STREAM_ACC << 28) | it, seed_algo & MASK, seed_algo >> 32)
+    return ((int(x) << 20) | (int(y) >> 12)) / 2.0 ** 52
+
+
+def pair_sample(seed_algo, it, N):
+    n_all = N * (N - 1) // 2
+    n_s = N - 1 if N < 3 else N
+    props = [(i, j) for j in range(N) for i in range(N) if i < j]   # i fastest (AlgoBGP.jl:653)
+    chosen = []
+    for t in range(n_s):
+        a = 0
+        while True:
+            x, y, _, _ = philox(t, a, 0, (STREAM_PAIR << 28) | it, seed_algo & MASK, seed_algo >> 32)
+            q = (((int(x) << 32) | int(y)) * n_all) >> 64
+            a += 1
+            if q not in chosen:
+                break
+        chosen.append(q)
+    return [props[q] for q in chosen]
+
+
+def objective(cfg, p, uid=0, rep=0, noseed=None):
+    """objfunc_norm / norm_mv with the draw matrix materialised (ObjExamples.jl:76-101)"""
+    P, M, S = cfg.n_params, cfg.n_moments, cfg.n_sim
+    noseed = cfg.noseed if noseed is None else noseed
+    X = np.stack([p[k] + sim_normals(cfg.seed_sim, k, S, noseed, uid, rep) for k in range(P)])
+    sim = X.mean(axis=1)
+    if M == 2 * P:
+        sim = np.concatenate([sim, X.var(axis=1, ddof=1)])
+    d = (sim - np.asarray(cfg.data_mom, float)) / np.asarray(cfg.data_w, float)
+    return float(np.mean(d * d)), sim
+
+
+def run(cfg, n_iters):
+    """run!(MAlgoBGP) as plain loops; returns dict of arrays shaped [n_iters][N](...)"""
+    N, P, M = cfg.n_chains, cfg.n_params, cfg.n_moments
+    lb, ub = np.asarray(cfg.lb, float), np.asarray(cfg.ub, float)
+    sigma = np.asarray(cfg.sigma0, float).copy()
+    tun, mi = np.asarray(cfg.acc_tuner, float), np.asarray(cfg.min_improve, float)
+    bs = cfg.batch_size or P
+    out = dict(value=np.zeros((n_iters, N)), prob=np.zeros((n_iters, N)), curr_val=np.zeros((n_iters, N)),
+               best_val=np.zeros((n_iters, N)), params=np.zeros((n_iters, N, P)), sim_moments=np.zeros((n_iters, N, M)),
+               accepted=np.zeros((n_iters, N), np.uint8), status=np.zeros((n_iters, N), np.int32),
+               exchanged=np.zeros((n_iters, N), np.int32), best_id=np.zeros((n_iters, N), np.int32))
+    evals = [[None] * n_iters for _ in range(N)]   # (value, prob, status, params, moments)
+
+    def last_accepted(c, it):
+        for t in range(it, 0, -1):
+            if out["accepted"][t - 1, c]:
+                return evals[c][t - 1]
+        raise AssertionError
+
+    def set_eval(c, it, ev, accepted):
+        evals[c][it - 1] = ev
+        i = it - 1
+        out["value"][i, c], out["prob"][i, c], out["status"][i, c] = ev[0], ev[1], ev[2]
+        out["params"][i, c], out["sim_moments"][i, c] = ev[3], ev[4]
+        out["accepted"][i, c] = accepted
+        if it == 1:
+            out["best_val"][i, c] = out["curr_val"][i, c] = ev[0]
+            out["best_id"][i, c] = 1
+        else:
+            out["curr_val"][i, c] = ev[0] if accepted else out["curr_val"][i - 1, c]
+            if ev[0] < out["best_val"][i - 1, c]:
+                out["best_val"][i, c], out["best_id"][i, c] = ev[0], it
+            else:
+                out["best_val"][i, c], out["best_id"][i, c] = out["best_val"][i - 1, c], out["best_id"][i - 1, c]
+
+    for it in range(1, n_iters + 1):
+        for c in range(N):
+            if it == 1:
+                pp = np.asarray(cfg.init, float).copy()
+            else:
+                old = last_accepted(c, it - 1)
+                mu01 = (old[3] - lb) / (ub - lb)
+                x01 = np.zeros(P)
+                for b0 in range(0, P, bs):
+                    for a in range(cfg.smpl_iters):
+                        cand = np.array([mu01[k] + sigma[c] * prop_normal(cfg.seed_algo, c, it, a, k) for k in range(b0, b0 + bs)])
+                        if np.all(cand >= 0) and np.all(cand <= 1):
+                            x01[b0:b0 + bs] = cand
+                            break
+                pp = x01 * (ub - lb) + lb
+            value, sim = objective(cfg, pp, c, it)
+            status = 1
+            if it == 1:
+                prob, accepted = 1.0, True
+            else:
+                old = last_accepted(c, it - 1)
+                e = math.exp(tun[c] * (old[0] - value))
+                prob = min(1.0, e)
+                accepted = prob > acc_uniform(cfg.seed_algo, c, it)
+            set_eval(c, it, (value, prob, status, pp, sim), accepted)
+            if it > 1:
+                noex = out["exchanged"][:it, c] == 0
+                rate = out["accepted"][:it, c][noex].mean()
+                if it % cfg.sigma_update_steps == 0:
+                    sigma[c] = sigma[c] * (1.0 + cfg.sigma_adjust_by) if rate > 0.234 else sigma[c] * (1.0 - cfg.sigma_adjust_by)
+        if it >= 2 and N > 1:
+            for (i, j) in pair_sample(cfg.seed_algo, it, N):
+                ei, ej = last_accepted(i, it), last_accepted(j, it)
+                if ei[0] - ej[0] > mi[i]:
+                    set_eval(i, it, ej, True)
+                    set_eval(j, it, ei, True)
+                    out["exchanged"][it - 1, i], out["exchanged"][it - 1, j] = j + 1, i + 1
+    out["sigma"] = sigma
+    return out

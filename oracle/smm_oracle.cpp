@@ -680,8 +680,7 @@ void smm_oracle_normal_from_words(uint32_t x, uint32_t y, uint32_t z, uint32_t w
   smm_u32x4 r = {x, y, z, w};
   smm_normal_pair(r, &out[0], &out[1]);
 }
-double smm_oracle_log01(double u) { return smm_log01(u, smm_logtab()); }
-void smm_oracle_sincos52(uint64_t B, double *c, double *s) { smm_sincos_turn52(B, c, s); }
+double smm_oracle_neglog01(double u) { return smm_neglog01(u, smm_logtab()); }
 double smm_oracle_acc_uniform(uint64_t seed, uint32_t chain, uint32_t iter) { return smm_acc_uniform(seed, chain, iter); }
 void smm_oracle_pair_unrank(uint32_t q, uint32_t *i, uint32_t *j) { smm_pair_unrank(q, i, j); }
 

@@ -1,8 +1,8 @@
 """ctypes mirror of include/smm_b200.h (structs, constants) -- interface only, no compute.
 
-Both the product binding (smm_jl_b200/_lib.py -> libsmm_b200.so) and the test oracle binding
-(oracle/oracle_lib.py -> libsmm_oracle.so) fill the same `smm_bgp_config`, which is what makes
-"same inputs" in the parity tests literal.
+The product binding (smm_jl_b200/_lib.py -> libsmm_b200.so) fills `smm_bgp_config` from here; the test
+suite's CPU checker fills the very same struct, which is what makes "same inputs" in the parity tests
+literal.
 """
 from __future__ import annotations
 

@@ -20,7 +20,8 @@ EXPORTS = [
     "smm_bgp_destroy", "smm_bgp_step", "smm_bgp_iteration", "smm_bgp_local_chains", "smm_bgp_stream",
     "smm_bgp_read_trace", "smm_bgp_read_chain_state", "smm_bgp_get_counters", "smm_bgp_eval_batch",
     "smm_bgp_state_bytes", "smm_bgp_export_state", "smm_bgp_import_state", "smm_debug_normals",
-    "smm_debug_pairs", "smm_debug_rng_throughput",
+    "smm_debug_pairs", "smm_debug_rng_throughput", "smm_stream_acc_uniforms", "smm_bgp_set_profiling",
+    "smm_bgp_kernel_times",
 ]
 
 
@@ -67,6 +68,9 @@ def lib():
     L.smm_debug_normals.argtypes = [C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, dp]
     L.smm_debug_pairs.argtypes = [vp, C.c_int32, ip, ip, ip]
     L.smm_debug_rng_throughput.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float), dp]
+    L.smm_stream_acc_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, dp]
+    L.smm_bgp_set_profiling.argtypes = [vp, C.c_int32]
+    L.smm_bgp_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -152,6 +156,17 @@ class BGPHandle:
                                        mom.ctypes.data_as(dp), status.ctypes.data_as(C.POINTER(C.c_int32))))
         return value, mom, status
 
+    def set_profiling(self, on: bool):
+        check(lib().smm_bgp_set_profiling(self._h, int(on)))
+
+    def kernel_times(self) -> dict:
+        """{kind: (ms_sum, launches)} accumulated while profiling was on"""
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        check(lib().smm_bgp_kernel_times(self._h, ms, n))
+        kinds = ("eval", "exchange", "pairs", "allgather")
+        return {k: (ms[i], n[i]) for i, k in enumerate(kinds)}
+
     def export_state(self) -> bytes:
         n = lib().smm_bgp_state_bytes(self._h)
         buf = C.create_string_buffer(n)
@@ -170,6 +185,12 @@ class BGPHandle:
         ip = C.POINTER(C.c_int32)
         check(lib().smm_debug_pairs(self._h, it, ij.ctypes.data_as(ip), off.ctypes.data_as(ip), C.byref(nlev)))
         return ij, off[: nlev.value + 1], nlev.value
+
+
+def acc_uniforms(seed_algo: int, chain: int, iter_lo: int, iter_hi: int) -> np.ndarray:
+    out = np.zeros(iter_hi - iter_lo + 1)
+    check(lib().smm_stream_acc_uniforms(seed_algo, chain, iter_lo, iter_hi, out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
 
 
 def debug_normals(seed: int, k: int, c2: int, c3: int, n_pairs: int, device: int = 0) -> np.ndarray:

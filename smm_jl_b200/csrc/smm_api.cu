@@ -83,6 +83,11 @@ struct smm_bgp {
   DevProblem pb{};
   DevState st{};
   smm_counters ctr{};
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;          // pairs of events, reused
+  std::vector<int> prof_kind;                // kind of each recorded pair in the current step
+  double prof_ms[4] = {0, 0, 0, 0};
+  int64_t prof_n[4] = {0, 0, 0, 0};
   // owned device memory
   DevBuf<double> lb, ub, init, data, w, acc_tuner, min_improve;
   DevBuf<double> sigma, accept_rate, la_cur, la_pub, la_all;
@@ -105,6 +110,8 @@ struct smm_bgp {
     t_acc.free(); t_status.free(); t_exch.free(); t_bestid.free();
     partials.free(); arrive.free(); sched_ij.free(); sched_off.free(); sched_nlev.free(); err.free();
     counters.free();
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
+    prof_ev.clear();
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -361,25 +368,50 @@ int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
   cudaStream_t s = h->stream;
   CUDA_TRY(cudaEventRecord(h->ev0, s));
   const bool exchange = h->N > 1;
+  h->prof_kind.clear();
+  auto prof_begin = [&](int kind) -> cudaError_t {
+    if (!h->profiling) return cudaSuccess;
+    const size_t i = h->prof_kind.size();
+    while (h->prof_ev.size() < 2 * (i + 1)) {
+      cudaEvent_t e;
+      cudaError_t rc = cudaEventCreate(&e);
+      if (rc != cudaSuccess) return rc;
+      h->prof_ev.push_back(e);
+    }
+    h->prof_kind.push_back(kind);
+    return cudaEventRecord(h->prof_ev[2 * i], s);
+  };
+  auto prof_end = [&]() -> cudaError_t {
+    if (!h->profiling) return cudaSuccess;
+    return cudaEventRecord(h->prof_ev[2 * (h->prof_kind.size() - 1) + 1], s);
+  };
   for (int k = 0; k < n_iters; ++k) {
     const int it = h->iter + 1;
     if (exchange && it >= 2 && (h->sched_iter0 < 0 || it >= h->sched_iter0 + h->sched_n)) {
       // precompute Pairs[it .. it+chunk) and their level schedules
       int n = h->max_iter - it + 1;
       if (n > kPairChunk) n = kPairChunk;
+      CUDA_TRY(prof_begin(2));
       launch_pairs(h->pb, h->st, it, n, h->n_s, s);
+      CUDA_TRY(prof_end());
       h->sched_iter0 = it;
       h->sched_n = n;
       h->ctr.kernel_launches++;
     }
+    CUDA_TRY(prof_begin(0));
     launch_eval(h->pb, h->st, it, h->n_split, h->part_len, s);
+    CUDA_TRY(prof_end());
     h->ctr.kernel_launches++;
     if (exchange && it >= 2) {  // AlgoBGP.jl:637
       if (h->world > 1) {
+        CUDA_TRY(prof_begin(3));
         NCCL_TRY(ncclAllGather(h->st.la_pub, h->st.la_all, (size_t)h->L * h->R, ncclDouble, h->comm, s));
+        CUDA_TRY(prof_end());
         h->ctr.collectives++;
       }
+      CUDA_TRY(prof_begin(1));
       launch_exchange(h->pb, h->st, it, it - h->sched_iter0, h->n_s, s);
+      CUDA_TRY(prof_end());
       h->ctr.kernel_launches++;
     }
     h->iter = it;
@@ -388,6 +420,12 @@ int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(s));
   if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  for (size_t i = 0; i < h->prof_kind.size(); ++i) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    h->prof_ms[h->prof_kind[i]] += ms;
+    h->prof_n[h->prof_kind[i]] += 1;
+  }
   h->ctr.iterations = h->iter;
   h->ctr.evaluations = (int64_t)h->iter * h->L;
   int flags = 0;
@@ -480,6 +518,31 @@ int smm_bgp_eval_batch(smm_bgp *h, const double *params, int32_t B, int32_t nose
   if (moments) CUDA_TRY(cudaMemcpyAsync(moments, d_mom.p, sizeof(double) * B * M, cudaMemcpyDeviceToHost, s));
   if (status) CUDA_TRY(cudaMemcpyAsync(status, d_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int smm_stream_acc_uniforms(uint64_t seed_algo, uint32_t chain, int32_t iter_lo, int32_t iter_hi, double *out) {
+  if (!out || iter_lo < 1 || iter_hi < iter_lo) return fail(SMM_E_ARG, "bad argument");
+  for (int32_t it = iter_lo; it <= iter_hi; ++it) out[it - iter_lo] = smm_acc_uniform(seed_algo, chain, (uint32_t)it);
+  return 0;
+}
+
+int smm_bgp_set_profiling(smm_bgp *h, int32_t enabled) {
+  if (!h) return fail(SMM_E_ARG, "null handle");
+  h->profiling = enabled != 0;
+  for (int k = 0; k < 4; ++k) {
+    h->prof_ms[k] = 0.0;
+    h->prof_n[k] = 0;
+  }
+  return 0;
+}
+
+int smm_bgp_kernel_times(smm_bgp *h, double ms_sum[4], int64_t launches[4]) {
+  if (!h || !ms_sum || !launches) return fail(SMM_E_ARG, "null argument");
+  for (int k = 0; k < 4; ++k) {
+    ms_sum[k] = h->prof_ms[k];
+    launches[k] = h->prof_n[k];
+  }
   return 0;
 }
 

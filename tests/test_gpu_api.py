@@ -1,0 +1,103 @@
+"""The reference-facing host API on the GPU: MProb / MAlgoBGP / run! / history / summary / restart!"""
+import os
+
+import numpy as np
+import pytest
+
+from smm_jl_b200 import api, configs
+from tests.parity import assert_trace_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def serial_normal_problem():
+    # Examples.jl:373-446 (snorm_impl, npar = 2)
+    m = api.MProb()
+    api.addSampledParam(m, {"p1": [0.2, -3, 3], "p2": [-0.2, -20, 20]})
+    api.addMoment(m, {"name": ["mu1", "mu2"], "value": [-1.0, 10.0], "weight": [1.0, 1.0]})
+    api.addEvalFunc(m, api.objfunc_norm)
+    opts = {"N": 3, "maxiter": 20, "maxtemp": 5, "coverage": 0.02, "smpl_iters": 1000, "parallel": False,
+            "min_improve": [0.0] * 3, "acc_tuners": [20, 2, 1.0], "animate": False, "seed": 12}
+    return m, opts
+
+
+def test_serial_normal_runs(oracle):
+    """test/test_algoBGP.jl:30-38: serialNormal(2,20): history is 20 x 9, o.i == 20"""
+    m, opts = serial_normal_problem()
+    MA = api.MAlgoBGP(m, opts)
+    api.run(MA)
+    assert MA.i == 20 and len(MA.chains) == 3
+    h = api.history(MA.chains[0])
+    assert h.shape == (20, 9)
+    assert list(h.columns) == ["iter", "value", "accepted", "curr_val", "best_val", "prob", "exchanged", "p1", "p2"]
+    # the same run through the oracle
+    ref = oracle.run(configs.c1_serial_normal(20), 20)
+    c = MA.chains[0]
+    assert_trace_parity(MA._trace, ref.trace)
+    assert c.id == 1 and c.iter == 20 and c.accept_rate == ref.accept_rate[0] and c.sigma == ref.sigma[0]
+    np.testing.assert_array_equal(c.probs_acc, [oracle.acc_uniform(12, 0, it) for it in range(1, 21)])
+    ev = c.evals[0]
+    assert ev.accepted and ev.prob == 1.0 and ev.status == 1 and list(ev.params) == ["p1", "p2"]
+    assert api.param(ev, "p1") == 0.2 and ev.simMoments["mu1"] == ref.trace.sim_moments[0, 0, 0]
+    s = api.summary(MA)
+    assert list(s.columns) == ["id", "acc_rate", "perc_exchanged", "exchanged_most_with", "best_val"] and len(s) == 3
+    v, idx = api.best(c)
+    assert v == ref.trace.value[:, 0].min() and idx == int(np.argmin(ref.trace.value[:, 0])) + 1
+    assert set(api.mean(c)) == {"p1", "p2"} and api.CI(c)["p1"].shape == (2,)
+    assert len(api.allAccepted(c)) == int(ref.trace.accepted[:, 0].sum())
+    MA.close()
+
+
+def test_recover_the_mean():
+    """test/test_algoBGP.jl:57-121: 2 chains x 200 iterations, median of chain 1 within 1.0 of (-1, 1)"""
+    m = api.MProb()
+    api.addSampledParam(m, {"p1": [0.2, -3, 3], "p2": [-0.2, -2, 2]})
+    api.addMoment(m, {"name": ["mu1", "mu2"], "value": [-1.0, 1.0], "weight": [1.0, 1.0]})
+    api.addEvalFunc(m, api.objfunc_norm)
+    opts = {"N": 2, "maxiter": 200, "maxtemp": 5, "sigma_update_steps": 201, "sigma_adjust_by": 0.01, "smpl_iters": 1000,
+            "parallel": True, "min_improve": [0.0, 0.0], "acc_tuners": [5, 1.0], "seed": 1234}
+    MA = api.MAlgoBGP(m, opts)
+    api.run(MA)
+    med = api.median(MA.chains[0])
+    assert abs(med["p1"] + 1.0) < 1.0 and abs(med["p2"] - 1.0) < 1.0
+    MA.close()
+
+
+def test_objfunc_norm_eval(oracle):
+    """test/test_objfunc.jl:22-29 through evaluateObjective on the device"""
+    m = api.MProb()
+    api.addSampledParam(m, {"p1": [0.0, -3, 3], "p2": [0.0, -3, 3]})
+    api.addMoment(m, {"mu1": {"value": 0.0, "weight": 1.0}, "mu2": {"value": 0.0, "weight": 1.0}})
+    api.addEvalFunc(m, api.objfunc_norm)
+    ev = api.evaluateObjective(m, {"p1": 0.0, "p2": 0.0})
+    assert ev.status == 1
+    assert abs(ev.simMoments["mu1"] - ev.dataMoments["mu1"]) < 0.1 and abs(ev.simMoments["mu2"]) < 0.1
+    ev2 = api.evaluateObjective(m, {"p1": 0.0, "p2": 0.0}, noseed=True, rep=3)
+    assert ev2.simMoments != ev.simMoments and ev2.options["noseed"]
+    api.addEvalFunc(m, api.Testobj_fails)
+    ev3 = api.evaluateObjective(m, {"p1": 0.0, "p2": 0.0})
+    assert ev3.status == -2 and ev3.value == -1.0 and len(ev3.simMoments) == 0     # mprob.jl:183-186
+
+
+def test_save_read_restart(tmp_path, oracle):
+    """test/test_AlgoAbstract.jl:36-62 (readMalgo == in-memory) and the restart test the reference meant to
+    write (test_algoBGP.jl:198-313): restart!(algo, k) == a straight run of maxiter + k"""
+    m, opts = serial_normal_problem()
+    fn = os.path.join(tmp_path, "algo.pkl")
+    opts = dict(opts, maxiter=10, save_frequency=5, filename=fn)
+    MA = api.MAlgoBGP(m, opts)
+    api.run(MA)
+    MB = api.readMalgo(fn)
+    assert MB.i == MA.i == 10
+    for a, b in zip(MA.chains, MB.chains):
+        for f in ("best_id", "best_val", "curr_val", "accepted", "exchanged", "probs_acc"):
+            np.testing.assert_array_equal(getattr(a, f), getattr(b, f))
+        assert a.sigma == b.sigma and a.accept_rate == b.accept_rate
+        assert a.evals[9] == b.evals[9]
+    api.restart(MB, 15)
+    assert MB.i == 25 and MB["maxiter"] == 25
+    ref = oracle.run(configs.c1_serial_normal(25), 25)
+    _ = MB.chains
+    assert_trace_parity(MB._trace, ref.trace)
+    MA.close()
+    MB.close()

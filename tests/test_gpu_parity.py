@@ -111,3 +111,126 @@ def test_batch_size_one(smm, oracle):
     tr, *_ = run_gpu(smm, cfg, 30)
     ref = oracle.run(cfg, 30, n_threads=8)
     assert_trace_parity(tr, ref.trace)
+
+
+def test_golden_vectors_on_gpu(smm):
+    """the committed fixtures (tests/golden/make_golden.py) without the oracle in the loop"""
+    import os
+    from smm_jl_b200._abi import Trace
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bgp_golden.npz"))
+    assert np.array_equal(smm.debug_normals(1234, 0, 0, 1 << 28, 64).view(np.uint64), g["normals_bits"])
+    for tag, cfg, n in (("c1", configs.c1_serial_normal(40), 40), ("mv", configs.mvnormal(8, 10), 10)):
+        tr, sigma, *_ = run_gpu(smm, cfg, n)
+        for f in Trace.INT_FIELDS:
+            np.testing.assert_array_equal(getattr(tr, f), g[f"{tag}_{f}"], err_msg=f)
+        for f in Trace.FLOAT_FIELDS:
+            np.testing.assert_allclose(getattr(tr, f), g[f"{tag}_{f}"], rtol=1e-6, atol=1e-12, err_msg=f)
+        np.testing.assert_array_equal(sigma, g[f"{tag}_sigma"])
+
+
+def test_step_in_pieces_equals_one_call(smm):
+    """run! iteration by iteration (the reference's loop) == n iterations enqueued at once"""
+    cfg = configs.mvnormal(16, 30)
+    tr_a, *_ = run_gpu(smm, cfg, 30)
+    with smm.BGPHandle(cfg) as h:
+        for n in (1, 1, 5, 13, 10):
+            h.step(n)
+        tr_b = h.read_trace(1, 30)
+    for f in tr_a.FLOAT_FIELDS + tr_a.INT_FIELDS:
+        assert np.array_equal(getattr(tr_a, f), getattr(tr_b, f), equal_nan=True), f
+
+
+def test_checkpoint_restart_is_bit_exact(smm):
+    """save / readMalgo / restart! (AlgoAbstract.jl:83-102, AlgoBGP.jl:804-884): a run resumed from an
+    exported state equals the straight run bit for bit (all randomness is counter-indexed)"""
+    cfg = configs.mvnormal(16, 40)
+    tr_a, sig_a, acc_a, _ = run_gpu(smm, cfg, 40)
+    with smm.BGPHandle(cfg) as h:
+        h.step(17)
+        blob = h.export_state()
+    with smm.BGPHandle(configs.mvnormal(16, 40)) as h2:
+        h2.import_state(blob)
+        assert h2.iteration == 17
+        h2.step(23)
+        tr_b = h2.read_trace(1, 40)
+        sig_b, acc_b = h2.chain_state()
+    for f in tr_a.FLOAT_FIELDS + tr_a.INT_FIELDS:
+        assert np.array_equal(getattr(tr_a, f), getattr(tr_b, f), equal_nan=True), f
+    assert np.array_equal(sig_a, sig_b) and np.array_equal(acc_a, acc_b)
+
+
+def test_large_config_properties(smm):
+    """BASELINE C2 at full size (256 chains x 10 000 draws): size-independent properties"""
+    n = 60
+    cfg = configs.mvnormal(256, n)
+    tr, sigma, acc, ctr = run_gpu(smm, cfg, n)
+    # running-minimum / index bookkeeping (set_eval!)
+    np.testing.assert_array_equal(tr.best_val, np.minimum.accumulate(tr.value, axis=0))
+    rows = tr.best_id - 1
+    np.testing.assert_array_equal(np.take_along_axis(tr.value, rows, axis=0), tr.best_val)
+    # curr_val follows accepted values
+    want = np.where(tr.accepted[1:] == 1, tr.value[1:], tr.curr_val[:-1])
+    np.testing.assert_array_equal(tr.curr_val[1:], want)
+    # common random numbers: simulated means are affine in the parameters, variances are constant
+    zbar = tr.sim_moments[:, :, :8] - tr.params
+    assert np.ptp(zbar, axis=(0, 1)).max() < 1e-12
+    assert np.ptp(tr.sim_moments[:, :, 8:], axis=(0, 1)).max() < 1e-9
+    # value is the weighted distance of the stored moments
+    d = (tr.sim_moments - np.asarray(cfg.data_mom)) / np.asarray(cfg.data_w)
+    np.testing.assert_allclose(tr.value, (d * d).mean(axis=2), rtol=1e-12)
+    # exchanges are symmetric, partner ids valid, and swap accepted records
+    ex = tr.exchanged
+    assert (ex[0] == 0).all() and ex.max() <= 256
+    its, cs = np.nonzero(ex)
+    assert len(its) > 0 and (tr.accepted[its, cs] == 1).all()
+    # a chain that swapped exactly once points at a partner that points back
+    assert ctr["swaps"] > 0 and ctr["evaluations"] == 256 * n
+    # proposals stay inside the box
+    assert (tr.params >= -3).all() and (tr.params <= 3).all()
+    assert (sigma > 0).all() and ((acc >= 0) & (acc <= 1)).all()
+
+
+def test_sampler_exhaustion_is_an_error(smm, oracle):
+    """AlgoBGP.jl:409: `error("no draw in support ...")` with a single batch"""
+    from smm_jl_b200._abi import SMM_E_SAMPLER_EXHAUSTED
+    cfg = configs.mvnormal(4, 6, sigma0=[50.0] * 4, smpl_iters=3)
+    with pytest.raises(smm.SMMError) as e:
+        with smm.BGPHandle(cfg) as h:
+            h.step(6)
+    assert e.value.code == SMM_E_SAMPLER_EXHAUSTED
+    with pytest.raises(oracle.OracleError) as e2:
+        oracle.run(cfg, 6)
+    assert e2.value.code == SMM_E_SAMPLER_EXHAUSTED
+    # several batches: the failure is swallowed and the parameter falls to its lower bound (:445-452)
+    cfg = configs.mvnormal(4, 6, sigma0=[50.0] * 4, smpl_iters=3, batch_size=1)
+    tr, *_ = run_gpu(smm, cfg, 6)
+    ref = oracle.run(cfg, 6)
+    assert_trace_parity(tr, ref.trace)
+    assert (tr.params[1:] == -3.0).any()
+
+
+def test_odd_draw_count_and_other_dims(smm, oracle):
+    for P, S in ((2, 9999), (5, 1001), (16, 2000)):
+        cfg = configs.mvnormal(6, 8, n_params=P, n_sim=S)
+        tr, *_ = run_gpu(smm, cfg, 8)
+        ref = oracle.run(cfg, 8, n_threads=4)
+        assert_trace_parity(tr, ref.trace)
+    cfg = configs.normal_means(6, 8, n_params=18, batch_size=1, sigma0=[0.001] * 6)   # snorm_18 shape (Examples.jl:232)
+    tr, *_ = run_gpu(smm, cfg, 8)
+    assert_trace_parity(tr, oracle.run(cfg, 8, n_threads=4).trace)
+
+
+def test_noseed_run(smm, oracle):
+    cfg = configs.mvnormal(8, 12, noseed=1)
+    tr, *_ = run_gpu(smm, cfg, 12)
+    assert_trace_parity(tr, oracle.run(cfg, 12, n_threads=4).trace)
+
+
+def test_slow_objective(smm, oracle):
+    import time
+    cfg = configs.slow_normal(8, 6, slow_seconds=0.02)
+    t0 = time.time()
+    tr, *_ = run_gpu(smm, cfg, 6)
+    assert time.time() - t0 >= 6 * 0.02
+    cfg_fast = configs.slow_normal(8, 6, slow_seconds=0.0)
+    assert_trace_parity(tr, oracle.run(cfg_fast, 6).trace)

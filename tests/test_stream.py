@@ -1,0 +1,92 @@
+"""The stream definitions of include/smm_stream.h (CPU side): Philox known-answer vectors, accuracy of
+the fp64 transform against a 120-bit evaluation of its own definition, distribution sanity."""
+import mpmath as mp
+import numpy as np
+from scipy import stats
+
+
+def test_philox_known_answers(oracle):
+    # Random123 kat_vectors, philox4x32-10
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    for c, k, want in kat:
+        assert tuple(int(x) for x in oracle.philox(c, k)) == want
+
+
+def test_neglog_accuracy(oracle):
+    mp.mp.prec = 120
+    rng = np.random.default_rng(1)
+    us = list(rng.random(1500)) + [2.0 ** -52, 0.5, 1 - 2.0 ** -52, 0.70710678118, 2.0 ** -30 * 1.999, 1 - 2.0 ** -20]
+    worst = max(abs(mp.mpf(oracle.neglog01(float(u))) + mp.log(mp.mpf(float(u)))) / -mp.log(mp.mpf(float(u))) for u in us)
+    assert worst < 1e-14
+
+
+def test_normal_pair_matches_its_definition(oracle):
+    """z0,z1 = sqrt(-2 ln u1) (cos,sin)((pi/4) g) under the drawn symmetry, to ~4 ulp"""
+    mp.mp.prec = 120
+    rng = np.random.default_rng(2)
+    worst = mp.mpf(0)
+    for _ in range(1500):
+        x, y, z, w = [int(v) for v in rng.integers(0, 2 ** 32, 4)]
+        z0, z1 = oracle.normal_from_words(x, y, z, w)
+        A = ((x << 20) | (y >> 12)) | 1
+        u1 = mp.mpf(2 ** 52 - A) / 2 ** 52
+        g = mp.mpf(((z << 20) | (w >> 12)) & (2 ** 49 - 1)) / 2 ** 49
+        rad = mp.sqrt(-2 * mp.log(u1))
+        c, s = mp.cos(mp.pi / 4 * g), mp.sin(mp.pi / 4 * g)
+        if (z >> 29) & 1:
+            c, s = s, c
+        if (z >> 30) & 1:
+            c = -c
+        if (z >> 31) & 1:
+            s = -s
+        worst = max(worst, abs(mp.mpf(z0) - rad * c), abs(mp.mpf(z1) - rad * s))
+    assert worst < 4e-15
+
+
+def test_extreme_words(oracle):
+    for words in [(0, 0, 0, 0), (0xffffffff,) * 4, (0xffffffff, 0xffffffff, 0, 0), (0, 0, 0xffffffff, 0xffffffff)]:
+        z = oracle.normal_from_words(*words)
+        assert np.all(np.isfinite(z)) and np.all(np.abs(z) < 8.6)
+
+
+def test_normals_are_standard_normal(oracle):
+    z = oracle.normals(1234, 0, 0, 1 << 28, 500_000)
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 5e-3           # the pair is uncorrelated
+    assert stats.kstest(z[0::2] ** 2 + z[1::2] ** 2, "chi2", args=(2,)).pvalue > 1e-3
+    z2 = oracle.normals(1234, 1, 0, 1 << 28, 500_000)                 # another row: independent stream
+    assert abs(np.corrcoef(z, z2)[0, 1]) < 5e-3
+
+
+def test_acc_uniform_range_and_determinism(oracle):
+    u = np.array([oracle.acc_uniform(12, c, it) for c in range(3) for it in range(1, 400)])
+    assert (u >= 0).all() and (u < 1).all() and abs(u.mean() - 0.5) < 0.05
+    assert oracle.acc_uniform(12, 1, 7) == oracle.acc_uniform(12, 1, 7)
+    assert oracle.acc_uniform(12, 1, 7) != oracle.acc_uniform(13, 1, 7)
+
+
+def test_pair_unrank_is_the_reference_order(oracle):
+    # [(i,j) for i in 1:N, j in 1:N if i<j]: i fastest (AlgoBGP.jl:653)
+    N = 7
+    want = [(i, j) for j in range(N) for i in range(N) if i < j]
+    got = [oracle.pair_unrank(q) for q in range(N * (N - 1) // 2)]
+    assert got == want
+    for q in [0, 1, 2, 523775, 2 ** 25 + 17, 33550335]:
+        i, j = oracle.pair_unrank(q)
+        assert 0 <= i < j and j * (j - 1) // 2 + i == q
+
+
+def test_pairs_are_distinct_and_in_range(oracle):
+    for N in (2, 3, 5, 64, 300):
+        for it in (2, 3, 99):
+            p = oracle.pairs(777, it, N)
+            assert len(p) == (N - 1 if N < 3 else N)
+            assert len({tuple(r) for r in p.tolist()}) == len(p)
+            assert (p[:, 0] < p[:, 1]).all() and (p >= 0).all() and (p < N).all()
+    assert not np.array_equal(oracle.pairs(777, 2, 64), oracle.pairs(777, 3, 64))
