@@ -97,14 +97,15 @@ def addSampledParam(m: MProb, name, init=None, lb=None, ub=None):
 
 def addMoment(m: MProb, name, value=None, weight=1.0):
     """addMoment!(m, name, value[, weight]) / dict of {value, weight} / table with name,value,weight (mprob.jl:123-155)"""
+    if hasattr(name, "columns") or (isinstance(name, dict) and "name" in name and "value" in name):  # DataFrame-like
+        names, values = list(name["name"]), list(name["value"])
+        weights = list(name["weight"]) if "weight" in name else [1.0] * len(names)
+        for n, v, w in zip(names, values, weights):
+            addMoment(m, n, v, w)
+        return m
     if isinstance(name, dict):
         for k, v in name.items():
             addMoment(m, k, v["value"], v.get("weight", 1.0))
-        return m
-    if hasattr(name, "columns") or hasattr(name, "keys") and "name" in name:  # DataFrame-like
-        names, values, weights = list(name["name"]), list(name["value"]), list(name["weight"])
-        for n, v, w in zip(names, values, weights):
-            addMoment(m, n, v, w)
         return m
     m.moments[str(name)] = {"value": float(value), "weight": float(weight)}
     return m

@@ -43,6 +43,10 @@ def mvnormal(n_chains: int = 256, niter: int = 1000, n_params: int = 8, **kw) ->
         n_chains=n_chains, max_iter=niter,
         sigma0=0.05 * temps, acc_tuner=tuners, min_improve=[0.0] * n_chains,
         objective_id=SMM_OBJ_NORM_MV, n_sim=10000, seed_sim=1234, seed_algo=20261017,
+        # upstream's default of 1000 rejection attempts (AlgoBGP.jl:520) makes the reference algorithm itself
+        # abort at this scale: a hot chain in a corner of the 8-dim box has P(in support) ~ 0.5^8 per attempt,
+        # and with 256+ chains x 1000 iterations some proposal exhausts 1000 attempts (-> `error`, :409).
+        smpl_iters=100000,
     )
     args.update(kw)
     return BGPConfig(**args)

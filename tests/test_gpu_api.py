@@ -38,7 +38,7 @@ def test_serial_normal_runs(oracle):
     np.testing.assert_array_equal(c.probs_acc, [oracle.acc_uniform(12, 0, it) for it in range(1, 21)])
     ev = c.evals[0]
     assert ev.accepted and ev.prob == 1.0 and ev.status == 1 and list(ev.params) == ["p1", "p2"]
-    assert api.param(ev, "p1") == 0.2 and ev.simMoments["mu1"] == ref.trace.sim_moments[0, 0, 0]
+    assert api.param(ev, "p1") == 0.2 and ev.simMoments["mu1"] == pytest.approx(ref.trace.sim_moments[0, 0, 0], rel=1e-9)
     s = api.summary(MA)
     assert list(s.columns) == ["id", "acc_rate", "perc_exchanged", "exchanged_most_with", "best_val"] and len(s) == 3
     v, idx = api.best(c)
