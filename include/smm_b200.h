@@ -96,8 +96,10 @@ typedef struct smm_bgp_config {
   int32_t world_size;  /* number of processes/GPUs sharing the chains (1, 2, 4, 8)                   */
   int32_t rank;        /* this process: owns chains [rank*N/world, (rank+1)*N/world)                  */
   uint8_t nccl_id[SMM_NCCL_ID_BYTES]; /* from smm_nccl_unique_id on rank 0 (ignored if world == 1)   */
-  int32_t exchange_mode; /* 0 = ncclAllGather + exchange kernel; 1 = fused peer-store all-gather       */
-  int32_t n_split;       /* CTAs per chain evaluation; 0 = choose from the SM count                    */
+  int32_t exchange_mode; /* 0 = one launch per iteration (+ ncclAllGather + exchange kernel when world > 1);
+                            1 = persistent cooperative kernel; with world > 1 the all-gather is fused into it
+                            as peer stores over NVLink (CUDA IPC) and a flag exchange inside the grid barrier  */
+  int32_t n_split;       /* mode 0: CTAs per chain evaluation; mode 1: cap on CTAs per SM; 0 = automatic      */
 } smm_bgp_config;
 
 /* Host-side SoA view of iterations [iter_lo, iter_hi] (1-based, inclusive) of the chains this rank
@@ -163,7 +165,9 @@ int smm_stream_acc_uniforms(uint64_t seed_algo, uint32_t chain, int32_t iter_lo,
 
 /* per-kernel device timing: when enabled, smm_bgp_step brackets every launch with CUDA events on the
  * library's stream and accumulates the elapsed time per kernel kind (slows the step; off by default).
- * kinds: 0 = evaluation kernel, 1 = exchange kernel, 2 = pair-schedule kernel, 3 = all-gather. */
+ * kinds: 0 = evaluation kernel (multi-launch) or persistent kernel, 1 = exchange kernel, 2 = pair-schedule
+ * kernel, 3 = all-gather.  smm_bgp_kernel_times returns the number of BGP iterations the kind-0 launches
+ * covered (>= 0; a persistent launch covers many), or a negative error code. */
 int smm_bgp_set_profiling(smm_bgp *h, int32_t enabled);
 int smm_bgp_kernel_times(smm_bgp *h, double ms_sum[4], int64_t launches[4]);
 
@@ -172,6 +176,9 @@ int smm_debug_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, ui
                       double *out /* [2*n_pairs] */);
 int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij /* [n_pairs][2] in execution order */,
                     int32_t *level_offsets /* [n_pairs+1] */, int32_t *n_levels);
+/* debug: per-CTA globaltimer stamps {start, after proposal, after simulate, end} of the last iteration;
+ * needs SMM_PHASE_TS=1 in the environment at create time.  Returns n_split (>0) or an error. */
+int smm_debug_phase_ts(smm_bgp *h, uint64_t *out, int64_t n);
 int smm_debug_rng_throughput(int32_t device, int64_t n_pairs_per_thread, int32_t blocks, int32_t threads,
                              float *elapsed_ms, double *checksum);
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "smm_bgp_read_trace", "smm_bgp_read_chain_state", "smm_bgp_get_counters", "smm_bgp_eval_batch",
     "smm_bgp_state_bytes", "smm_bgp_export_state", "smm_bgp_import_state", "smm_debug_normals",
     "smm_debug_pairs", "smm_debug_rng_throughput", "smm_stream_acc_uniforms", "smm_bgp_set_profiling",
-    "smm_bgp_kernel_times",
+    "smm_bgp_kernel_times", "smm_debug_phase_ts",
 ]
 
 
@@ -71,6 +71,7 @@ def lib():
     L.smm_stream_acc_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, dp]
     L.smm_bgp_set_profiling.argtypes = [vp, C.c_int32]
     L.smm_bgp_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_int64)]
+    L.smm_debug_phase_ts.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int64]
     _lib = L
     return L
 
@@ -163,9 +164,21 @@ class BGPHandle:
         """{kind: (ms_sum, launches)} accumulated while profiling was on"""
         ms = (C.c_double * 4)()
         n = (C.c_int64 * 4)()
-        check(lib().smm_bgp_kernel_times(self._h, ms, n))
+        iters = lib().smm_bgp_kernel_times(self._h, ms, n)
+        if iters < 0:
+            check(iters)
         kinds = ("eval", "exchange", "pairs", "allgather")
-        return {k: (ms[i], n[i]) for i, k in enumerate(kinds)}
+        out = {k: (ms[i], n[i]) for i, k in enumerate(kinds)}
+        out["eval_iterations"] = iters
+        return out
+
+    def phase_ts(self) -> np.ndarray:
+        """[L][n_split][4] globaltimer stamps (ns) of the last iteration (needs SMM_PHASE_TS=1 at create)"""
+        out = np.zeros(1 << 18, dtype=np.uint64)
+        nblk = lib().smm_debug_phase_ts(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), out.size)
+        if nblk <= 0:
+            check(nblk)
+        return out[: nblk * 4].reshape(nblk, 4)
 
     def export_state(self) -> bytes:
         n = lib().smm_bgp_state_bytes(self._h)

@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -18,6 +19,9 @@ size_t pairs_smem_bytes(int N, int n_s);
 size_t exch_smem_bytes(int N);
 cudaError_t configure_kernels(int N, int n_s);
 int eval_max_blocks_per_sm();
+int persistent_max_blocks_per_sm(int N);
+cudaError_t launch_persistent(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int sched_iter0,
+                              int n_s, int part_len, int max_seg, int grid, cudaStream_t s);
 void launch_eval(const DevProblem &pb, const DevState &st, int iter, int n_split, int part_len, cudaStream_t s);
 void launch_pairs(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int n_s, cudaStream_t s);
 void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sched_idx, int n_s, cudaStream_t s);
@@ -75,6 +79,10 @@ struct smm_bgp {
   int P = 0, M = 0, N = 0, L = 0, chain0 = 0, R = 0, max_iter = 0, world = 1, rank = 0;
   int n_s = 0;       // pairs per iteration
   int n_split = 1, part_len = 0;
+  double eval_param_limit = 0.0;  // |param| bound for which the fixed-point accumulators are sized
+  int mode = 0;           // 0 = multi-launch (+ NCCL), 1 = persistent kernel (+ fused peer-store all-gather)
+  int grid = 0, max_seg = 1;  // persistent kernel: CTAs, partial slots per chain
+  void *peer_ptrs[3 * kMaxWorld] = {nullptr};  // IPC-opened peer buffers (closed in release)
   int iter = 0;      // iterations completed (algo.i)
   int sched_iter0 = -1, sched_n = 0;
   cudaStream_t stream = nullptr;
@@ -87,10 +95,13 @@ struct smm_bgp {
   std::vector<cudaEvent_t> prof_ev;          // pairs of events, reused
   std::vector<int> prof_kind;                // kind of each recorded pair in the current step
   double prof_ms[4] = {0, 0, 0, 0};
+  int64_t prof_iters = 0;                    // iterations covered by the kind-0 launches
   int64_t prof_n[4] = {0, 0, 0, 0};
   // owned device memory
   DevBuf<double> lb, ub, init, data, w, acc_tuner, min_improve;
-  DevBuf<double> sigma, accept_rate, la_cur, la_pub, la_all;
+  DevBuf<double> sigma, accept_rate, la_cur, la_pub, la_all, val_all, pp;
+  DevBuf<GridBarrier> bar;
+  DevBuf<unsigned long long> sync_seq, flags;
   DevBuf<int> n_noex, n_acc;
   DevBuf<double> t_value, t_prob, t_curr, t_best, t_params, t_mom;
   DevBuf<uint8_t> t_acc;
@@ -98,18 +109,23 @@ struct smm_bgp {
   DevBuf<double> partials;
   DevBuf<unsigned> arrive;
   DevBuf<int> sched_ij, sched_off, sched_nlev, err;
-  DevBuf<unsigned long long> counters;
+  DevBuf<unsigned long long> counters, phase_ts;
 
   void release() {
+    for (void *&q : peer_ptrs) {
+      if (q) cudaIpcCloseMemHandle(q);
+      q = nullptr;
+    }
     if (comm) ncclCommDestroy(comm);
     comm = nullptr;
+    val_all.free(); pp.free(); bar.free(); sync_seq.free(); flags.free();
     lb.free(); ub.free(); init.free(); data.free(); w.free(); acc_tuner.free(); min_improve.free();
     sigma.free(); accept_rate.free(); la_cur.free(); la_pub.free(); la_all.free();
     n_noex.free(); n_acc.free();
     t_value.free(); t_prob.free(); t_curr.free(); t_best.free(); t_params.free(); t_mom.free();
     t_acc.free(); t_status.free(); t_exch.free(); t_bestid.free();
     partials.free(); arrive.free(); sched_ij.free(); sched_off.free(); sched_nlev.free(); err.free();
-    counters.free();
+    counters.free(); phase_ts.free();
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
     prof_ev.clear();
     if (ev0) cudaEventDestroy(ev0);
@@ -206,6 +222,8 @@ int device_error_to_rc(int flags) {
                 "AlgoBGP assumes that your objective function returns a non-negative number (AlgoBGP.jl:341)");
   if (flags & kErrExhausted)
     return fail(SMM_E_SAMPLER_EXHAUSTED, "no draw in support after smpl_iters trials (AlgoBGP.jl:409)");
+  if (flags & kErrTimeout)
+    return fail(SMM_E_CUDA, "persistent kernel: barrier / peer-flag wait timed out (a rank did not reach the exchange)");
   return 0;
 }
 
@@ -292,9 +310,15 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   const double nan = std::numeric_limits<double>::quiet_NaN(), inf = std::numeric_limits<double>::infinity();
   if (int rc = fill(h->la_cur, (size_t)L * R, nan)) return rc;
   if (int rc = fill(h->la_pub, (size_t)L * R, nan)) return rc;
+  h->mode = cfg->exchange_mode ? 1 : 0;
   if (h->world > 1) {
-    if (int rc = fill(h->la_all, (size_t)N * R, nan)) return rc;
+    if (int rc = fill(h->la_all, (size_t)(h->mode ? 2 : 1) * N * R, nan)) return rc;
   }
+  if (int rc = fill(h->val_all, (size_t)2 * N, nan)) return rc;
+  if (int rc = fill(h->pp, (size_t)L * P, nan)) return rc;
+  if (int rc = fill(h->bar, 1, GridBarrier{0u, 0u})) return rc;
+  if (int rc = fill(h->sync_seq, 1, 0ull)) return rc;
+  if (int rc = fill(h->flags, (size_t)kMaxWorld, 0ull)) return rc;
   // trace: unrun slots look like a fresh BGPChain (AlgoBGP.jl:81-89); Eval slots are `undef` -> NaN
   const size_t IL = (size_t)I * L;
   if (int rc = fill(h->t_value, IL, nan)) return rc;
@@ -314,24 +338,67 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   const int n_blocks_philox = (cfg->n_sim + 1) / 2;
   h->n_split = choose_split(L, prop.multiProcessorCount, eval_max_blocks_per_sm(), n_blocks_philox, cfg->n_split);
   if (cfg->objective_id == SMM_OBJ_FAILS) h->n_split = 1;
-  if (int rc = fill(h->partials, (size_t)L * h->n_split * h->part_len, 0.0)) return rc;
+  if (N > 1) CUDA_TRY(configure_kernels(N, h->n_s));
+  h->max_seg = h->n_split;
+  if (h->mode == 1) {
+    int coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
+    if (!coop) return fail(SMM_E_CUDA, "device does not support cooperative launches (exchange_mode 1)");
+    int occ = persistent_max_blocks_per_sm(N);
+    if (occ < 1) return fail(SMM_E_CUDA, "persistent kernel does not fit on an SM");
+    if (cfg->n_split > 0 && cfg->n_split < occ) occ = cfg->n_split;  // n_split caps CTAs per SM in this mode
+    h->grid = prop.multiProcessorCount * occ;
+    const int per_chain = (h->grid + L - 1) / L + 1;
+    if (per_chain > h->max_seg) h->max_seg = per_chain;
+  }
+  if (int rc = fill(h->partials, (size_t)L * h->max_seg * h->part_len, 0.0)) return rc;
   if (int rc = fill(h->arrive, (size_t)L, 0u)) return rc;
   if (h->N > 1) {
     if (int rc = fill(h->sched_ij, (size_t)kPairChunk * h->n_s * 2, 0)) return rc;
     if (int rc = fill(h->sched_off, (size_t)kPairChunk * (h->n_s + 1), 0)) return rc;
     if (int rc = fill(h->sched_nlev, (size_t)kPairChunk, 0)) return rc;
-    CUDA_TRY(configure_kernels(N, h->n_s));
   }
   if (int rc = fill(h->err, 1, 0)) return rc;
   if (int rc = fill(h->counters, 4, 0ull)) return rc;
 
   DevProblem &pb = h->pb;
   pb.P = P; pb.M = M; pb.S = cfg->n_sim; pb.obj = cfg->objective_id; pb.noseed = cfg->noseed;
-  pb.N = N; pb.L = L; pb.chain0 = h->chain0; pb.max_iter = I; pb.world = h->world;
+  pb.N = N; pb.L = L; pb.chain0 = h->chain0; pb.max_iter = I; pb.world = h->world; pb.rank = h->rank;
+  {
+    uint32_t k0 = (uint32_t)cfg->seed_sim, k1 = (uint32_t)(cfg->seed_sim >> 32);
+    for (int r = 0; r < 10; ++r) {
+      pb.rk_sim0[r] = k0;
+      pb.rk_sim1[r] = k1;
+      k0 += SMM_PHILOX_W0;
+      k1 += SMM_PHILOX_W1;
+    }
+  }
   pb.sigma_update_steps = cfg->sigma_update_steps; pb.smpl_iters = cfg->smpl_iters; pb.batch_size = cfg->batch_size;
   pb.panel_T = cfg->panel_T; pb.panel_N = cfg->panel_N; pb.panel_K = cfg->panel_K;
   pb.sigma_adjust_by = cfg->sigma_adjust_by; pb.slow_seconds = cfg->slow_seconds;
   pb.seed_sim = cfg->seed_sim; pb.seed_algo = cfg->seed_algo;
+  {
+    // fixed-point grids of the order-invariant accumulators (smm_kernels.cu): |x| <= xmax = box + 9 sigma-units,
+    // totals S*xmax and S*xmax^2 must stay below 2^62, single terms below 2^(51-F) (4x headroom for eval_batch)
+    double box = 0.0;
+    for (int k = 0; k < P; ++k) {
+      box = std::fmax(box, std::fabs(cfg->lb[k]));
+      box = std::fmax(box, std::fabs(cfg->ub[k]));
+    }
+    const double xmax = 4.0 * (box + 9.0);
+    auto pick = [&](double term_max) {
+      int f_total = 62 - (int)std::ceil(std::log2((double)cfg->n_sim * term_max));
+      int f_term = 51 - (int)std::ceil(std::log2(term_max));
+      int f = f_total < f_term ? f_total : f_term;
+      return f > 60 ? 60 : f;
+    };
+    const int f_sum = pick(xmax), f_sq = pick(xmax * xmax);
+    pb.magic_sum = std::ldexp(1.5, 52 - f_sum);
+    pb.magic_sq = std::ldexp(1.5, 52 - f_sq);
+    pb.scale_sum = std::ldexp(1.0, -f_sum);
+    pb.scale_sq = std::ldexp(1.0, -f_sq);
+    h->eval_param_limit = xmax - 9.0;
+  }
   pb.lb = h->lb.p; pb.ub = h->ub.p; pb.init = h->init.p; pb.data = h->data.p; pb.w = h->w.p;
   pb.acc_tuner = h->acc_tuner.p; pb.min_improve = h->min_improve.p;
 
@@ -344,11 +411,64 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   st.partials = h->partials.p; st.arrive = h->arrive.p;
   st.sched_ij = h->sched_ij.p; st.sched_off = h->sched_off.p; st.sched_nlev = h->sched_nlev.p;
   st.err = h->err.p; st.counters = h->counters.p;
+  st.val_all = h->val_all.p; st.pp = h->pp.p; st.bar = h->bar.p; st.sync_seq = h->sync_seq.p; st.flags = h->flags.p;
+  for (int r = 0; r < kMaxWorld; ++r) {
+    st.peer_la_all[r] = nullptr;
+    st.peer_val_all[r] = nullptr;
+    st.peer_flags[r] = nullptr;
+  }
+  st.phase_ts = nullptr;
+  if (getenv("SMM_PHASE_TS")) {
+    size_t slots = (size_t)L * h->n_split;
+    if ((size_t)h->grid * 2 > slots) slots = (size_t)h->grid * 2;
+    if (int rc = fill(h->phase_ts, slots * 4, 0ull)) return rc;
+    st.phase_ts = h->phase_ts.p;
+  }
 
   if (h->world > 1) {
+    if (h->world > kMaxWorld) return fail(SMM_E_ARG, "world_size > 8");
     ncclUniqueId id;
     memcpy(&id, cfg->nccl_id, sizeof id);
     NCCL_TRY(ncclCommInitRank(&h->comm, h->world, id, h->rank));
+    if (h->mode == 1) {
+      // fused all-gather: map every peer's gather buffers (CUDA IPC); the handles travel over the communicator
+      struct Handles {
+        cudaIpcMemHandle_t la, val, flags;
+      } mine;
+      CUDA_TRY(cudaIpcGetMemHandle(&mine.la, h->la_all.p));
+      CUDA_TRY(cudaIpcGetMemHandle(&mine.val, h->val_all.p));
+      CUDA_TRY(cudaIpcGetMemHandle(&mine.flags, h->flags.p));
+      DevBuf<char> d_mine, d_all;
+      CUDA_TRY(d_mine.alloc(sizeof(Handles)));
+      CUDA_TRY(d_all.alloc(sizeof(Handles) * h->world));
+      CUDA_TRY(cudaMemcpy(d_mine.p, &mine, sizeof mine, cudaMemcpyHostToDevice));
+      ncclResult_t nr = ncclAllGather(d_mine.p, d_all.p, sizeof(Handles), ncclChar, h->comm, h->stream);
+      std::vector<Handles> all(h->world);
+      cudaError_t ce = cudaStreamSynchronize(h->stream);
+      if (ce == cudaSuccess) ce = cudaMemcpy(all.data(), d_all.p, sizeof(Handles) * h->world, cudaMemcpyDeviceToHost);
+      d_mine.free();
+      d_all.free();
+      NCCL_TRY(nr);
+      CUDA_TRY(ce);
+      for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) {
+          st.peer_la_all[r] = h->la_all.p;
+          st.peer_val_all[r] = h->val_all.p;
+          st.peer_flags[r] = h->flags.p;
+          continue;
+        }
+        void *q = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&q, all[r].la, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_ptrs[3 * r] = q;
+        st.peer_la_all[r] = (double *)q;
+        CUDA_TRY(cudaIpcOpenMemHandle(&q, all[r].val, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_ptrs[3 * r + 1] = q;
+        st.peer_val_all[r] = (double *)q;
+        CUDA_TRY(cudaIpcOpenMemHandle(&q, all[r].flags, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_ptrs[3 * r + 2] = q;
+        st.peer_flags[r] = (unsigned long long *)q;
+      }
+    }
   }
   CUDA_TRY(cudaDeviceSynchronize());
   guard.ok = true;
@@ -385,7 +505,30 @@ int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
     if (!h->profiling) return cudaSuccess;
     return cudaEventRecord(h->prof_ev[2 * (h->prof_kind.size() - 1) + 1], s);
   };
-  for (int k = 0; k < n_iters; ++k) {
+  if (h->mode == 1) {
+    int left = n_iters;
+    while (left > 0) {
+      const int it0 = h->iter + 1;
+      const int n = left < kPairChunk ? left : kPairChunk;
+      const int s0 = it0 < 2 ? 2 : it0;  // first iteration whose exchange runs inside this launch
+      if (exchange && it0 + n - 1 >= 2) {
+        CUDA_TRY(prof_begin(2));
+        launch_pairs(h->pb, h->st, s0, it0 + n - s0, h->n_s, s);
+        CUDA_TRY(prof_end());
+        h->ctr.kernel_launches++;
+      }
+      h->sched_iter0 = -1;
+      h->sched_n = 0;
+      CUDA_TRY(prof_begin(0));
+      CUDA_TRY(launch_persistent(h->pb, h->st, it0, n, s0, h->n_s, h->part_len, h->max_seg, h->grid, s));
+      CUDA_TRY(prof_end());
+      h->prof_iters += h->profiling ? n : 0;
+      h->ctr.kernel_launches++;
+      h->iter += n;
+      left -= n;
+    }
+  }
+  for (int k = 0; h->mode == 0 && k < n_iters; ++k) {
     const int it = h->iter + 1;
     if (exchange && it >= 2 && (h->sched_iter0 < 0 || it >= h->sched_iter0 + h->sched_n)) {
       // precompute Pairs[it .. it+chunk) and their level schedules
@@ -401,6 +544,7 @@ int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
     CUDA_TRY(prof_begin(0));
     launch_eval(h->pb, h->st, it, h->n_split, h->part_len, s);
     CUDA_TRY(prof_end());
+    h->prof_iters += h->profiling ? 1 : 0;
     h->ctr.kernel_launches++;
     if (exchange && it >= 2) {  // AlgoBGP.jl:637
       if (h->world > 1) {
@@ -484,6 +628,9 @@ int smm_bgp_eval_batch(smm_bgp *h, const double *params, int32_t B, int32_t nose
                        double *moments, int32_t *status) {
   if (!h || !params) return fail(SMM_E_ARG, "null argument");
   if (B < 1) return fail(SMM_E_ARG, "B must be positive");
+  for (int64_t i = 0; i < (int64_t)B * h->P; ++i)
+    if (!(std::fabs(params[i]) <= h->eval_param_limit))
+      return fail(SMM_E_ARG, "parameter far outside the sampling box (> 4x): accumulators are sized from the box");
   CUDA_TRY(cudaSetDevice(h->device));
   const int P = h->P, M = h->M;
   int n_split = h->n_split;
@@ -530,6 +677,7 @@ int smm_stream_acc_uniforms(uint64_t seed_algo, uint32_t chain, int32_t iter_lo,
 int smm_bgp_set_profiling(smm_bgp *h, int32_t enabled) {
   if (!h) return fail(SMM_E_ARG, "null handle");
   h->profiling = enabled != 0;
+  h->prof_iters = 0;
   for (int k = 0; k < 4; ++k) {
     h->prof_ms[k] = 0.0;
     h->prof_n[k] = 0;
@@ -543,7 +691,7 @@ int smm_bgp_kernel_times(smm_bgp *h, double ms_sum[4], int64_t launches[4]) {
     ms_sum[k] = h->prof_ms[k];
     launches[k] = h->prof_n[k];
   }
-  return 0;
+  return (int)h->prof_iters;  /* iterations covered by the kind-0 launches (>= 0) */
 }
 
 // ---- checkpoint ----------------------------------------------------------------------------------
@@ -668,6 +816,15 @@ int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij, int32_t *level_offset
   CUDA_TRY(cudaMemcpy(level_offsets, h->st.sched_off, sizeof(int) * (h->n_s + 1), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(n_levels, h->st.sched_nlev, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
+}
+
+int smm_debug_phase_ts(smm_bgp *h, uint64_t *out, int64_t n) {
+  if (!h || !out) return fail(SMM_E_ARG, "null argument");
+  if (!h->st.phase_ts) return fail(SMM_E_STATE, "set SMM_PHASE_TS=1 before smm_bgp_create");
+  const int64_t blocks = h->mode == 1 ? (int64_t)h->grid * 2 : (int64_t)h->L * h->n_split;
+  const int64_t have = blocks * 4;
+  CUDA_TRY(cudaMemcpy(out, h->st.phase_ts, sizeof(uint64_t) * (n < have ? n : have), cudaMemcpyDeviceToHost));
+  return (int)blocks;
 }
 
 int smm_debug_rng_throughput(int32_t device, int64_t n_pairs_per_thread, int32_t blocks, int32_t threads,

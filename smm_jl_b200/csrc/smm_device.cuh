@@ -8,11 +8,12 @@
 
 namespace smm {
 
-constexpr int kEvalThreads = 128;   // CTA size of the evaluation kernel
-constexpr int kExchThreads = 512;   // CTA size of the exchange kernel
+constexpr int kEvalThreads = 128;   // CTA size of the evaluation / persistent kernels
+constexpr int kExchThreads = 512;   // CTA size of the stand-alone exchange kernel
 constexpr int kPairThreads = 256;   // CTA size of the pair-schedule kernel
-constexpr int kMaxSplit = 64;       // CTAs cooperating on one evaluation
+constexpr int kMaxSplit = 64;       // CTAs cooperating on one evaluation (multi-launch mode)
 constexpr int kPairChunk = 128;     // iterations of pair schedules precomputed per launch
+constexpr int kMaxWorld = 8;        // GPUs of one box
 
 // Last-accepted record of a chain, one row of R = 3 + P + M doubles:
 //   [0] value  [1] prob  [2] status (as double)  [3..3+P) params  [3+P..3+P+M) simMoments
@@ -21,16 +22,25 @@ __host__ __device__ inline int rec_len(int P, int M) { return 3 + P + M; }
 // device error flags (sticky, OR-ed into DevState::err)
 constexpr int kErrNegative = 1;
 constexpr int kErrExhausted = 2;
+constexpr int kErrTimeout = 4;
 
 struct DevProblem {
   int P, M, S, obj, noseed;
-  int N, L, chain0, max_iter, world;
+  int N, L, chain0, max_iter, world, rank;
   int sigma_update_steps, smpl_iters, batch_size;
   int panel_T, panel_N, panel_K;
   double sigma_adjust_by, slow_seconds;
+  double magic_sum, magic_sq;               // 1.5 * 2^(52-F): fixed-point rounding constants of the accumulators
+  double scale_sum, scale_sq;               // 2^-F
   uint64_t seed_sim, seed_algo;
+  uint32_t rk_sim0[10], rk_sim1[10];        // Philox round keys of seed_sim (constant-bank operands)
   const double *lb, *ub, *init, *data, *w;  // [P] x3, [M] x2
   const double *acc_tuner, *min_improve;    // [N]
+};
+
+struct GridBarrier {
+  unsigned arrive;
+  unsigned gen;
 };
 
 struct DevState {
@@ -39,21 +49,31 @@ struct DevState {
   int *n_noex, *n_acc;         // iterations without exchange / accepted among them (set_acceptRate!)
   double *la_cur;              // [L][R] last accepted record = proposal centre for the next iteration
   double *la_pub;              // [L][R] record published to the exchange step
-  double *la_all;              // [N][R] gathered records (== la_pub when world == 1)
+  double *la_all;              // gathered records: [N][R] (multi-launch) or [2][N][R] by iteration parity (fused)
+  double *val_all;             // [2][N] compact values of la_all (fused mode)
+  double *pp;                  // [L][P] proposals of the current iteration (persistent kernel)
   // trace, [max_iter][L] (+[P], +[M])
   double *t_value, *t_prob, *t_curr, *t_best, *t_params, *t_mom;
   uint8_t *t_acc;
   int *t_status, *t_exch, *t_bestid;
   // evaluation scratch
-  double *partials;            // [L][n_split][2*kPartLen]
+  double *partials;            // [L][max segments][part_len]
   unsigned *arrive;            // [L]
   // exchange schedule for iterations [sched_iter0, sched_iter0 + kPairChunk)
   int *sched_ij;               // [kPairChunk][n_s][2], level order
   int *sched_off;              // [kPairChunk][n_s + 1]
   int *sched_nlev;             // [kPairChunk]
+  // persistent kernel
+  GridBarrier *bar;
+  unsigned long long *sync_seq;            // cross-GPU sync sequence number (monotone over the handle's life)
+  double *peer_la_all[kMaxWorld];          // every rank's la_all (IPC-mapped; [rank] is our own)
+  double *peer_val_all[kMaxWorld];
+  unsigned long long *peer_flags[kMaxWorld];  // every rank's flags[kMaxWorld]; we write slot [our rank]
+  unsigned long long *flags;               // our own flags[kMaxWorld], written by the peers
   // diagnostics
   int *err;
-  unsigned long long *counters;  // [0] accepted [1] swaps [2] proposal attempts
+  unsigned long long *phase_ts;  // debug: per-CTA globaltimer stamps of the last iteration (or null)
+  unsigned long long *counters;  // [0] accepted [1] swaps [2] proposal attempts [3] barrier spins
 };
 
 }  // namespace smm

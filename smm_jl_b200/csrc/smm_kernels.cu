@@ -1,21 +1,28 @@
 // smm_kernels.cu -- sm_100a kernels of the BGP hot path.
 //
-//   bgp_eval_kernel    one iteration of every local chain: truncated random-walk proposal
-//                      (AlgoBGP.jl:424-471), model simulation + moments + weighted distance
-//                      (ObjExamples.jl:59-116), Metropolis accept/reject + sigma adaptation
-//                      (AlgoBGP.jl:324-392), trace bookkeeping (set_eval! :220-245).
-//                      Grid (n_split, L): n_split CTAs share one evaluation; each thread owns one
-//                      simulated dimension k and a strided set of Philox blocks, keeps its draws in
-//                      registers, accumulates in fp64; the last CTA to arrive reduces the partials in
-//                      a fixed order (deterministic) and finishes the chain.
-//   bgp_pairs_kernel   Pairs[iter] for a chunk of iterations (AlgoBGP.jl:653-656) plus a level
-//                      schedule: pairs that share no chain with an earlier unfinished pair get the
-//                      same level, so the sequential pair loop (:662-691) runs level-parallel with
-//                      identical results.  Data independent -> off the critical path.
-//   bgp_exchange_kernel exchangeMoves! / swap_ev_ij! (AlgoBGP.jl:647-749) on the gathered records.
-//   objective_kernel   batched bare objective (evaluateObjective, mprob.jl:175-205).
-#include <cooperative_groups.h>
-
+// Two ways to run an iteration, same device functions, bit-identical results:
+//
+//  (A) multi-launch (exchange_mode 0):
+//      bgp_eval_kernel      grid (n_split, L): proposal -> simulate -> [last CTA of the chain] moments,
+//                           distance, accept/reject, trace.
+//      [ncclAllGather of the last-accepted records when world > 1]
+//      bgp_exchange_kernel  exchangeMoves! on the gathered records.
+//
+//  (B) persistent (exchange_mode 1): bgp_persistent_kernel, one cooperative launch for up to kPairChunk
+//      iterations, one CTA set resident on every SM, two grid barriers per iteration:
+//        [owner CTAs: exchange of iteration i-1 (replicated), proposal of iteration i]      -- barrier --
+//        [all CTAs: an equal share of the flattened (chain, draw) space; the CTA that completes a
+//         chain finishes it (moments, distance, accept/reject, trace) and, with world > 1, stores the
+//         chain's record straight into every peer GPU's gather buffer over NVLink]         -- barrier,
+//         folded with a cross-GPU flag exchange: the all-gather costs no launch and no extra barrier --
+//
+// Reference lines: proposal AlgoBGP.jl:424-471 (mysample :400-410, mapto_01/ab mprob.jl:246-272);
+// objfunc_norm ObjExamples.jl:59-116; doAcceptReject! AlgoBGP.jl:324-392; set_eval! :220-245;
+// set_acceptRate! :253-257; exchangeMoves! :647-691; swap_ev_ij! :734-749; pair sample :653-656.
+//
+// Each thread owns one simulated dimension k and a strided set of Philox blocks, keeps its draws in
+// registers and accumulates in fp64; partial sums meet in shared memory, then (across CTAs) in a small
+// global buffer that the last-arriving CTA reduces in a fixed order, so results are deterministic.
 #include "smm_device.cuh"
 
 namespace smm {
@@ -28,25 +35,56 @@ struct EvalSmem {
   double mu01[SMM_MAX_PARAMS];      // centre in unit-cube coordinates
   double cand[2 * kEvalThreads];    // candidates of one round of attempts, [attempt][P]
   double red[2 * kEvalThreads];     // per-thread partial sums
-  double tot[2 * SMM_MAX_PARAMS];   // totals over all splits
+  double tot[2 * SMM_MAX_PARAMS];   // totals over all segments
   double mom[SMM_MAX_MOMENTS];      // simulated moments
   smm_logent logtab[1 << SMM_LOG_BITS];
   unsigned char okf[2 * kEvalThreads];
   int first[SMM_MAX_PARAMS];        // per batch: first in-support attempt of this round
   int resolved[SMM_MAX_PARAMS];     // per batch: attempts used (0 = unresolved)
   int is_last;
-  double value;
+  int acc, status;
+  double value, prob;
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PHASE_STAMP(slot, i)                                                                  \
+  do {                                                                                        \
+    if (st.phase_ts && threadIdx.x == 0) st.phase_ts[(size_t)(slot)*4 + (i)] = gtimer();      \
+  } while (0)
 
 __device__ __forceinline__ void load_logtab(smm_logent *dst) {
   const smm_logent *src = smm_logtab();
   for (int i = threadIdx.x; i < (1 << SMM_LOG_BITS); i += blockDim.x) dst[i] = src[i];
 }
 
+// Philox4x32-10 with the round keys of seed_sim taken from the kernel-parameter constant bank
+__device__ __forceinline__ smm_u32x4 philox_sim(const DevProblem &pb, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                uint32_t c3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)SMM_PHILOX_M0 * c0;
+    const uint64_t p1 = (uint64_t)SMM_PHILOX_M1 * c2;
+    c0 = (uint32_t)(p1 >> 32) ^ c1 ^ pb.rk_sim0[r];
+    c1 = (uint32_t)p1;
+    c2 = (uint32_t)(p0 >> 32) ^ c3 ^ pb.rk_sim1[r];
+    c3 = (uint32_t)p0;
+  }
+  smm_u32x4 out;
+  out.x = c0;
+  out.y = c1;
+  out.z = c2;
+  out.w = c3;
+  return out;
+}
+
 // ------------------------------------------------------------------------------------------------
-// proposal(c) -- AlgoBGP.jl:424-471, mysample :400-410, mapto_01/ab mprob.jl:246-272.
-// Attempts are counter-indexed, so a round evaluates blockDim/kp attempts at once and the lowest
-// in-support attempt wins: identical to the reference's sequential loop.
+// proposal(c) -- AlgoBGP.jl:424-471.  Attempts are counter-indexed, so a round evaluates
+// blockDim/kp attempts at once and the lowest in-support attempt wins: identical to the reference's
+// sequential rejection loop.  Result in sm.pp.
 // ------------------------------------------------------------------------------------------------
 __device__ void block_proposal(const DevProblem &pb, const DevState &st, EvalSmem &sm, int c, int gc, int iter,
                                bool count) {
@@ -58,12 +96,12 @@ __device__ void block_proposal(const DevProblem &pb, const DevState &st, EvalSme
   }
   const int R = rec_len(pb.P, pb.M);
   const double *la = st.la_cur + (size_t)c * R;
-  const double sigma = st.sigma[c];
+  const double sigma = __ldcg(st.sigma + c);
   const int kp = (P + 1) >> 1;
-  const int A = nthr / kp;                // attempts per round
+  const int A = nthr / kp;  // attempts per round
   const int bs = pb.batch_size, nb = P / bs;
   for (int k = tid; k < P; k += nthr) {
-    sm.mu01[k] = __ddiv_rn(__dsub_rn(la[3 + k], pb.lb[k]), __dsub_rn(pb.ub[k], pb.lb[k]));
+    sm.mu01[k] = __ddiv_rn(__dsub_rn(__ldcg(la + 3 + k), pb.lb[k]), __dsub_rn(pb.ub[k], pb.lb[k]));
     sm.pp[k] = 0.0;  // pp = zero(mu01) (:445)
   }
   for (int b = tid; b < nb; b += nthr) sm.resolved[b] = 0;
@@ -103,27 +141,20 @@ __device__ void block_proposal(const DevProblem &pb, const DevState &st, EvalSme
       const int b = k / bs;
       if (sm.resolved[b] == 0 && sm.first[b] != 0x7fffffff) sm.pp[k] = sm.cand[sm.first[b] * P + k];
     }
-    __syncthreads();
     int still = 0;
-    for (int b = 0; b < nb; ++b) {  // every thread computes the same count (nb <= 64)
-      if (sm.resolved[b] == 0) {
-        if (sm.first[b] != 0x7fffffff) {
-          if (tid == 0) sm.resolved[b] = base + sm.first[b] + 1;
-        } else {
-          ++still;
-        }
-      }
-    }
+    for (int b = 0; b < nb; ++b)  // every thread computes the same count (nb <= 64)
+      if (sm.resolved[b] == 0 && sm.first[b] == 0x7fffffff) ++still;
     unresolved = still;
     __syncthreads();
+    for (int b = tid; b < nb; b += nthr)
+      if (sm.resolved[b] == 0 && sm.first[b] != 0x7fffffff) sm.resolved[b] = base + sm.first[b] + 1;
+    __syncthreads();
   }
-  if (unresolved > 0) {
+  if (unresolved > 0 && nb == 1) {
     // single batch: `error("no draw in support ...")` (:409) aborts the run -> sticky error flag;
-    // several batches: the exception is logged and swallowed, pp[i] stays 0 (:447-451)
-    if (nb == 1) {
-      if (tid == 0) atomicOr(st.err, kErrExhausted);
-      for (int k = tid; k < P; k += nthr) sm.pp[k] = sm.mu01[k];
-    }
+    // (several batches: the exception is logged and swallowed, pp[i] stays 0, :447-451)
+    if (tid == 0) atomicOr(st.err, kErrExhausted);
+    for (int k = tid; k < P; k += nthr) sm.pp[k] = sm.mu01[k];
   }
   if (count && tid == 0) {
     unsigned long long att = 0;
@@ -138,160 +169,146 @@ __device__ void block_proposal(const DevProblem &pb, const DevState &st, EvalSme
 
 // ------------------------------------------------------------------------------------------------
 // Simulation of the MvNormal objectives (ObjExamples.jl:76-79): X[k,s] = p_k + Z[k,s], reduced on the
-// fly to sum_s X and sum_s X^2 per row.  Thread t owns row k = t % D and Philox blocks
-// j = j0 + t/D, +lanes, ... of this CTA's share [j0, j1) of the ceil(S/2) blocks.
-// Writes this CTA's partial sums [2][D] to `part`.
+// fly to sum_s X and sum_s X^2 per row, for Philox blocks j in [j0, j1) of this evaluation.
+// Thread t owns row k = t % D and blocks j0 + t/D, +lanes, ...   Writes partial sums [2][D] to `part`.
+//
+// ORDER-INVARIANT ACCUMULATION.  Every term is rounded once to a fixed-point grid (x -> x + M with
+// M = 1.5 * 2^(52-F): the low mantissa bits of the sum are round(x * 2^F)) and the 64-bit patterns are
+// added as integers, so the totals do not depend on how draws are split over threads, CTAs, launches or
+// GPUs: chains with equal parameters get bit-equal values (the exchange step compares values, ties must
+// stay ties as in the sequential reference), and 1-GPU and N-GPU runs agree to the bit.  Grid error per
+// term <= 2^-(F+1) (F chosen by the host from S and the parameter box; ~2^-45 for the C2 shapes).
 // ------------------------------------------------------------------------------------------------
-__device__ void simulate_norm_partial(const DevProblem &pb, EvalSmem &sm, int split, int n_split, uint32_t uid,
-                                      uint32_t rep, double *part) {
+__device__ void simulate_norm_segment(const DevProblem &pb, EvalSmem &sm, int j0, int j1, uint32_t uid, uint32_t rep,
+                                      double *part) {
   const int D = pb.P, S = pb.S, tid = threadIdx.x;
   const int lanes = blockDim.x / D;
-  const int n_blocks = (S + 1) >> 1;
-  const int j0 = (int)(((long long)n_blocks * split) / n_split);
-  const int j1 = (int)(((long long)n_blocks * (split + 1)) / n_split);
-  double sum = 0.0, sq = 0.0;
+  const int n_full = S >> 1;  // blocks whose two normals are both used
+  const uint32_t c2 = pb.noseed ? uid : 0u;
+  const uint32_t c3 = (SMM_STREAM_SIM << 28) | (pb.noseed ? (rep & SMM_ITER_MASK) : 0u);
+  const double Msum = pb.magic_sum, Msq = pb.magic_sq;
+  unsigned long long isum = 0ull, isq = 0ull;  // sums of raw bit patterns; the n*bits(M) offset leaves at the end
   if (tid < lanes * D) {
     const int k = tid % D, ln = tid / D;
     const double p = sm.pp[k];
-    for (int j = j0 + ln; j < j1; j += lanes) {
+    const int jend = j1 < n_full ? j1 : n_full;
+    for (int j = j0 + ln; j < jend; j += lanes) {
       double z0, z1;
-      smm_normal_pair_tab(smm_sim_block(pb.seed_sim, (uint32_t)j, (uint32_t)k, pb.noseed, uid, rep), sm.logtab, &z0,
-                          &z1);
+      smm_normal_pair_tab(philox_sim(pb, (uint32_t)j, (uint32_t)k, c2, c3), sm.logtab, &z0, &z1);
       const double x0 = __dadd_rn(p, z0);
-      sum = __dadd_rn(sum, x0);
-      sq = __fma_rn(x0, x0, sq);
-      if (2 * j + 1 < S) {
-        const double x1 = __dadd_rn(p, z1);
-        sum = __dadd_rn(sum, x1);
-        sq = __fma_rn(x1, x1, sq);
-      }
+      const double x1 = __dadd_rn(p, z1);
+      isum += (unsigned long long)__double_as_longlong(__dadd_rn(x0, Msum));
+      isq += (unsigned long long)__double_as_longlong(__fma_rn(x0, x0, Msq));
+      isum += (unsigned long long)__double_as_longlong(__dadd_rn(x1, Msum));
+      isq += (unsigned long long)__double_as_longlong(__fma_rn(x1, x1, Msq));
+    }
+    if ((S & 1) && ln == 0 && j0 <= n_full && n_full < j1) {  // odd S: the last block contributes one draw
+      double z0, z1;
+      smm_normal_pair_tab(philox_sim(pb, (uint32_t)n_full, (uint32_t)k, c2, c3), sm.logtab, &z0, &z1);
+      const double x0 = __dadd_rn(p, z0);
+      isum += (unsigned long long)__double_as_longlong(__dadd_rn(x0, Msum));
+      isq += (unsigned long long)__double_as_longlong(__fma_rn(x0, x0, Msq));
     }
   }
-  sm.red[2 * tid] = sum;
-  sm.red[2 * tid + 1] = sq;
+  unsigned long long *red = (unsigned long long *)sm.red;
+  red[2 * tid] = isum;
+  red[2 * tid + 1] = isq;
   __syncthreads();
   if (tid < 2 * D) {
     const int k = tid % D, which = tid / D;
-    double acc = 0.0;
-    for (int ln = 0; ln < lanes; ++ln) acc = __dadd_rn(acc, sm.red[2 * (ln * D + k) + which]);
-    part[which * D + k] = acc;
+    unsigned long long acc = 0ull;
+    for (int ln = 0; ln < lanes; ++ln) acc += red[2 * (ln * D + k) + which];
+    ((unsigned long long *)part)[which * D + k] = acc;
   }
+  __syncthreads();
 }
 
-// moments + weighted distance from the totals (thread 0..M-1 compute moments, thread 0 the value)
-__device__ void finalize_norm(const DevProblem &pb, EvalSmem &sm, bool with_var) {
+// sum the n_seg partials of an evaluation (integer adds: exact), then moments + weighted distance
+__device__ void reduce_and_finalize(const DevProblem &pb, EvalSmem &sm, const double *part_base, int n_seg,
+                                    int part_len) {
   const int D = pb.P, tid = threadIdx.x;
+  if (pb.obj == SMM_OBJ_FAILS) {
+    // the objective throws -> caught by evaluateObjective: status -2, value stays -1.0, no moments
+    for (int k = tid; k < pb.M; k += blockDim.x) sm.mom[k] = __longlong_as_double(0x7ff8000000000000ll);
+    if (tid == 0) {
+      sm.value = -1.0;
+      sm.status = -2;
+    }
+    __syncthreads();
+    return;
+  }
+  if (tid < 2 * D) {
+    unsigned long long acc = 0ull;
+    const unsigned long long *pu = (const unsigned long long *)part_base;
+    for (int s = 0; s < n_seg; ++s) acc += __ldcg(pu + (size_t)s * part_len + tid);
+    // remove S copies of bits(M) (mod 2^64: exact), then fixed point -> double
+    const bool is_sq = tid >= D;
+    const unsigned long long mb = (unsigned long long)__double_as_longlong(is_sq ? pb.magic_sq : pb.magic_sum);
+    const long long fixed = (long long)(acc - (unsigned long long)pb.S * mb);
+    sm.tot[tid] = __dmul_rn((double)fixed, is_sq ? pb.scale_sq : pb.scale_sum);
+  }
+  __syncthreads();
   const double S = (double)pb.S;
   if (tid < D) {
     const double mean = __ddiv_rn(sm.tot[tid], S);
     sm.mom[tid] = mean;
-    if (with_var) {
+    if (pb.obj == SMM_OBJ_NORM_MV) {
       // sum (x - mean)^2 = sum x^2 - mean * sum x
       const double ss = __dsub_rn(sm.tot[D + tid], __dmul_rn(mean, sm.tot[tid]));
       sm.mom[D + tid] = __ddiv_rn(ss, S - 1.0);
     }
   }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < 32) {  // value = mean_k ((sim_k - data_k) / w_k)^2, divisions in parallel, summed in moment order
     double acc = 0.0;
-    for (int k = 0; k < pb.M; ++k) {
-      const double d = __ddiv_rn(__dsub_rn(sm.mom[k], pb.data[k]), pb.w[k]);
-      acc = __fma_rn(d, d, acc);
+    for (int k0 = 0; k0 < pb.M; k0 += 32) {
+      const int k = k0 + tid;
+      double d2 = 0.0;
+      if (k < pb.M) {
+        const double d = __ddiv_rn(__dsub_rn(sm.mom[k], pb.data[k]), pb.w[k]);
+        d2 = __dmul_rn(d, d);
+      }
+      const int n = pb.M - k0 < 32 ? pb.M - k0 : 32;
+      for (int l = 0; l < n; ++l) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, d2, l));
     }
-    sm.value = __ddiv_rn(acc, (double)pb.M);
+    if (tid == 0) {
+      sm.value = __ddiv_rn(acc, (double)pb.M);
+      sm.status = 1;
+    }
   }
   __syncthreads();
 }
 
 __device__ __forceinline__ void slow_spin(double seconds) {
   // objfunc_norm_slow: sleep(0.1) (ObjExamples.jl:130)
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const unsigned long long t0 = gtimer();
   const unsigned long long ns = (unsigned long long)(seconds * 1e9);
-  do {
-    __nanosleep(20000);
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-  } while (t1 - t0 < ns);
+  while (gtimer() - t0 < ns) __nanosleep(20000);
 }
 
-// Evaluate the objective at sm.pp cooperatively over n_split CTAs.  Returns true in the one CTA that
-// arrives last; there sm.mom / sm.value / *status are complete.
-__device__ bool objective_core(const DevProblem &pb, EvalSmem &sm, int split, int n_split, int part_len,
-                               uint32_t uid, uint32_t rep, double *part_base, unsigned *arrive, int *status) {
+// ------------------------------------------------------------------------------------------------
+// doAcceptReject! (AlgoBGP.jl:324-392) + set_eval! (:220-245) for chain c with the evaluation in
+// sm.value / sm.status / sm.mom / sm.pp.  Writes the trace slot, the last-accepted record (la_cur),
+// the published record (la_pub) and -- fused multi-GPU mode -- the record and its value into every
+// rank's gather buffer (peer stores over NVLink).
+// ------------------------------------------------------------------------------------------------
+__device__ void accept_and_store(const DevProblem &pb, const DevState &st, EvalSmem &sm, int c, int gc, int iter,
+                                 bool fused) {
   const int tid = threadIdx.x;
-  if (pb.obj == SMM_OBJ_FAILS) {
-    // the objective throws -> caught by evaluateObjective, status -2, value stays -1.0, no moments
-    if (split != 0) return false;
-    for (int k = tid; k < pb.M; k += blockDim.x) sm.mom[k] = __longlong_as_double(0x7ff8000000000000ll);
-    if (tid == 0) sm.value = -1.0;
-    *status = -2;
-    __syncthreads();
-    return true;
-  }
-  if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
-  double *part = part_base + (size_t)split * part_len;
-  simulate_norm_partial(pb, sm, split, n_split, uid, rep, part);
-  const int n_tot = 2 * pb.P;
-  if (n_split > 1) {
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned prev = atomicAdd(arrive, 1u);
-      sm.is_last = (prev == (unsigned)(n_split - 1));
-      if (sm.is_last) *arrive = 0u;  // re-arm for the next iteration
-    }
-    __syncthreads();
-    if (!sm.is_last) return false;
-    __threadfence();
-  } else {
-    __syncthreads();
-  }
-  if (tid < n_tot) {
-    double acc = 0.0;
-    for (int s = 0; s < n_split; ++s) acc = __dadd_rn(acc, __ldcg(part_base + (size_t)s * part_len + tid));
-    sm.tot[tid] = acc;
-  }
-  __syncthreads();
-  finalize_norm(pb, sm, pb.obj == SMM_OBJ_NORM_MV);
-  *status = 1;
-  return true;
-}
-
-// ------------------------------------------------------------------------------------------------
-// one BGP iteration for every local chain
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, DevState st, int iter, int n_split,
-                                                                int part_len) {
-  __shared__ EvalSmem sm;
-  const int c = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
-  const int gc = pb.chain0 + c;
   const int P = pb.P, M = pb.M, R = rec_len(P, M), L = pb.L;
-  load_logtab(sm.logtab);
-  __syncthreads();
-  block_proposal(pb, st, sm, c, gc, iter, split == 0);
-
-  int ev_status = -1;
-  const bool last = objective_core(pb, sm, split, n_split, part_len, (uint32_t)gc, (uint32_t)iter,
-                                   st.partials + (size_t)c * n_split * part_len, st.arrive + c, &ev_status);
-  if (!last) return;
-
-  // ---- doAcceptReject! (AlgoBGP.jl:324-392) + set_eval! (:220-245), one thread ------------------
   double *la = st.la_cur + (size_t)c * R;
   double *pub = st.la_pub + (size_t)c * R;
   const size_t slot = (size_t)(iter - 1) * L + c;
-  __shared__ int s_acc;
-  __shared__ double s_prob;
-  __shared__ int s_status;
   if (tid == 0) {
     const double value = sm.value;
     double prob;
-    int accepted, status = ev_status;
+    int accepted, status = sm.status;
     if (iter == 1) {
       prob = 1.0;
       accepted = 1;
       status = 1;
     } else {
-      const double old_value = la[0];
+      const double old_value = __ldcg(la);
       if (status < 0) {
         prob = 0.0;
         accepted = 0;
@@ -313,13 +330,13 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, D
       }
     }
     // set_acceptRate! (:253-257): this iteration has exchanged == 0 at this point
-    const int n_noex = st.n_noex[c] + 1, n_acc = st.n_acc[c] + accepted;
+    const int n_noex = __ldcg(st.n_noex + c) + 1, n_acc = __ldcg(st.n_acc + c) + accepted;
     st.n_noex[c] = n_noex;
     st.n_acc[c] = n_acc;
     const double rate = __ddiv_rn((double)n_acc, (double)n_noex);
     st.accept_rate[c] = rate;
     if (iter > 1 && iter % pb.sigma_update_steps == 0) {
-      const double s = st.sigma[c];
+      const double s = __ldcg(st.sigma + c);
       st.sigma[c] = rate > 0.234 ? __dmul_rn(s, __dadd_rn(1.0, pb.sigma_adjust_by))
                                  : __dmul_rn(s, __dsub_rn(1.0, pb.sigma_adjust_by));
     }
@@ -332,14 +349,14 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, D
       best_id = 1;
     } else {
       const size_t prev = slot - L;
-      curr = accepted ? value : st.t_curr[prev];
-      const double bprev = st.t_best[prev];
+      curr = accepted ? value : __ldcg(st.t_curr + prev);
+      const double bprev = __ldcg(st.t_best + prev);
       if (value < bprev) {
         best = value;
         best_id = iter;
       } else {
         best = bprev;
-        best_id = st.t_bestid[prev];
+        best_id = __ldcg(st.t_bestid + prev);
       }
     }
     st.t_value[slot] = value;
@@ -351,49 +368,386 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, D
     st.t_exch[slot] = 0;
     st.t_bestid[slot] = best_id;
     if (accepted) atomicAdd(&st.counters[0], 1ull);
-    s_acc = accepted;
-    s_prob = prob;
-    s_status = status;
+    sm.acc = accepted;
+    sm.prob = prob;
+    sm.status = status;
   }
   __syncthreads();
   // trace rows + last-accepted record (coalesced over threads)
   for (int k = tid; k < P; k += blockDim.x) st.t_params[slot * P + k] = sm.pp[k];
   for (int k = tid; k < M; k += blockDim.x) st.t_mom[slot * M + k] = sm.mom[k];
-  if (s_acc) {
-    if (tid == 0) {
-      la[0] = sm.value;
-      la[1] = s_prob;
-      la[2] = (double)s_status;
+  const int par = fused ? (iter & 1) : 0;
+  for (int k = tid; k < R; k += blockDim.x) {
+    double v;
+    if (sm.acc) {
+      v = k == 0 ? sm.value : k == 1 ? sm.prob : k == 2 ? (double)sm.status : k < 3 + P ? sm.pp[k - 3] : sm.mom[k - 3 - P];
+      la[k] = v;
+    } else {
+      v = __ldcg(la + k);
     }
-    for (int k = tid; k < P; k += blockDim.x) la[3 + k] = sm.pp[k];
-    for (int k = tid; k < M; k += blockDim.x) la[3 + P + k] = sm.mom[k];
+    pub[k] = v;
+    if (fused) {
+      // the all-gather: one coalesced row per peer, straight into its gather buffer
+      for (int r = 0; r < pb.world; ++r) st.peer_la_all[r][((size_t)par * pb.N + gc) * R + k] = v;
+      if (k == 0)
+        for (int r = 0; r < pb.world; ++r) st.peer_val_all[r][(size_t)par * pb.N + gc] = v;
+    } else if (k == 0) {
+      st.val_all[gc] = v;  // compact copy of the values for the exchange step
+    }
   }
   __syncthreads();
-  for (int k = tid; k < R; k += blockDim.x) pub[k] = la[k];
 }
 
 // ------------------------------------------------------------------------------------------------
-// batched bare objective: grid (n_split, B)
+// exchangeMoves! (AlgoBGP.jl:647-691): the sequential pair loop, run level-parallel over the schedule of
+// iteration `iter` (pairs inside a level share no chain).  val/own/exch live in shared memory.
+// ------------------------------------------------------------------------------------------------
+__device__ unsigned exchange_levels(const DevProblem &pb, const DevState &st, int sched_idx, int n_s, double *val,
+                                    unsigned short *own, unsigned short *exch) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int *ij = st.sched_ij + (size_t)sched_idx * n_s * 2;
+  const int *off = st.sched_off + (size_t)sched_idx * (n_s + 1);
+  const int nlev = st.sched_nlev[sched_idx];
+  unsigned n_swaps = 0;
+  for (int l = 0; l < nlev; ++l) {
+    const int lo = off[l], hi = off[l + 1];
+    for (int t = lo + tid; t < hi; t += nthr) {
+      const int i = ij[2 * t], j = ij[2 * t + 1];
+      const double vi = val[i], vj = val[j];
+      if (__dsub_rn(vi, vj) > pb.min_improve[i]) {  // dist_fun(evi.value, evj.value) > min_improve[i]
+        val[i] = vj;
+        val[j] = vi;
+        const unsigned short oi = own[i];
+        own[i] = own[j];
+        own[j] = oi;
+        exch[i] = (unsigned short)(j + 1);
+        exch[j] = (unsigned short)(i + 1);
+        ++n_swaps;
+      }
+    }
+    __syncthreads();
+  }
+  return n_swaps;
+}
+
+// swap_ev_ij! (:734-749) for one chain this rank owns: set_eval!(ci, ej) + set_exchanged!(ci, j).
+// One warp; `src` is the record that ended up on this chain.
+__device__ void exchange_apply_chain(const DevProblem &pb, const DevState &st, int iter, int c, int partner,
+                                     const double *src, int lane) {
+  const int P = pb.P, M = pb.M, R = rec_len(P, M), L = pb.L;
+  double *la = st.la_cur + (size_t)c * R;
+  const size_t slot = (size_t)(iter - 1) * L + c;
+  for (int k = lane; k < R; k += 32) {
+    const double v = __ldcg(src + k);
+    la[k] = v;
+    if (k >= 3 && k < 3 + P) st.t_params[slot * P + (k - 3)] = v;
+    if (k >= 3 + P) st.t_mom[slot * M + (k - 3 - P)] = v;
+  }
+  if (lane == 0) {
+    const double value = __ldcg(src);
+    // this iteration no longer counts towards the acceptance rate (exchanged != 0)
+    st.n_noex[c] = __ldcg(st.n_noex + c) - 1;
+    st.n_acc[c] = __ldcg(st.n_acc + c) - (int)__ldcg(st.t_acc + slot);
+    st.t_value[slot] = value;
+    st.t_prob[slot] = __ldcg(src + 1);
+    st.t_status[slot] = (int)__ldcg(src + 2);
+    st.t_acc[slot] = 1;  // the swapped-in eval is an accepted one
+    st.t_curr[slot] = value;
+    const double bprev = __ldcg(st.t_best + slot - L);
+    if (value < bprev) {
+      st.t_best[slot] = value;
+      st.t_bestid[slot] = iter;
+    } else {
+      st.t_best[slot] = bprev;
+      st.t_bestid[slot] = __ldcg(st.t_bestid + slot - L);
+    }
+    st.t_exch[slot] = partner;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (A) multi-launch mode
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, DevState st, int iter, int n_split,
+                                                                int part_len) {
+  __shared__ EvalSmem sm;
+  const int c = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
+  const int gc = pb.chain0 + c;
+  const size_t stamp = (size_t)c * n_split + split;
+  PHASE_STAMP(stamp, 0);
+  load_logtab(sm.logtab);
+  __syncthreads();
+  block_proposal(pb, st, sm, c, gc, iter, split == 0);
+  PHASE_STAMP(stamp, 1);
+  double *part_base = st.partials + (size_t)c * n_split * part_len;
+  if (pb.obj == SMM_OBJ_FAILS) {
+    if (split != 0) return;
+  } else {
+    if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
+    const int nb = (pb.S + 1) >> 1;
+    const int j0 = (int)(((long long)nb * split) / n_split), j1 = (int)(((long long)nb * (split + 1)) / n_split);
+    simulate_norm_segment(pb, sm, j0, j1, (uint32_t)gc, (uint32_t)iter, part_base + (size_t)split * part_len);
+    PHASE_STAMP(stamp, 2);
+    if (n_split > 1) {
+      if (tid == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(st.arrive + c, 1u);
+        sm.is_last = (prev == (unsigned)(n_split - 1));
+        if (sm.is_last) st.arrive[c] = 0u;  // re-arm for the next iteration
+        __threadfence();
+      }
+      __syncthreads();
+      if (!sm.is_last) return;
+    }
+  }
+  reduce_and_finalize(pb, sm, part_base, n_split, part_len);
+  accept_and_store(pb, st, sm, c, gc, iter, false);
+  PHASE_STAMP(stamp, 3);
+}
+
+// dynamic smem: val[N] (double) own[N] exch[N] (u16)
+__global__ void __launch_bounds__(kExchThreads) bgp_exchange_kernel(DevProblem pb, DevState st, int iter,
+                                                                    int sched_idx, int n_s) {
+  extern __shared__ double smem_d[];
+  const int N = pb.N, tid = threadIdx.x, nthr = blockDim.x;
+  const int R = rec_len(pb.P, pb.M), L = pb.L;
+  double *val = smem_d;
+  unsigned short *own = (unsigned short *)(val + N), *exch = own + N;
+  for (int i = tid; i < N; i += nthr) {
+    val[i] = st.la_all[(size_t)i * R];
+    own[i] = (unsigned short)i;
+    exch[i] = 0;
+  }
+  __syncthreads();
+  const unsigned n_swaps = exchange_levels(pb, st, sched_idx, n_s, val, own, exch);
+  if (pb.chain0 == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
+  for (int c = tid / 32; c < L; c += nthr / 32) {  // one warp per chain
+    const int gc = pb.chain0 + c;
+    const int partner = exch[gc];
+    if (partner == 0) continue;
+    exchange_apply_chain(pb, st, iter, c, partner, st.la_all + (size_t)own[gc] * R, tid & 31);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (B) persistent mode
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) { return *(const volatile unsigned *)p; }
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+  return *(const volatile unsigned long long *)p;
+}
+
+constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;  // 4 s: a stuck peer becomes an error, not a hang
+
+// Grid barrier (CTA 0 is the master).  With `cross`, the master also exchanges sequence flags with every
+// peer GPU before releasing, so the records stored into our gather buffer by the peers are complete.
+// Returns false if the kernel must abort (timeout somewhere).
+__device__ bool grid_barrier(const DevProblem &pb, const DevState &st, unsigned &gen, bool cross,
+                             unsigned long long &seq) {
+  __shared__ int s_ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool ok = true;
+    const unsigned G = gridDim.x;
+    const unsigned target = ++gen;
+    if (cross) {
+      ++seq;
+      __threadfence_system();  // this CTA's peer stores (all threads, ordered by the bar.sync above)
+    } else {
+      __threadfence();
+    }
+    if (blockIdx.x == 0) {
+      const unsigned long long t0 = gtimer();
+      unsigned spins = 0;
+      while (ld_volatile_u32(&st.bar->arrive) < G - 1) {
+        if ((++spins & 1023u) == 0 &&
+            (gtimer() - t0 > kSpinTimeoutNs || (*(volatile int *)st.err & kErrTimeout))) {
+          atomicOr(st.err, kErrTimeout);
+          ok = false;
+          break;
+        }
+      }
+      st.bar->arrive = 0;
+      if (cross && ok) {
+        __threadfence_system();
+        for (int r = 0; r < pb.world; ++r) *(volatile unsigned long long *)(st.peer_flags[r] + pb.rank) = seq;
+        for (int r = 0; r < pb.world && ok; ++r) {
+          spins = 0;
+          while (ld_volatile_u64(st.flags + r) < seq) {
+            if ((++spins & 1023u) == 0 && gtimer() - t0 > kSpinTimeoutNs) {
+              atomicOr(st.err, kErrTimeout);
+              ok = false;
+              break;
+            }
+          }
+        }
+        __threadfence_system();
+      }
+      __threadfence();
+      *(volatile unsigned *)&st.bar->gen = target;
+    } else {
+      atomicAdd(&st.bar->arrive, 1u);
+      const unsigned long long t0 = gtimer();
+      unsigned spins = 0;
+      while ((int)(ld_volatile_u32(&st.bar->gen) - target) < 0) {
+        if ((++spins & 1023u) == 0 && gtimer() - t0 > 2 * kSpinTimeoutNs) {
+          atomicOr(st.err, kErrTimeout);
+          break;
+        }
+      }
+    }
+    __threadfence();
+    if (*(volatile int *)st.err & kErrTimeout) ok = false;
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
+// block that holds flattened index x when T items are split evenly over G blocks: [floor(b*T/G), floor((b+1)*T/G))
+__device__ __forceinline__ long long block_of(long long x, long long T, long long G) {
+  return ((x + 1) * G + T - 1) / T - 1;
+}
+
+// exchange of iteration `pit` for the chains CTA b owns (replicated computation of the pair loop)
+__device__ void persistent_exchange(const DevProblem &pb, const DevState &st, int pit, int sched_iter0, int n_s,
+                                    bool fused, double *val, unsigned short *own, unsigned short *exch) {
+  const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
+  const int N = pb.N, L = pb.L, R = rec_len(pb.P, pb.M);
+  const int par = fused ? (pit & 1) : 0;
+  const double *la_all = st.la_all + (size_t)par * N * R;
+  const double *val_all = st.val_all + (size_t)par * N;
+  for (int i = tid; i < N; i += blockDim.x) {
+    val[i] = __ldcg(val_all + i);
+    own[i] = (unsigned short)i;
+    exch[i] = 0;
+  }
+  __syncthreads();
+  const unsigned n_swaps = exchange_levels(pb, st, pit - sched_iter0, n_s, val, own, exch);
+  if (b == 0 && pb.chain0 == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
+  for (int c = b; c < L; c += G) {
+    const int gc = pb.chain0 + c;
+    const int partner = exch[gc];
+    if (partner != 0 && tid < 32) exchange_apply_chain(pb, st, pit, c, partner, la_all + (size_t)own[gc] * R, tid);
+  }
+  __syncthreads();
+}
+
+// dynamic smem: val[N] (double) own[N] exch[N] (u16)
+__global__ void __launch_bounds__(kEvalThreads, 8) bgp_persistent_kernel(DevProblem pb, DevState st, int iter0,
+                                                                      int n_iters, int sched_iter0, int n_s,
+                                                                      int part_len, int max_seg) {
+  __shared__ EvalSmem sm;
+  extern __shared__ double smem_d[];
+  const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
+  const int N = pb.N, L = pb.L, P = pb.P, R = rec_len(pb.P, pb.M);
+  const bool fused = pb.world > 1;
+  double *val = smem_d;
+  unsigned short *own = (unsigned short *)(val + N), *exch = own + N;
+  load_logtab(sm.logtab);
+  unsigned gen = ld_volatile_u32(&st.bar->gen);
+  unsigned long long seq = ld_volatile_u64(st.sync_seq);
+  __syncthreads();
+  const int nb = (pb.S + 1) >> 1;
+  const long long T = (long long)L * nb;
+  const long long Gw = T < G ? T : G;  // CTAs that take a share of the draw space (all of them unless T is tiny)
+  const long long lo = b < Gw ? (T * b) / Gw : 0, hi = b < Gw ? (T * (b + 1)) / Gw : 0;
+  const bool owner = b < L;  // owner CTAs handle chains b, b + G, ...
+
+  for (int it = iter0; it < iter0 + n_iters; ++it) {
+    // ---- exchange of iteration it-1 (AlgoBGP.jl:637), then this iteration's proposals ----
+    if (owner) {
+      if (N > 1 && it - 1 >= 2 && it > iter0) persistent_exchange(pb, st, it - 1, sched_iter0, n_s, fused, val, own, exch);
+      for (int c = b; c < L; c += G) {
+        block_proposal(pb, st, sm, c, pb.chain0 + c, it, true);
+        for (int k = tid; k < P; k += blockDim.x) st.pp[(size_t)c * P + k] = sm.pp[k];
+        __syncthreads();
+      }
+    }
+    if (!grid_barrier(pb, st, gen, false, seq)) return;
+
+    // ---- an equal share of the flattened (chain, Philox block) space; finish the chains we complete ----
+    PHASE_STAMP(b * 2 + (it & 1), 0);
+    if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
+    for (long long x = lo; x < hi;) {
+      const int c = (int)(x / nb);
+      const long long cbase = (long long)c * nb;
+      const int j0 = (int)(x - cbase);
+      const long long xe = (cbase + nb < hi) ? cbase + nb : hi;
+      const int j1 = (int)(xe - cbase);
+      const int b_first = (int)block_of(cbase, T, Gw), b_last = (int)block_of(cbase + nb - 1, T, Gw);
+      const int n_seg = b_last - b_first + 1;
+      double *part_base = st.partials + (size_t)c * max_seg * part_len;
+      for (int k = tid; k < P; k += blockDim.x) sm.pp[k] = __ldcg(st.pp + (size_t)c * P + k);
+      __syncthreads();
+      if (pb.obj != SMM_OBJ_FAILS)
+        simulate_norm_segment(pb, sm, j0, j1, (uint32_t)(pb.chain0 + c), (uint32_t)it,
+                              part_base + (size_t)(b - b_first) * part_len);
+      PHASE_STAMP(b * 2 + (it & 1), 1);
+      if (tid == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(st.arrive + c, 1u);
+        sm.is_last = (prev == (unsigned)(n_seg - 1));
+        if (sm.is_last) st.arrive[c] = 0u;
+        __threadfence();
+      }
+      __syncthreads();
+      if (sm.is_last) {
+        reduce_and_finalize(pb, sm, part_base, n_seg, part_len);
+        accept_and_store(pb, st, sm, c, pb.chain0 + c, it, fused);
+      }
+      __syncthreads();
+      x = xe;
+    }
+    PHASE_STAMP(b * 2 + (it & 1), 2);
+    if (!grid_barrier(pb, st, gen, fused, seq)) return;
+    PHASE_STAMP(b * 2 + (it & 1), 3);
+  }
+  // ---- exchange of the last iteration of this launch ----
+  const int pit = iter0 + n_iters - 1;
+  if (owner && N > 1 && pit >= 2) persistent_exchange(pb, st, pit, sched_iter0, n_s, fused, val, own, exch);
+  if (b == 0 && tid == 0) *st.sync_seq = seq;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched bare objective: grid (n_split, B)  (evaluateObjective, mprob.jl:175-205)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEvalThreads) objective_kernel(DevProblem pb, const double *params, int noseed,
                                                                  uint32_t rep0, int n_split, int part_len,
                                                                  double *partials, unsigned *arrive, double *value,
                                                                  double *moments, int *status) {
   __shared__ EvalSmem sm;
-  const int b = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
+  const int bi = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
   load_logtab(sm.logtab);
-  for (int k = tid; k < pb.P; k += blockDim.x) sm.pp[k] = params[(size_t)b * pb.P + k];
+  for (int k = tid; k < pb.P; k += blockDim.x) sm.pp[k] = params[(size_t)bi * pb.P + k];
   __syncthreads();
   pb.noseed = noseed;
-  int ev_status = -1;
-  const bool last = objective_core(pb, sm, split, n_split, part_len, (uint32_t)b, rep0 + (uint32_t)b,
-                                   partials + (size_t)b * n_split * part_len, arrive + b, &ev_status);
-  if (!last) return;
-  if (tid == 0) {
-    value[b] = sm.value;
-    status[b] = ev_status;
+  double *part_base = partials + (size_t)bi * n_split * part_len;
+  if (pb.obj == SMM_OBJ_FAILS) {
+    if (split != 0) return;
+  } else {
+    if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
+    const int nb = (pb.S + 1) >> 1;
+    const int j0 = (int)(((long long)nb * split) / n_split), j1 = (int)(((long long)nb * (split + 1)) / n_split);
+    simulate_norm_segment(pb, sm, j0, j1, (uint32_t)bi, rep0 + (uint32_t)bi, part_base + (size_t)split * part_len);
+    if (n_split > 1) {
+      if (tid == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(arrive + bi, 1u);
+        sm.is_last = (prev == (unsigned)(n_split - 1));
+        if (sm.is_last) arrive[bi] = 0u;
+        __threadfence();
+      }
+      __syncthreads();
+      if (!sm.is_last) return;
+    }
   }
-  for (int k = tid; k < pb.M; k += blockDim.x) moments[(size_t)b * pb.M + k] = sm.mom[k];
+  reduce_and_finalize(pb, sm, part_base, n_split, part_len);
+  if (tid == 0) {
+    value[bi] = sm.value;
+    status[bi] = sm.status;
+  }
+  for (int k = tid; k < pb.M; k += blockDim.x) moments[(size_t)bi * pb.M + k] = sm.mom[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -479,85 +833,9 @@ __global__ void __launch_bounds__(kPairThreads) bgp_pairs_kernel(DevProblem pb, 
     int *ij = st.sched_ij + (size_t)it_idx * n_s * 2;
     for (int t = 0; t < n_s; ++t) {
       const int l = lvl[t];
-      const int pos = cnt[l]++;  // cnt[l] = running start of level l (levels are 1-based)
+      const int pos = cnt[l]++;
       ij[2 * pos] = pi[t];
       ij[2 * pos + 1] = pj[t];
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// exchangeMoves! (AlgoBGP.jl:647-691) + swap_ev_ij! (:734-749): replicated on every rank over the
-// gathered last-accepted records; each rank rewrites slot `iter` of the chains it owns.
-// dynamic smem: val[N] (double) own[N] exch[N] (int)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kExchThreads) bgp_exchange_kernel(DevProblem pb, DevState st, int iter,
-                                                                    int sched_idx, int n_s) {
-  extern __shared__ double smem_d[];
-  const int N = pb.N, tid = threadIdx.x, nthr = blockDim.x;
-  const int P = pb.P, M = pb.M, R = rec_len(P, M), L = pb.L;
-  double *val = smem_d;
-  int *own = (int *)(val + N), *exch = own + N;
-  for (int i = tid; i < N; i += nthr) {
-    val[i] = st.la_all[(size_t)i * R];
-    own[i] = i;
-    exch[i] = 0;
-  }
-  __syncthreads();
-  const int *ij = st.sched_ij + (size_t)sched_idx * n_s * 2;
-  const int *off = st.sched_off + (size_t)sched_idx * (n_s + 1);
-  const int nlev = st.sched_nlev[sched_idx];
-  unsigned n_swaps = 0;
-  for (int l = 0; l < nlev; ++l) {
-    const int lo = off[l], hi = off[l + 1];
-    for (int t = lo + tid; t < hi; t += nthr) {
-      const int i = ij[2 * t], j = ij[2 * t + 1];
-      const double vi = val[i], vj = val[j];
-      if (__dsub_rn(vi, vj) > pb.min_improve[i]) {  // dist_fun(evi.value, evj.value) > min_improve[i]
-        val[i] = vj;
-        val[j] = vi;
-        const int oi = own[i];
-        own[i] = own[j];
-        own[j] = oi;
-        exch[i] = j + 1;
-        exch[j] = i + 1;
-        ++n_swaps;
-      }
-    }
-    __syncthreads();
-  }
-  if (pb.chain0 == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
-  // rewrite the chains this rank owns that took part in a swap: set_eval!(ci, ej) + set_exchanged!
-  const size_t row = (size_t)(iter - 1) * L;
-  for (int c = tid / 32; c < L; c += nthr / 32) {  // one warp per chain
-    const int lane = tid & 31, gc = pb.chain0 + c;
-    const int partner = exch[gc];
-    if (partner == 0) continue;
-    const double *src = st.la_all + (size_t)own[gc] * R;
-    double *la = st.la_cur + (size_t)c * R;
-    for (int k = lane; k < R; k += 32) la[k] = src[k];
-    const size_t slot = row + c;
-    for (int k = lane; k < P; k += 32) st.t_params[slot * P + k] = src[3 + k];
-    for (int k = lane; k < M; k += 32) st.t_mom[slot * M + k] = src[3 + P + k];
-    if (lane == 0) {
-      const double value = src[0];
-      // this iteration no longer counts towards the acceptance rate (exchanged != 0)
-      st.n_noex[c] -= 1;
-      st.n_acc[c] -= (int)st.t_acc[slot];
-      st.t_value[slot] = value;
-      st.t_prob[slot] = src[1];
-      st.t_status[slot] = (int)src[2];
-      st.t_acc[slot] = 1;  // the swapped-in eval is an accepted one
-      st.t_curr[slot] = value;
-      const double bprev = st.t_best[slot - L];
-      if (value < bprev) {
-        st.t_best[slot] = value;
-        st.t_bestid[slot] = iter;
-      } else {
-        st.t_best[slot] = bprev;
-        st.t_bestid[slot] = st.t_bestid[slot - L];
-      }
-      st.t_exch[slot] = partner;
     }
   }
 }
@@ -597,19 +875,26 @@ __global__ void __launch_bounds__(kEvalThreads) rng_throughput_kernel(long long 
 // launchers (called from smm_api.cu)
 // ------------------------------------------------------------------------------------------------
 size_t pairs_smem_bytes(int N, int n_s) { return sizeof(unsigned) * ((size_t)5 * n_s + 2 + N); }
-size_t exch_smem_bytes(int N) { return sizeof(double) * (size_t)N + sizeof(int) * 2 * (size_t)N; }
+size_t exch_smem_bytes(int N) { return sizeof(double) * (size_t)N + sizeof(unsigned short) * 2 * (size_t)N; }
 
 cudaError_t configure_kernels(int N, int n_s) {
   cudaError_t e = cudaFuncSetAttribute(bgp_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)pairs_smem_bytes(N, n_s));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(bgp_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(bgp_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exch_smem_bytes(N));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(bgp_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)exch_smem_bytes(N));
 }
 
 int eval_max_blocks_per_sm() {
   int n = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bgp_eval_kernel, kEvalThreads, 0);
+  return n;
+}
+int persistent_max_blocks_per_sm(int N) {
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bgp_persistent_kernel, kEvalThreads, exch_smem_bytes(N));
   return n;
 }
 
@@ -622,6 +907,14 @@ void launch_pairs(const DevProblem &pb, const DevState &st, int iter0, int n_ite
 }
 void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sched_idx, int n_s, cudaStream_t s) {
   bgp_exchange_kernel<<<1, kExchThreads, exch_smem_bytes(pb.N), s>>>(pb, st, iter, sched_idx, n_s);
+}
+cudaError_t launch_persistent(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int sched_iter0,
+                              int n_s, int part_len, int max_seg, int grid, cudaStream_t s) {
+  DevProblem pbc = pb;
+  DevState stc = st;
+  void *args[] = {&pbc, &stc, &iter0, &n_iters, &sched_iter0, &n_s, &part_len, &max_seg};
+  return cudaLaunchCooperativeKernel((void *)bgp_persistent_kernel, dim3(grid), dim3(kEvalThreads), args,
+                                     exch_smem_bytes(pb.N), s);
 }
 void launch_objective(const DevProblem &pb, const double *params, int B, int noseed, uint32_t rep0, int n_split,
                       int part_len, double *partials, unsigned *arrive, double *value, double *moments, int *status,

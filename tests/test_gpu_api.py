@@ -42,7 +42,7 @@ def test_serial_normal_runs(oracle):
     s = api.summary(MA)
     assert list(s.columns) == ["id", "acc_rate", "perc_exchanged", "exchanged_most_with", "best_val"] and len(s) == 3
     v, idx = api.best(c)
-    assert v == ref.trace.value[:, 0].min() and idx == int(np.argmin(ref.trace.value[:, 0])) + 1
+    assert v == pytest.approx(ref.trace.value[:, 0].min(), rel=1e-9) and idx == int(np.argmin(ref.trace.value[:, 0])) + 1
     assert set(api.mean(c)) == {"p1", "p2"} and api.CI(c)["p1"].shape == (2,)
     assert len(api.allAccepted(c)) == int(ref.trace.accepted[:, 0].sum())
     MA.close()

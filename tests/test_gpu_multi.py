@@ -46,7 +46,7 @@ def _worker(rank, world, port, n_chains, n_iter, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", [0])
+@pytest.mark.parametrize("mode", [0, 1])
 def test_two_gpus_match_the_oracle(smm, oracle, mode):
     from smm_jl_b200 import configs
     if smm.device_count() < 2:
@@ -66,4 +66,5 @@ def test_two_gpus_match_the_oracle(smm, oracle, mode):
     ref = oracle.run(configs.mvnormal(n_chains, n_iter), n_iter, n_threads=8)
     assert_trace_parity(res[0][2], ref.trace)
     np.testing.assert_array_equal(res[0][3], ref.sigma)
-    assert res[0][4]["swaps"] == ref.swaps and res[0][4]["collectives"] == n_iter - 1
+    assert res[0][4]["swaps"] == ref.swaps
+    assert res[0][4]["collectives"] == (n_iter - 1 if mode == 0 else 0)

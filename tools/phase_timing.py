@@ -1,0 +1,38 @@
+"""Per-CTA phase stamps (debug aid).  mode 0: one evaluation-kernel launch; mode 1: the last two iterations
+of a persistent launch."""
+import os, sys
+os.environ["SMM_PHASE_TS"] = "1"
+sys.path.insert(0, ".")
+import numpy as np
+from smm_jl_b200 import configs, _lib
+chains = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+cfg = configs.mvnormal(chains, 200, exchange_mode=mode)
+pct = lambda a: tuple(np.percentile(a, [0, 50, 90, 100]))
+with _lib.BGPHandle(cfg) as h:
+    h.step(50)
+    if mode == 0:
+        h.step(1)
+        ts = h.phase_ts().astype(np.int64)
+        t0 = ts[:, 0].min()
+        start, prop, sim, end = [(ts[:, i] - t0) / 1e3 for i in range(4)]
+        print("proposal dur us: min %.1f med %.1f p90 %.1f max %.1f" % pct(prop - start))
+        print("simulate dur us: min %.1f med %.1f p90 %.1f max %.1f" % pct(sim - prop))
+        print("sim end      us: min %.1f med %.1f p90 %.1f max %.1f" % pct(sim))
+    else:
+        ms = h.step(100)
+        print("us/iter", ms * 10)
+        ts = h.phase_ts().astype(np.int64).reshape(-1, 2, 4)     # [block][parity][stamp]
+        last_par = h.iteration & 1
+        cur, prev = ts[:, last_par, :], ts[:, 1 - last_par, :]
+        t0 = prev[:, 0].min()
+        f = lambda a: (a - t0) / 1e3
+        print("prev iter: A start  us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 0])))
+        print("prev iter: first segment simulated us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 1])))
+        print("prev iter: A end    us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 2])))
+        print("prev iter: B2 exit  us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 3])))
+        print("last iter: A start  us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 0])))
+        print("last iter: A end    us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 2])))
+        print("last iter: B2 exit  us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 3])))
+        print("A duration per block us: min %.1f med %.1f p90 %.1f max %.1f" % pct((prev[:, 2] - prev[:, 0]) / 1e3))
+        print("X+P+B1 (B2 exit -> next A start) us: min %.1f med %.1f p90 %.1f max %.1f" % pct((cur[:, 0] - prev[:, 3]) / 1e3))
