@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--n-split", type=int, default=0)
-    ap.add_argument("--exchange-mode", type=int, default=0)
+    ap.add_argument("--exchange-mode", type=int, default=1, help="0 = one launch per iteration (+NCCL), 1 = persistent kernel (+fused peer all-gather)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -205,15 +205,19 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: this repo has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    nccl_id = b""
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def fresh_id() -> bytes:
+        """every handle owns a communicator: a new NCCL id per handle, made on rank 0, broadcast by torch"""
+        if world == 1:
+            return b""
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.tensor(list(_lib.nccl_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().tolist())
+        return bytes(idt.cpu().tolist())
 
     def barrier():
         if world > 1:
@@ -222,7 +226,7 @@ def main():
 
     K, W = args.steps, args.warmup
     cfg = bench_config(world, K + W)
-    cfg.device, cfg.world_size, cfg.rank, cfg.nccl_id = local_rank, world, rank, nccl_id
+    cfg.device, cfg.world_size, cfg.rank, cfg.nccl_id = local_rank, world, rank, fresh_id()
     cfg.n_split, cfg.exchange_mode = args.n_split, args.exchange_mode
     n_chains = cfg.n_chains
     L = n_chains // world
@@ -253,7 +257,7 @@ def main():
     # ---- per-kernel durations (separate short pass with event brackets around every launch) ------
     Kp = min(K, 300)
     cfgp = bench_config(world, Kp + W)
-    cfgp.device, cfgp.world_size, cfgp.rank, cfgp.nccl_id = local_rank, world, rank, nccl_id
+    cfgp.device, cfgp.world_size, cfgp.rank, cfgp.nccl_id = local_rank, world, rank, fresh_id()
     cfgp.n_split, cfgp.exchange_mode = args.n_split, args.exchange_mode
     barrier()
     hp = _lib.BGPHandle(cfgp)
@@ -262,22 +266,27 @@ def main():
     hp.step(Kp)
     kt = hp.kernel_times()
     hp.close()
-    eval_ms = kt["eval"][0] / max(kt["eval"][1], 1)
+    eval_ms = kt["eval"][0] / max(kt["eval"][1], 1)          # average duration of one launch of the dominant kernel
+    iters_per_launch = kt["eval_iterations"] / max(kt["eval"][1], 1)
     peak, peak_src = measured_peaks()
-    achieved = b_alg() * L / (eval_ms * 1e-3) / 1e9          # GB/s of algorithmic bytes per eval-kernel launch
+    # algorithmic bytes one launch processes: B_alg per evaluation x local chains x iterations in the launch
+    bytes_per_launch = b_alg() * L * iters_per_launch
+    achieved = bytes_per_launch / (eval_ms * 1e-3) / 1e9     # GB/s
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get("bgp_eval_kernel_dram_bytes_per_launch")
+                traffic = json.load(f).get(("bgp_persistent_kernel" if args.exchange_mode else "bgp_eval_kernel") + "_dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "bgp_eval_kernel",
-                "kernel_ms": eval_ms, "algorithmic_bytes_per_launch": b_alg() * L,
-                "kernel_share_of_step": kt["eval"][0] / max(sum(v[0] for v in kt.values()), 1e-12),
-                "other_kernels_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in kt.items() if k != "eval"},
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "bgp_persistent_kernel" if args.exchange_mode else "bgp_eval_kernel",
+                "kernel_ms": eval_ms, "iterations_per_launch": iters_per_launch,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "kernel_share_of_step": kt["eval"][0] / max(sum(kt[k][0] for k in ("eval", "exchange", "pairs", "allgather")), 1e-12),
+                "other_kernels_ms": {k: (kt[k][0] / kt[k][1] if kt[k][1] else None) for k in ("exchange", "pairs", "allgather")},
                 "note": "path is instruction-bound (Philox + fp64 Box-Muller), not HBM-bound: B_alg counts the reference's "
                         "draw matrix which the fused kernel never materialises (DESIGN.md)"}
 
@@ -293,7 +302,7 @@ def main():
     Ke = min(K, 500)
     opts = {"N": n_chains, "maxiter": Ke + W, "maxtemp": 5.0, "sigma": 0.05, "acc_tuners": list(np.asarray(cfg.acc_tuner)),
             "min_improve": [0.0] * n_chains, "seed": cfg.seed_algo, "device": local_rank, "world_size": world, "rank": rank,
-            "nccl_id": nccl_id, "n_split": args.n_split, "exchange_mode": args.exchange_mode}
+            "nccl_id": fresh_id(), "n_split": args.n_split, "exchange_mode": args.exchange_mode}
     pinned = {}
     barrier()
     t_create0 = time.perf_counter()
@@ -346,7 +355,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(world), "n_chains": n_chains, "chains_per_gpu": L, "n_params": N_PARAMS,
                        "n_moments": N_MOMENTS, "n_sim": N_SIM, "objective": "norm_mv (means + variances)",
-                       "parallelism": f"chains sharded over {world} GPU(s)" + (", ncclAllGather per iteration" if world > 1 else ""),
+                       "parallelism": f"chains sharded over {world} GPU(s)" + ((", all-gather fused into the persistent kernel (peer stores over NVLink)" if args.exchange_mode else ", ncclAllGather per iteration") if world > 1 else ""),
+                       "exchange_mode": args.exchange_mode,
                        "l2": "no input is re-read between iterations: every draw is generated in registers; the only "
                              "carried data is the chains' own state (~60 KB), which the algorithm's data dependence requires",
                        "normals_per_eval": N_PARAMS * N_SIM},
