@@ -179,6 +179,12 @@ int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij /* [n_pairs][2] in exe
 /* debug: per-CTA globaltimer stamps {start, after proposal, after simulate, end} of the last iteration;
  * needs SMM_PHASE_TS=1 in the environment at create time.  Returns n_split (>0) or an error. */
 int smm_debug_phase_ts(smm_bgp *h, uint64_t *out, int64_t n);
+/* n grid barriers back to back on one 1024-thread CTA per SM (variant 0 = the one the persistent kernel uses) */
+int smm_debug_barrier_bench(smm_bgp *h, int32_t variant, int32_t n, float *elapsed_ms);
+/* the simulate inner loop alone with this handle's keys/accumulators: blocks x threads CTAs, each thread
+ * n_pairs_per_thread Philox blocks; dynamic != 0 uses the shared-counter unit distribution of the persistent kernel */
+int smm_debug_sim_throughput(smm_bgp *h, int32_t n_pairs_per_thread, int32_t blocks, int32_t threads, int32_t dynamic,
+                             float *elapsed_ms);
 int smm_debug_rng_throughput(int32_t device, int64_t n_pairs_per_thread, int32_t blocks, int32_t threads,
                              float *elapsed_ms, double *checksum);
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "smm_bgp_read_trace", "smm_bgp_read_chain_state", "smm_bgp_get_counters", "smm_bgp_eval_batch",
     "smm_bgp_state_bytes", "smm_bgp_export_state", "smm_bgp_import_state", "smm_debug_normals",
     "smm_debug_pairs", "smm_debug_rng_throughput", "smm_stream_acc_uniforms", "smm_bgp_set_profiling",
-    "smm_bgp_kernel_times", "smm_debug_phase_ts",
+    "smm_bgp_kernel_times", "smm_debug_phase_ts", "smm_debug_sim_throughput", "smm_debug_barrier_bench",
 ]
 
 
@@ -72,6 +72,8 @@ def lib():
     L.smm_bgp_set_profiling.argtypes = [vp, C.c_int32]
     L.smm_bgp_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_int64)]
     L.smm_debug_phase_ts.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int64]
+    L.smm_debug_barrier_bench.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
+    L.smm_debug_sim_throughput.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -179,6 +181,18 @@ class BGPHandle:
         if nblk <= 0:
             check(nblk)
         return out[: nblk * 4].reshape(nblk, 4)
+
+    def barrier_bench(self, variant: int, n: int) -> float:
+        """microseconds per grid barrier"""
+        ms = C.c_float(0.0)
+        check(lib().smm_debug_barrier_bench(self._h, variant, n, C.byref(ms)))
+        return ms.value * 1e3 / n
+
+    def sim_throughput(self, n_pairs_per_thread: int, blocks: int, threads: int, dynamic: bool):
+        """the simulate inner loop alone: returns (ms, normals/s)"""
+        ms = C.c_float(0.0)
+        check(lib().smm_debug_sim_throughput(self._h, n_pairs_per_thread, blocks, threads, int(dynamic), C.byref(ms)))
+        return ms.value, 2.0 * n_pairs_per_thread * blocks * threads / (ms.value * 1e-3)
 
     def export_state(self) -> bytes:
         n = lib().smm_bgp_state_bytes(self._h)

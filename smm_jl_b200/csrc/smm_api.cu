@@ -19,9 +19,11 @@ size_t pairs_smem_bytes(int N, int n_s);
 size_t exch_smem_bytes(int N);
 cudaError_t configure_kernels(int N, int n_s);
 int eval_max_blocks_per_sm();
-int persistent_max_blocks_per_sm(int N);
+int persistent_max_blocks_per_sm(int N, int D, int M, int cta_seg);
+int persistent_max_cta_seg();
+cudaError_t configure_persistent(int N, int D, int M, int cta_seg);
 cudaError_t launch_persistent(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int sched_iter0,
-                              int n_s, int part_len, int max_seg, int grid, cudaStream_t s);
+                              int n_s, int part_len, int max_seg, int cta_seg, int grid, cudaStream_t s);
 void launch_eval(const DevProblem &pb, const DevState &st, int iter, int n_split, int part_len, cudaStream_t s);
 void launch_pairs(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int n_s, cudaStream_t s);
 void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sched_idx, int n_s, cudaStream_t s);
@@ -31,6 +33,9 @@ void launch_objective(const DevProblem &pb, const double *params, int B, int nos
 void launch_debug_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, double *out,
                           cudaStream_t s);
 void launch_rng_throughput(long long n_per_thread, int blocks, double *out, cudaStream_t s);
+cudaError_t launch_barrier_bench(const DevProblem &pb, const DevState &st, int variant, int n, int grid, cudaStream_t s);
+void launch_sim_throughput(const DevProblem &pb, int n_per_thread, int blocks, int threads, int dyn, double *out,
+                           cudaStream_t s);
 }  // namespace smm
 
 using namespace smm;
@@ -81,7 +86,7 @@ struct smm_bgp {
   int n_split = 1, part_len = 0;
   double eval_param_limit = 0.0;  // |param| bound for which the fixed-point accumulators are sized
   int mode = 0;           // 0 = multi-launch (+ NCCL), 1 = persistent kernel (+ fused peer-store all-gather)
-  int grid = 0, max_seg = 1;  // persistent kernel: CTAs, partial slots per chain
+  int grid = 0, max_seg = 1, cta_seg = 1;  // persistent kernel: CTAs, partial slots per chain, chains per CTA share
   void *peer_ptrs[3 * kMaxWorld] = {nullptr};  // IPC-opened peer buffers (closed in release)
   int iter = 0;      // iterations completed (algo.i)
   int sched_iter0 = -1, sched_n = 0;
@@ -344,11 +349,19 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     int coop = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
     if (!coop) return fail(SMM_E_CUDA, "device does not support cooperative launches (exchange_mode 1)");
-    int occ = persistent_max_blocks_per_sm(N);
-    if (occ < 1) return fail(SMM_E_CUDA, "persistent kernel does not fit on an SM");
-    if (cfg->n_split > 0 && cfg->n_split < occ) occ = cfg->n_split;  // n_split caps CTAs per SM in this mode
-    h->grid = prop.multiProcessorCount * occ;
-    const int per_chain = (h->grid + L - 1) / L + 1;
+    if (P > 32)
+      return fail(SMM_E_UNSUPPORTED_SHAPE, "exchange_mode 1 (persistent kernel) needs n_params <= 32; use exchange_mode 0");
+    h->grid = prop.multiProcessorCount;  // one 1024-thread CTA per SM
+    if (cfg->n_split > 0 && cfg->n_split < h->grid) h->grid = cfg->n_split;  // n_split caps the CTA count in this mode
+    const long long Tj = (long long)L * n_blocks_philox;
+    const long long gw = Tj < h->grid ? Tj : h->grid;
+    h->cta_seg = (int)((Tj / gw + 1 + n_blocks_philox - 1) / n_blocks_philox + 1);  // chains one CTA's share can touch
+    if (h->cta_seg > persistent_max_cta_seg())
+      return fail(SMM_E_UNSUPPORTED_SHAPE, "exchange_mode 1: too many chains per SM for the persistent kernel; use exchange_mode 0");
+    CUDA_TRY(configure_persistent(N, P, M, h->cta_seg));
+    if (persistent_max_blocks_per_sm(N, P, M, h->cta_seg) < 1)
+      return fail(SMM_E_CUDA, "persistent kernel does not fit on an SM");
+    const int per_chain = (int)((gw + L - 1) / L + 1);
     if (per_chain > h->max_seg) h->max_seg = per_chain;
   }
   if (int rc = fill(h->partials, (size_t)L * h->max_seg * h->part_len, 0.0)) return rc;
@@ -420,7 +433,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   st.phase_ts = nullptr;
   if (getenv("SMM_PHASE_TS")) {
     size_t slots = (size_t)L * h->n_split;
-    if ((size_t)h->grid * 2 > slots) slots = (size_t)h->grid * 2;
+    if ((size_t)h->grid * 4 > slots) slots = (size_t)h->grid * 4;
     if (int rc = fill(h->phase_ts, slots * 4, 0ull)) return rc;
     st.phase_ts = h->phase_ts.p;
   }
@@ -509,18 +522,27 @@ int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
     int left = n_iters;
     while (left > 0) {
       const int it0 = h->iter + 1;
-      const int n = left < kPairChunk ? left : kPairChunk;
-      const int s0 = it0 < 2 ? 2 : it0;  // first iteration whose exchange runs inside this launch
-      if (exchange && it0 + n - 1 >= 2) {
-        CUDA_TRY(prof_begin(2));
-        launch_pairs(h->pb, h->st, s0, it0 + n - s0, h->n_s, s);
-        CUDA_TRY(prof_end());
-        h->ctr.kernel_launches++;
+      int n = left < kPairChunk ? left : kPairChunk;
+      if (exchange) {
+        // the launch needs the schedules of exchanges max(it0, 2) .. it0 + n - 1: keep a window of kPairChunk
+        // iterations precomputed (one pairs launch per window, also across one-iteration step() calls)
+        const int first_ex = it0 < 2 ? 2 : it0;
+        if (it0 + n - 1 >= 2 &&
+            (h->sched_iter0 < 0 || first_ex < h->sched_iter0 || first_ex >= h->sched_iter0 + h->sched_n)) {
+          int w = h->max_iter - first_ex + 1;
+          if (w > kPairChunk) w = kPairChunk;
+          CUDA_TRY(prof_begin(2));
+          launch_pairs(h->pb, h->st, first_ex, w, h->n_s, s);
+          CUDA_TRY(prof_end());
+          h->ctr.kernel_launches++;
+          h->sched_iter0 = first_ex;
+          h->sched_n = w;
+        }
+        if (h->sched_iter0 >= 0 && it0 + n > h->sched_iter0 + h->sched_n) n = h->sched_iter0 + h->sched_n - it0;
       }
-      h->sched_iter0 = -1;
-      h->sched_n = 0;
       CUDA_TRY(prof_begin(0));
-      CUDA_TRY(launch_persistent(h->pb, h->st, it0, n, s0, h->n_s, h->part_len, h->max_seg, h->grid, s));
+      CUDA_TRY(launch_persistent(h->pb, h->st, it0, n, h->sched_iter0 < 0 ? 2 : h->sched_iter0, h->n_s, h->part_len,
+                                 h->max_seg, h->cta_seg, h->grid, s));
       CUDA_TRY(prof_end());
       h->prof_iters += h->profiling ? n : 0;
       h->ctr.kernel_launches++;
@@ -821,10 +843,44 @@ int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij, int32_t *level_offset
 int smm_debug_phase_ts(smm_bgp *h, uint64_t *out, int64_t n) {
   if (!h || !out) return fail(SMM_E_ARG, "null argument");
   if (!h->st.phase_ts) return fail(SMM_E_STATE, "set SMM_PHASE_TS=1 before smm_bgp_create");
-  const int64_t blocks = h->mode == 1 ? (int64_t)h->grid * 2 : (int64_t)h->L * h->n_split;
+  const int64_t blocks = h->mode == 1 ? (int64_t)h->grid * 4 : (int64_t)h->L * h->n_split;
   const int64_t have = blocks * 4;
   CUDA_TRY(cudaMemcpy(out, h->st.phase_ts, sizeof(uint64_t) * (n < have ? n : have), cudaMemcpyDeviceToHost));
   return (int)blocks;
+}
+
+int smm_debug_barrier_bench(smm_bgp *h, int32_t variant, int32_t n, float *elapsed_ms) {
+  if (!h || n < 1) return fail(SMM_E_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+  cudaStream_t s = h->stream;
+  CUDA_TRY(launch_barrier_bench(h->pb, h->st, variant, 10, prop.multiProcessorCount, s));
+  CUDA_TRY(cudaEventRecord(h->ev0, s));
+  CUDA_TRY(launch_barrier_bench(h->pb, h->st, variant, n, prop.multiProcessorCount, s));
+  CUDA_TRY(cudaEventRecord(h->ev1, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  return 0;
+}
+
+int smm_debug_sim_throughput(smm_bgp *h, int32_t n_pairs_per_thread, int32_t blocks, int32_t threads, int32_t dynamic,
+                             float *elapsed_ms) {
+  if (!h || threads < 32 || threads > 1024 || threads % 32 || blocks < 1) return fail(SMM_E_ARG, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  DevBuf<double> d;
+  CUDA_TRY(d.alloc((size_t)blocks * threads * 2));
+  cudaStream_t s = h->stream;
+  launch_sim_throughput(h->pb, n_pairs_per_thread, blocks, threads, dynamic, d.p, s);  // warm-up
+  CUDA_TRY(cudaEventRecord(h->ev0, s));
+  launch_sim_throughput(h->pb, n_pairs_per_thread, blocks, threads, dynamic, d.p, s);
+  CUDA_TRY(cudaEventRecord(h->ev1, s));
+  cudaError_t e = cudaStreamSynchronize(s);
+  d.free();
+  CUDA_TRY(e);
+  CUDA_TRY(cudaGetLastError());
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  return 0;
 }
 
 int smm_debug_rng_throughput(int32_t device, int64_t n_pairs_per_thread, int32_t blocks, int32_t threads,

@@ -8,7 +8,8 @@
 
 namespace smm {
 
-constexpr int kEvalThreads = 128;   // CTA size of the evaluation / persistent kernels
+constexpr int kEvalThreads = 128;   // CTA size of the evaluation kernel (multi-launch mode)
+constexpr int kPersistThreads = 1024;  // CTA size of the persistent kernel: one CTA per SM
 constexpr int kExchThreads = 512;   // CTA size of the stand-alone exchange kernel
 constexpr int kPairThreads = 256;   // CTA size of the pair-schedule kernel
 constexpr int kMaxSplit = 64;       // CTAs cooperating on one evaluation (multi-launch mode)

@@ -3,48 +3,104 @@
 // Two ways to run an iteration, same device functions, bit-identical results:
 //
 //  (A) multi-launch (exchange_mode 0):
-//      bgp_eval_kernel      grid (n_split, L): proposal -> simulate -> [last CTA of the chain] moments,
-//                           distance, accept/reject, trace.
+//      bgp_eval_kernel      grid (n_split, L) x 128 threads: proposal -> simulate -> [last CTA of the chain]
+//                           moments, distance, accept/reject, trace.
 //      [ncclAllGather of the last-accepted records when world > 1]
 //      bgp_exchange_kernel  exchangeMoves! on the gathered records.
 //
-//  (B) persistent (exchange_mode 1): bgp_persistent_kernel, one cooperative launch for up to kPairChunk
-//      iterations, one CTA set resident on every SM, two grid barriers per iteration:
-//        [owner CTAs: exchange of iteration i-1 (replicated), proposal of iteration i]      -- barrier --
-//        [all CTAs: an equal share of the flattened (chain, draw) space; the CTA that completes a
-//         chain finishes it (moments, distance, accept/reject, trace) and, with world > 1, stores the
-//         chain's record straight into every peer GPU's gather buffer over NVLink]         -- barrier,
+//  (B) persistent (exchange_mode 1): bgp_persistent_kernel, ONE cooperative launch for up to kPairChunk
+//      iterations, one 1024-thread CTA per SM, two grid barriers per iteration:
+//        [exchange of iteration i-1 (replicated per CTA), proposals of iteration i for the chains the
+//         CTA owns, several chains at a time in warp groups]                               -- barrier --
+//        [every CTA takes an equal share of the flattened (chain, draw) space; inside the CTA warps pull
+//         small units of draws from a shared-memory counter, so all 32 warps finish together whatever the
+//         warp scheduler favours; the CTA that completes a chain finishes it (moments, distance,
+//         accept/reject, trace) in one warp group while the other warps already simulate the next chain;
+//         with world > 1 the finished record is stored straight into every peer GPU's gather buffer
+//         over NVLink]                                                                      -- barrier,
 //         folded with a cross-GPU flag exchange: the all-gather costs no launch and no extra barrier --
 //
 // Reference lines: proposal AlgoBGP.jl:424-471 (mysample :400-410, mapto_01/ab mprob.jl:246-272);
 // objfunc_norm ObjExamples.jl:59-116; doAcceptReject! AlgoBGP.jl:324-392; set_eval! :220-245;
 // set_acceptRate! :253-257; exchangeMoves! :647-691; swap_ev_ij! :734-749; pair sample :653-656.
 //
-// Each thread owns one simulated dimension k and a strided set of Philox blocks, keeps its draws in
-// registers and accumulates in fp64; partial sums meet in shared memory, then (across CTAs) in a small
-// global buffer that the last-arriving CTA reduces in a fixed order, so results are deterministic.
+// Draws never touch memory: a thread owns one simulated dimension k, generates its normals in registers
+// (Philox4x32-10 + the fp64 Box-Muller of include/smm_stream.h) and adds them to ORDER-INVARIANT
+// accumulators (see simulate_*), so the result does not depend on how the draw space is cut up.
 #include "smm_device.cuh"
 
 namespace smm {
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory scratch of the evaluation CTA
+// thread groups: a CTA or a warp-aligned part of one, synchronised with a named barrier
 // ------------------------------------------------------------------------------------------------
-struct EvalSmem {
-  double pp[SMM_MAX_PARAMS];        // proposed parameter vector
-  double mu01[SMM_MAX_PARAMS];      // centre in unit-cube coordinates
-  double cand[2 * kEvalThreads];    // candidates of one round of attempts, [attempt][P]
-  double red[2 * kEvalThreads];     // per-thread partial sums
-  double tot[2 * SMM_MAX_PARAMS];   // totals over all segments
-  double mom[SMM_MAX_MOMENTS];      // simulated moments
-  smm_logent logtab[1 << SMM_LOG_BITS];
-  unsigned char okf[2 * kEvalThreads];
-  int first[SMM_MAX_PARAMS];        // per batch: first in-support attempt of this round
-  int resolved[SMM_MAX_PARAMS];     // per batch: attempts used (0 = unresolved)
-  int is_last;
-  int acc, status;
-  double value, prob;
+struct Grp {
+  int tid;  // index of this thread in the group
+  int n;    // threads in the group (multiple of 32)
+  int bar;  // named barrier id (0 = the CTA-wide barrier, i.e. __syncthreads when n == blockDim.x)
 };
+__device__ __forceinline__ void gsync(const Grp &g) {
+  if (g.n == 32)
+    __syncwarp();
+  else
+    asm volatile("bar.sync %0, %1;" ::"r"(g.bar), "r"(g.n) : "memory");
+}
+
+// scratch of one proposal (shared memory)
+struct PropScratch {
+  double *pp;              // [P]  out: proposed parameter vector
+  double *mu01;            // [P]
+  double *cand;            // [attempts per round][P]
+  unsigned char *okf;      // [attempts per round][P]
+  int *first;              // [P]  per batch: first in-support attempt of this round
+  int *resolved;           // [P]  per batch: attempts used (0 = unresolved)
+  const smm_logent *logtab;
+};
+
+// scratch of one finalisation (shared memory)
+struct FinScratch {
+  double *pp;    // [P]   parameters of the evaluation
+  double *tot;   // [2D]  totals
+  double *mom;   // [M]   simulated moments
+  double *value; // [2]   value, prob
+  int *flags;    // [2]   accepted, status
+};
+
+// acquire/release accesses (PTX memory model) -- lighter than __threadfence(), which is a sequentially
+// consistent fence plus an L1 invalidate; every cross-CTA read in this file bypasses L1 (__ldcg) anyway
+__device__ __forceinline__ void red_release_gpu(unsigned *p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atom_acq_rel_gpu(unsigned *p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned *p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -82,16 +138,16 @@ __device__ __forceinline__ smm_u32x4 philox_sim(const DevProblem &pb, uint32_t c
 }
 
 // ------------------------------------------------------------------------------------------------
-// proposal(c) -- AlgoBGP.jl:424-471.  Attempts are counter-indexed, so a round evaluates
-// blockDim/kp attempts at once and the lowest in-support attempt wins: identical to the reference's
-// sequential rejection loop.  Result in sm.pp.
+// proposal(c) -- AlgoBGP.jl:424-471.  Attempts are counter-indexed, so a round evaluates g.n/kp attempts
+// at once and the lowest in-support attempt wins: identical to the reference's sequential rejection loop.
+// Result in ps.pp.
 // ------------------------------------------------------------------------------------------------
-__device__ void block_proposal(const DevProblem &pb, const DevState &st, EvalSmem &sm, int c, int gc, int iter,
-                               bool count) {
-  const int P = pb.P, tid = threadIdx.x, nthr = blockDim.x;
+__device__ void group_proposal(const DevProblem &pb, const DevState &st, const Grp &g, const PropScratch &ps, int c,
+                               int gc, int iter, bool count) {
+  const int P = pb.P, tid = g.tid, nthr = g.n;
   if (iter == 1) {
-    for (int k = tid; k < P; k += nthr) sm.pp[k] = pb.init[k];
-    __syncthreads();
+    for (int k = tid; k < P; k += nthr) ps.pp[k] = pb.init[k];
+    gsync(g);
     return;
   }
   const int R = rec_len(pb.P, pb.M);
@@ -101,182 +157,188 @@ __device__ void block_proposal(const DevProblem &pb, const DevState &st, EvalSme
   const int A = nthr / kp;  // attempts per round
   const int bs = pb.batch_size, nb = P / bs;
   for (int k = tid; k < P; k += nthr) {
-    sm.mu01[k] = __ddiv_rn(__dsub_rn(__ldcg(la + 3 + k), pb.lb[k]), __dsub_rn(pb.ub[k], pb.lb[k]));
-    sm.pp[k] = 0.0;  // pp = zero(mu01) (:445)
+    ps.mu01[k] = __ddiv_rn(__dsub_rn(__ldcg(la + 3 + k), pb.lb[k]), __dsub_rn(pb.ub[k], pb.lb[k]));
+    ps.pp[k] = 0.0;  // pp = zero(mu01) (:445)
   }
-  for (int b = tid; b < nb; b += nthr) sm.resolved[b] = 0;
-  __syncthreads();
+  for (int b = tid; b < nb; b += nthr) ps.resolved[b] = 0;
+  gsync(g);
   int unresolved = nb;
   for (int base = 0; base < pb.smpl_iters && unresolved > 0; base += A) {
-    for (int b = tid; b < nb; b += nthr) sm.first[b] = 0x7fffffff;
+    for (int b = tid; b < nb; b += nthr) ps.first[b] = 0x7fffffff;
     if (tid < A * kp) {
       const int a_loc = tid / kp, kq = tid - a_loc * kp;
       const int a = base + a_loc;
       if (a < pb.smpl_iters) {
         double z0, z1;
         smm_normal_pair_tab(smm_prop_block(pb.seed_algo, (uint32_t)gc, (uint32_t)iter, (uint32_t)a, (uint32_t)kq),
-                            sm.logtab, &z0, &z1);
+                            ps.logtab, &z0, &z1);
         const int k0 = 2 * kq, k1 = k0 + 1;
-        const double x0 = __dadd_rn(sm.mu01[k0], __dmul_rn(sigma, z0));
-        sm.cand[a_loc * P + k0] = x0;
-        sm.okf[a_loc * P + k0] = (x0 >= 0.0) && (x0 <= 1.0);
+        const double x0 = __dadd_rn(ps.mu01[k0], __dmul_rn(sigma, z0));
+        ps.cand[a_loc * P + k0] = x0;
+        ps.okf[a_loc * P + k0] = (x0 >= 0.0) && (x0 <= 1.0);
         if (k1 < P) {
-          const double x1 = __dadd_rn(sm.mu01[k1], __dmul_rn(sigma, z1));
-          sm.cand[a_loc * P + k1] = x1;
-          sm.okf[a_loc * P + k1] = (x1 >= 0.0) && (x1 <= 1.0);
+          const double x1 = __dadd_rn(ps.mu01[k1], __dmul_rn(sigma, z1));
+          ps.cand[a_loc * P + k1] = x1;
+          ps.okf[a_loc * P + k1] = (x1 >= 0.0) && (x1 <= 1.0);
         }
       }
     }
-    __syncthreads();
+    gsync(g);
     for (int t = tid; t < A * nb; t += nthr) {
       const int a_loc = t / nb, b = t - a_loc * nb;
-      if (sm.resolved[b] == 0 && base + a_loc < pb.smpl_iters) {
+      if (ps.resolved[b] == 0 && base + a_loc < pb.smpl_iters) {
         bool ok = true;
-        for (int k = b * bs; k < (b + 1) * bs; ++k) ok = ok && sm.okf[a_loc * P + k];
-        if (ok) atomicMin(&sm.first[b], a_loc);
+        for (int k = b * bs; k < (b + 1) * bs; ++k) ok = ok && ps.okf[a_loc * P + k];
+        if (ok) atomicMin(&ps.first[b], a_loc);
       }
     }
-    __syncthreads();
+    gsync(g);
     for (int k = tid; k < P; k += nthr) {
       const int b = k / bs;
-      if (sm.resolved[b] == 0 && sm.first[b] != 0x7fffffff) sm.pp[k] = sm.cand[sm.first[b] * P + k];
+      if (ps.resolved[b] == 0 && ps.first[b] != 0x7fffffff) ps.pp[k] = ps.cand[ps.first[b] * P + k];
     }
     int still = 0;
     for (int b = 0; b < nb; ++b)  // every thread computes the same count (nb <= 64)
-      if (sm.resolved[b] == 0 && sm.first[b] == 0x7fffffff) ++still;
+      if (ps.resolved[b] == 0 && ps.first[b] == 0x7fffffff) ++still;
     unresolved = still;
-    __syncthreads();
+    gsync(g);
     for (int b = tid; b < nb; b += nthr)
-      if (sm.resolved[b] == 0 && sm.first[b] != 0x7fffffff) sm.resolved[b] = base + sm.first[b] + 1;
-    __syncthreads();
+      if (ps.resolved[b] == 0 && ps.first[b] != 0x7fffffff) ps.resolved[b] = base + ps.first[b] + 1;
+    gsync(g);
   }
   if (unresolved > 0 && nb == 1) {
     // single batch: `error("no draw in support ...")` (:409) aborts the run -> sticky error flag;
     // (several batches: the exception is logged and swallowed, pp[i] stays 0, :447-451)
     if (tid == 0) atomicOr(st.err, kErrExhausted);
-    for (int k = tid; k < P; k += nthr) sm.pp[k] = sm.mu01[k];
+    for (int k = tid; k < P; k += nthr) ps.pp[k] = ps.mu01[k];
   }
   if (count && tid == 0) {
     unsigned long long att = 0;
-    for (int b = 0; b < nb; ++b) att += sm.resolved[b] ? sm.resolved[b] : pb.smpl_iters;
+    for (int b = 0; b < nb; ++b) att += ps.resolved[b] ? ps.resolved[b] : pb.smpl_iters;
     atomicAdd(&st.counters[2], att);
   }
-  __syncthreads();
+  gsync(g);
   for (int k = tid; k < P; k += nthr)
-    sm.pp[k] = __dadd_rn(__dmul_rn(sm.pp[k], __dsub_rn(pb.ub[k], pb.lb[k])), pb.lb[k]);
-  __syncthreads();
+    ps.pp[k] = __dadd_rn(__dmul_rn(ps.pp[k], __dsub_rn(pb.ub[k], pb.lb[k])), pb.lb[k]);
+  gsync(g);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Simulation of the MvNormal objectives (ObjExamples.jl:76-79): X[k,s] = p_k + Z[k,s], reduced on the
-// fly to sum_s X and sum_s X^2 per row, for Philox blocks j in [j0, j1) of this evaluation.
-// Thread t owns row k = t % D and blocks j0 + t/D, +lanes, ...   Writes partial sums [2][D] to `part`.
+// fly to sum_s X and sum_s X^2 per row k, for Philox blocks j in [j0, j1) of an evaluation.
 //
 // ORDER-INVARIANT ACCUMULATION.  Every term is rounded once to a fixed-point grid (x -> x + M with
 // M = 1.5 * 2^(52-F): the low mantissa bits of the sum are round(x * 2^F)) and the 64-bit patterns are
-// added as integers, so the totals do not depend on how draws are split over threads, CTAs, launches or
-// GPUs: chains with equal parameters get bit-equal values (the exchange step compares values, ties must
+// added as integers, so the totals do not depend on how draws are split over threads, warps, CTAs, launches
+// or GPUs: chains with equal parameters get bit-equal values (the exchange step compares values; ties must
 // stay ties as in the sequential reference), and 1-GPU and N-GPU runs agree to the bit.  Grid error per
-// term <= 2^-(F+1) (F chosen by the host from S and the parameter box; ~2^-45 for the C2 shapes).
+// term <= 2^-(F+1), F chosen by the host from S and the parameter box (2^-43 / 2^-37 for the C2 shapes).
 // ------------------------------------------------------------------------------------------------
-__device__ void simulate_norm_segment(const DevProblem &pb, EvalSmem &sm, int j0, int j1, uint32_t uid, uint32_t rep,
-                                      double *part) {
-  const int D = pb.P, S = pb.S, tid = threadIdx.x;
-  const int lanes = blockDim.x / D;
+struct Acc {
+  unsigned long long sum, sq;  // sums of raw bit patterns; the n * bits(M) offset is removed at the end
+};
+
+__device__ __forceinline__ void add_pair(const DevProblem &pb, const smm_logent *logtab, Acc &a, double p, uint32_t j,
+                                         uint32_t k, uint32_t c2, uint32_t c3, bool both) {
+  double z0, z1;
+  smm_normal_pair_tab(philox_sim(pb, j, k, c2, c3), logtab, &z0, &z1);
+  const double x0 = __dadd_rn(p, z0);
+  a.sum += (unsigned long long)__double_as_longlong(__dadd_rn(x0, pb.magic_sum));
+  a.sq += (unsigned long long)__double_as_longlong(__fma_rn(x0, x0, pb.magic_sq));
+  if (both) {
+    const double x1 = __dadd_rn(p, z1);
+    a.sum += (unsigned long long)__double_as_longlong(__dadd_rn(x1, pb.magic_sum));
+    a.sq += (unsigned long long)__double_as_longlong(__fma_rn(x1, x1, pb.magic_sq));
+  }
+}
+
+// Static mapping, any D <= g.n: thread t owns row k = t % D and blocks j0 + t/D, +lanes, ...
+// red: shared [2 * g.n] u64.  Writes the group's partial sums [2][D] (u64 patterns) to `part`.
+__device__ void simulate_static(const DevProblem &pb, const Grp &g, const smm_logent *logtab, const double *pp, int j0,
+                                int j1, uint32_t uid, uint32_t rep, unsigned long long *red, double *part) {
+  const int D = pb.P, S = pb.S, tid = g.tid;
+  const int lanes = g.n / D;
   const int n_full = S >> 1;  // blocks whose two normals are both used
   const uint32_t c2 = pb.noseed ? uid : 0u;
   const uint32_t c3 = (SMM_STREAM_SIM << 28) | (pb.noseed ? (rep & SMM_ITER_MASK) : 0u);
-  const double Msum = pb.magic_sum, Msq = pb.magic_sq;
-  unsigned long long isum = 0ull, isq = 0ull;  // sums of raw bit patterns; the n*bits(M) offset leaves at the end
+  Acc a{0ull, 0ull};
   if (tid < lanes * D) {
     const int k = tid % D, ln = tid / D;
-    const double p = sm.pp[k];
+    const double p = pp[k];
     const int jend = j1 < n_full ? j1 : n_full;
-    for (int j = j0 + ln; j < jend; j += lanes) {
-      double z0, z1;
-      smm_normal_pair_tab(philox_sim(pb, (uint32_t)j, (uint32_t)k, c2, c3), sm.logtab, &z0, &z1);
-      const double x0 = __dadd_rn(p, z0);
-      const double x1 = __dadd_rn(p, z1);
-      isum += (unsigned long long)__double_as_longlong(__dadd_rn(x0, Msum));
-      isq += (unsigned long long)__double_as_longlong(__fma_rn(x0, x0, Msq));
-      isum += (unsigned long long)__double_as_longlong(__dadd_rn(x1, Msum));
-      isq += (unsigned long long)__double_as_longlong(__fma_rn(x1, x1, Msq));
-    }
-    if ((S & 1) && ln == 0 && j0 <= n_full && n_full < j1) {  // odd S: the last block contributes one draw
-      double z0, z1;
-      smm_normal_pair_tab(philox_sim(pb, (uint32_t)n_full, (uint32_t)k, c2, c3), sm.logtab, &z0, &z1);
-      const double x0 = __dadd_rn(p, z0);
-      isum += (unsigned long long)__double_as_longlong(__dadd_rn(x0, Msum));
-      isq += (unsigned long long)__double_as_longlong(__fma_rn(x0, x0, Msq));
-    }
+    for (int j = j0 + ln; j < jend; j += lanes) add_pair(pb, logtab, a, p, (uint32_t)j, (uint32_t)k, c2, c3, true);
+    if ((S & 1) && ln == 0 && j0 <= n_full && n_full < j1)  // odd S: the last block contributes one draw
+      add_pair(pb, logtab, a, p, (uint32_t)n_full, (uint32_t)k, c2, c3, false);
   }
-  unsigned long long *red = (unsigned long long *)sm.red;
-  red[2 * tid] = isum;
-  red[2 * tid + 1] = isq;
-  __syncthreads();
+  red[2 * tid] = a.sum;
+  red[2 * tid + 1] = a.sq;
+  gsync(g);
   if (tid < 2 * D) {
     const int k = tid % D, which = tid / D;
     unsigned long long acc = 0ull;
     for (int ln = 0; ln < lanes; ++ln) acc += red[2 * (ln * D + k) + which];
     ((unsigned long long *)part)[which * D + k] = acc;
   }
-  __syncthreads();
+  gsync(g);
 }
 
-// sum the n_seg partials of an evaluation (integer adds: exact), then moments + weighted distance
-__device__ void reduce_and_finalize(const DevProblem &pb, EvalSmem &sm, const double *part_base, int n_seg,
-                                    int part_len) {
-  const int D = pb.P, tid = threadIdx.x;
+constexpr int kUnitSteps = 4;  // warp steps per work unit of the persistent kernel (sim_throughput_kernel too)
+
+// Sum the n_seg partials of an evaluation (integer adds: exact), then moments + weighted distance.
+// Result in fs.mom, fs.value[0], fs.flags[1] (status).
+__device__ void group_finalize(const DevProblem &pb, const Grp &g, const FinScratch &fs, const double *part_base,
+                               int n_seg, int part_len) {
+  const int D = pb.P, tid = g.tid;
   if (pb.obj == SMM_OBJ_FAILS) {
     // the objective throws -> caught by evaluateObjective: status -2, value stays -1.0, no moments
-    for (int k = tid; k < pb.M; k += blockDim.x) sm.mom[k] = __longlong_as_double(0x7ff8000000000000ll);
+    for (int k = tid; k < pb.M; k += g.n) fs.mom[k] = __longlong_as_double(0x7ff8000000000000ll);
     if (tid == 0) {
-      sm.value = -1.0;
-      sm.status = -2;
+      fs.value[0] = -1.0;
+      fs.flags[1] = -2;
     }
-    __syncthreads();
+    gsync(g);
     return;
   }
-  if (tid < 2 * D) {
+  for (int e = tid; e < 2 * D; e += g.n) {
     unsigned long long acc = 0ull;
     const unsigned long long *pu = (const unsigned long long *)part_base;
-    for (int s = 0; s < n_seg; ++s) acc += __ldcg(pu + (size_t)s * part_len + tid);
+    for (int s = 0; s < n_seg; ++s) acc += __ldcg(pu + (size_t)s * part_len + e);
     // remove S copies of bits(M) (mod 2^64: exact), then fixed point -> double
-    const bool is_sq = tid >= D;
+    const bool is_sq = e >= D;
     const unsigned long long mb = (unsigned long long)__double_as_longlong(is_sq ? pb.magic_sq : pb.magic_sum);
     const long long fixed = (long long)(acc - (unsigned long long)pb.S * mb);
-    sm.tot[tid] = __dmul_rn((double)fixed, is_sq ? pb.scale_sq : pb.scale_sum);
+    fs.tot[e] = __dmul_rn((double)fixed, is_sq ? pb.scale_sq : pb.scale_sum);
   }
-  __syncthreads();
+  gsync(g);
   const double S = (double)pb.S;
-  if (tid < D) {
-    const double mean = __ddiv_rn(sm.tot[tid], S);
-    sm.mom[tid] = mean;
+  for (int k = tid; k < D; k += g.n) {
+    const double mean = __ddiv_rn(fs.tot[k], S);
+    fs.mom[k] = mean;
     if (pb.obj == SMM_OBJ_NORM_MV) {
       // sum (x - mean)^2 = sum x^2 - mean * sum x
-      const double ss = __dsub_rn(sm.tot[D + tid], __dmul_rn(mean, sm.tot[tid]));
-      sm.mom[D + tid] = __ddiv_rn(ss, S - 1.0);
+      const double ss = __dsub_rn(fs.tot[D + k], __dmul_rn(mean, fs.tot[k]));
+      fs.mom[D + k] = __ddiv_rn(ss, S - 1.0);
     }
   }
-  __syncthreads();
+  gsync(g);
   if (tid < 32) {  // value = mean_k ((sim_k - data_k) / w_k)^2, divisions in parallel, summed in moment order
     double acc = 0.0;
     for (int k0 = 0; k0 < pb.M; k0 += 32) {
       const int k = k0 + tid;
       double d2 = 0.0;
       if (k < pb.M) {
-        const double d = __ddiv_rn(__dsub_rn(sm.mom[k], pb.data[k]), pb.w[k]);
+        const double d = __ddiv_rn(__dsub_rn(fs.mom[k], pb.data[k]), pb.w[k]);
         d2 = __dmul_rn(d, d);
       }
       const int n = pb.M - k0 < 32 ? pb.M - k0 : 32;
       for (int l = 0; l < n; ++l) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, d2, l));
     }
     if (tid == 0) {
-      sm.value = __ddiv_rn(acc, (double)pb.M);
-      sm.status = 1;
+      fs.value[0] = __ddiv_rn(acc, (double)pb.M);
+      fs.flags[1] = 1;
     }
   }
-  __syncthreads();
+  gsync(g);
 }
 
 __device__ __forceinline__ void slow_spin(double seconds) {
@@ -288,27 +350,33 @@ __device__ __forceinline__ void slow_spin(double seconds) {
 
 // ------------------------------------------------------------------------------------------------
 // doAcceptReject! (AlgoBGP.jl:324-392) + set_eval! (:220-245) for chain c with the evaluation in
-// sm.value / sm.status / sm.mom / sm.pp.  Writes the trace slot, the last-accepted record (la_cur),
+// fs.value / fs.flags[1] / fs.mom / fs.pp.  Writes the trace slot, the last-accepted record (la_cur),
 // the published record (la_pub) and -- fused multi-GPU mode -- the record and its value into every
 // rank's gather buffer (peer stores over NVLink).
 // ------------------------------------------------------------------------------------------------
-__device__ void accept_and_store(const DevProblem &pb, const DevState &st, EvalSmem &sm, int c, int gc, int iter,
-                                 bool fused) {
-  const int tid = threadIdx.x;
+__device__ void group_accept_store(const DevProblem &pb, const DevState &st, const Grp &g, const FinScratch &fs, int c,
+                                   int gc, int iter, bool fused) {
+  const int tid = g.tid;
   const int P = pb.P, M = pb.M, R = rec_len(P, M), L = pb.L;
   double *la = st.la_cur + (size_t)c * R;
   double *pub = st.la_pub + (size_t)c * R;
   const size_t slot = (size_t)(iter - 1) * L + c;
   if (tid == 0) {
-    const double value = sm.value;
+    // everything this thread will need from global memory, requested at once (one L2 round trip)
+    const double old_value = __ldcg(la);
+    const int n_noex0 = __ldcg(st.n_noex + c), n_acc0 = __ldcg(st.n_acc + c);
+    const double sigma0 = __ldcg(st.sigma + c);
+    const size_t prev_slot = iter > 1 ? slot - L : slot;
+    const double curr_prev = __ldcg(st.t_curr + prev_slot), best_prev = __ldcg(st.t_best + prev_slot);
+    const int bestid_prev = __ldcg(st.t_bestid + prev_slot);
+    const double value = fs.value[0];
     double prob;
-    int accepted, status = sm.status;
+    int accepted, status = fs.flags[1];
     if (iter == 1) {
       prob = 1.0;
       accepted = 1;
       status = 1;
     } else {
-      const double old_value = __ldcg(la);
       if (status < 0) {
         prob = 0.0;
         accepted = 0;
@@ -330,15 +398,14 @@ __device__ void accept_and_store(const DevProblem &pb, const DevState &st, EvalS
       }
     }
     // set_acceptRate! (:253-257): this iteration has exchanged == 0 at this point
-    const int n_noex = __ldcg(st.n_noex + c) + 1, n_acc = __ldcg(st.n_acc + c) + accepted;
+    const int n_noex = n_noex0 + 1, n_acc = n_acc0 + accepted;
     st.n_noex[c] = n_noex;
     st.n_acc[c] = n_acc;
     const double rate = __ddiv_rn((double)n_acc, (double)n_noex);
     st.accept_rate[c] = rate;
     if (iter > 1 && iter % pb.sigma_update_steps == 0) {
-      const double s = __ldcg(st.sigma + c);
-      st.sigma[c] = rate > 0.234 ? __dmul_rn(s, __dadd_rn(1.0, pb.sigma_adjust_by))
-                                 : __dmul_rn(s, __dsub_rn(1.0, pb.sigma_adjust_by));
+      st.sigma[c] = rate > 0.234 ? __dmul_rn(sigma0, __dadd_rn(1.0, pb.sigma_adjust_by))
+                                 : __dmul_rn(sigma0, __dsub_rn(1.0, pb.sigma_adjust_by));
     }
     // set_eval!
     double curr, best;
@@ -348,15 +415,13 @@ __device__ void accept_and_store(const DevProblem &pb, const DevState &st, EvalS
       best = value;
       best_id = 1;
     } else {
-      const size_t prev = slot - L;
-      curr = accepted ? value : __ldcg(st.t_curr + prev);
-      const double bprev = __ldcg(st.t_best + prev);
-      if (value < bprev) {
+      curr = accepted ? value : curr_prev;
+      if (value < best_prev) {
         best = value;
         best_id = iter;
       } else {
-        best = bprev;
-        best_id = __ldcg(st.t_bestid + prev);
+        best = best_prev;
+        best_id = bestid_prev;
       }
     }
     st.t_value[slot] = value;
@@ -368,19 +433,20 @@ __device__ void accept_and_store(const DevProblem &pb, const DevState &st, EvalS
     st.t_exch[slot] = 0;
     st.t_bestid[slot] = best_id;
     if (accepted) atomicAdd(&st.counters[0], 1ull);
-    sm.acc = accepted;
-    sm.prob = prob;
-    sm.status = status;
+    fs.flags[0] = accepted;
+    fs.flags[1] = status;
+    fs.value[1] = prob;
   }
-  __syncthreads();
+  gsync(g);
+  const int acc = fs.flags[0];
   // trace rows + last-accepted record (coalesced over threads)
-  for (int k = tid; k < P; k += blockDim.x) st.t_params[slot * P + k] = sm.pp[k];
-  for (int k = tid; k < M; k += blockDim.x) st.t_mom[slot * M + k] = sm.mom[k];
+  for (int k = tid; k < P; k += g.n) st.t_params[slot * P + k] = fs.pp[k];
+  for (int k = tid; k < M; k += g.n) st.t_mom[slot * M + k] = fs.mom[k];
   const int par = fused ? (iter & 1) : 0;
-  for (int k = tid; k < R; k += blockDim.x) {
+  for (int k = tid; k < R; k += g.n) {
     double v;
-    if (sm.acc) {
-      v = k == 0 ? sm.value : k == 1 ? sm.prob : k == 2 ? (double)sm.status : k < 3 + P ? sm.pp[k - 3] : sm.mom[k - 3 - P];
+    if (acc) {
+      v = k == 0 ? fs.value[0] : k == 1 ? fs.value[1] : k == 2 ? (double)fs.flags[1] : k < 3 + P ? fs.pp[k - 3] : fs.mom[k - 3 - P];
       la[k] = v;
     } else {
       v = __ldcg(la + k);
@@ -395,23 +461,22 @@ __device__ void accept_and_store(const DevProblem &pb, const DevState &st, EvalS
       st.val_all[gc] = v;  // compact copy of the values for the exchange step
     }
   }
-  __syncthreads();
+  gsync(g);
 }
 
 // ------------------------------------------------------------------------------------------------
 // exchangeMoves! (AlgoBGP.jl:647-691): the sequential pair loop, run level-parallel over the schedule of
 // iteration `iter` (pairs inside a level share no chain).  val/own/exch live in shared memory.
 // ------------------------------------------------------------------------------------------------
-__device__ unsigned exchange_levels(const DevProblem &pb, const DevState &st, int sched_idx, int n_s, double *val,
-                                    unsigned short *own, unsigned short *exch) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
+__device__ unsigned exchange_levels(const DevProblem &pb, const DevState &st, const Grp &g, int sched_idx, int n_s,
+                                    double *val, unsigned short *own, unsigned short *exch) {
   const int *ij = st.sched_ij + (size_t)sched_idx * n_s * 2;
   const int *off = st.sched_off + (size_t)sched_idx * (n_s + 1);
   const int nlev = st.sched_nlev[sched_idx];
   unsigned n_swaps = 0;
   for (int l = 0; l < nlev; ++l) {
     const int lo = off[l], hi = off[l + 1];
-    for (int t = lo + tid; t < hi; t += nthr) {
+    for (int t = lo + g.tid; t < hi; t += g.n) {
       const int i = ij[2 * t], j = ij[2 * t + 1];
       const double vi = val[i], vj = val[j];
       if (__dsub_rn(vi, vj) > pb.min_improve[i]) {  // dist_fun(evi.value, evj.value) > min_improve[i]
@@ -425,7 +490,7 @@ __device__ unsigned exchange_levels(const DevProblem &pb, const DevState &st, in
         ++n_swaps;
       }
     }
-    __syncthreads();
+    gsync(g);
   }
   return n_swaps;
 }
@@ -444,22 +509,25 @@ __device__ void exchange_apply_chain(const DevProblem &pb, const DevState &st, i
     if (k >= 3 + P) st.t_mom[slot * M + (k - 3 - P)] = v;
   }
   if (lane == 0) {
-    const double value = __ldcg(src);
+    const double value = __ldcg(src), prob = __ldcg(src + 1), status = __ldcg(src + 2);
+    const int n_noex0 = __ldcg(st.n_noex + c), n_acc0 = __ldcg(st.n_acc + c);
+    const int acc0 = (int)__ldcg(st.t_acc + slot);
+    const double bprev = __ldcg(st.t_best + slot - L);
+    const int bidprev = __ldcg(st.t_bestid + slot - L);
     // this iteration no longer counts towards the acceptance rate (exchanged != 0)
-    st.n_noex[c] = __ldcg(st.n_noex + c) - 1;
-    st.n_acc[c] = __ldcg(st.n_acc + c) - (int)__ldcg(st.t_acc + slot);
+    st.n_noex[c] = n_noex0 - 1;
+    st.n_acc[c] = n_acc0 - acc0;
     st.t_value[slot] = value;
-    st.t_prob[slot] = __ldcg(src + 1);
-    st.t_status[slot] = (int)__ldcg(src + 2);
+    st.t_prob[slot] = prob;
+    st.t_status[slot] = (int)status;
     st.t_acc[slot] = 1;  // the swapped-in eval is an accepted one
     st.t_curr[slot] = value;
-    const double bprev = __ldcg(st.t_best + slot - L);
     if (value < bprev) {
       st.t_best[slot] = value;
       st.t_bestid[slot] = iter;
     } else {
       st.t_best[slot] = bprev;
-      st.t_bestid[slot] = __ldcg(st.t_bestid + slot - L);
+      st.t_bestid[slot] = bidprev;
     }
     st.t_exch[slot] = partner;
   }
@@ -468,16 +536,40 @@ __device__ void exchange_apply_chain(const DevProblem &pb, const DevState &st, i
 // ------------------------------------------------------------------------------------------------
 // (A) multi-launch mode
 // ------------------------------------------------------------------------------------------------
+struct EvalSmem {
+  double pp[SMM_MAX_PARAMS];
+  double mu01[SMM_MAX_PARAMS];
+  double cand[2 * kEvalThreads];
+  unsigned long long red[2 * kEvalThreads];
+  double tot[2 * SMM_MAX_PARAMS];
+  double mom[SMM_MAX_MOMENTS];
+  smm_logent logtab[1 << SMM_LOG_BITS];
+  unsigned char okf[2 * kEvalThreads];
+  int first[SMM_MAX_PARAMS];
+  int resolved[SMM_MAX_PARAMS];
+  double value[2];
+  int flags[2];
+  int is_last;
+};
+
+__device__ __forceinline__ PropScratch prop_scratch(EvalSmem &sm) {
+  return PropScratch{sm.pp, sm.mu01, sm.cand, sm.okf, sm.first, sm.resolved, sm.logtab};
+}
+__device__ __forceinline__ FinScratch fin_scratch(EvalSmem &sm) {
+  return FinScratch{sm.pp, sm.tot, sm.mom, sm.value, sm.flags};
+}
+
 __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, DevState st, int iter, int n_split,
                                                                 int part_len) {
   __shared__ EvalSmem sm;
   const int c = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
   const int gc = pb.chain0 + c;
+  const Grp g{tid, (int)blockDim.x, 0};
   const size_t stamp = (size_t)c * n_split + split;
   PHASE_STAMP(stamp, 0);
   load_logtab(sm.logtab);
   __syncthreads();
-  block_proposal(pb, st, sm, c, gc, iter, split == 0);
+  group_proposal(pb, st, g, prop_scratch(sm), c, gc, iter, split == 0);
   PHASE_STAMP(stamp, 1);
   double *part_base = st.partials + (size_t)c * n_split * part_len;
   if (pb.obj == SMM_OBJ_FAILS) {
@@ -486,7 +578,8 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, D
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
     const int nb = (pb.S + 1) >> 1;
     const int j0 = (int)(((long long)nb * split) / n_split), j1 = (int)(((long long)nb * (split + 1)) / n_split);
-    simulate_norm_segment(pb, sm, j0, j1, (uint32_t)gc, (uint32_t)iter, part_base + (size_t)split * part_len);
+    simulate_static(pb, g, sm.logtab, sm.pp, j0, j1, (uint32_t)gc, (uint32_t)iter, sm.red,
+                    part_base + (size_t)split * part_len);
     PHASE_STAMP(stamp, 2);
     if (n_split > 1) {
       if (tid == 0) {
@@ -500,8 +593,8 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, D
       if (!sm.is_last) return;
     }
   }
-  reduce_and_finalize(pb, sm, part_base, n_split, part_len);
-  accept_and_store(pb, st, sm, c, gc, iter, false);
+  group_finalize(pb, g, fin_scratch(sm), part_base, n_split, part_len);
+  group_accept_store(pb, st, g, fin_scratch(sm), c, gc, iter, false);
   PHASE_STAMP(stamp, 3);
 }
 
@@ -511,6 +604,7 @@ __global__ void __launch_bounds__(kExchThreads) bgp_exchange_kernel(DevProblem p
   extern __shared__ double smem_d[];
   const int N = pb.N, tid = threadIdx.x, nthr = blockDim.x;
   const int R = rec_len(pb.P, pb.M), L = pb.L;
+  const Grp g{tid, nthr, 0};
   double *val = smem_d;
   unsigned short *own = (unsigned short *)(val + N), *exch = own + N;
   for (int i = tid; i < N; i += nthr) {
@@ -519,7 +613,7 @@ __global__ void __launch_bounds__(kExchThreads) bgp_exchange_kernel(DevProblem p
     exch[i] = 0;
   }
   __syncthreads();
-  const unsigned n_swaps = exchange_levels(pb, st, sched_idx, n_s, val, own, exch);
+  const unsigned n_swaps = exchange_levels(pb, st, g, sched_idx, n_s, val, own, exch);
   if (pb.chain0 == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
   for (int c = tid / 32; c < L; c += nthr / 32) {  // one warp per chain
     const int gc = pb.chain0 + c;
@@ -539,9 +633,15 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 
 constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;  // 4 s: a stuck peer becomes an error, not a hang
 
-// Grid barrier (CTA 0 is the master).  With `cross`, the master also exchanges sequence flags with every
-// peer GPU before releasing, so the records stored into our gather buffer by the peers are complete.
-// Returns false if the kernel must abort (timeout somewhere).
+// Grid barrier (CTA 0 is the master).  Arrivals are release-adds (each CTA's writes become visible before its
+// arrival); the master waits for all of them, fences once (acquire for its own reads + release for the store
+// that follows) and publishes the new generation; the others spin on it with relaxed loads.  No fence on the
+// waiting side: everything a CTA reads after a barrier that another CTA wrote is fetched with ld.global.cg
+// (L2, never a stale L1 line) by instructions issued after the spin loop has seen the new generation.
+// Measured 2.0 us per barrier on 148 x 1024 threads (tools/barrier_bench.py) against 3.1 us with fences on
+// both sides.  The generation counter runs in the low 31 bits; bit 31 tells everybody to abort.
+// With `cross`, the master also exchanges sequence flags with every peer GPU (system scope) before
+// releasing, so the records stored into our gather buffer by the peers are complete.
 __device__ bool grid_barrier(const DevProblem &pb, const DevState &st, unsigned &gen, bool cross,
                              unsigned long long &seq) {
   __shared__ int s_ok;
@@ -549,55 +649,53 @@ __device__ bool grid_barrier(const DevProblem &pb, const DevState &st, unsigned 
   if (threadIdx.x == 0) {
     bool ok = true;
     const unsigned G = gridDim.x;
-    const unsigned target = ++gen;
+    gen = (gen + 1u) & 0x7fffffffu;
+    const unsigned target = gen;
     if (cross) {
       ++seq;
       __threadfence_system();  // this CTA's peer stores (all threads, ordered by the bar.sync above)
-    } else {
-      __threadfence();
     }
     if (blockIdx.x == 0) {
       const unsigned long long t0 = gtimer();
       unsigned spins = 0;
-      while (ld_volatile_u32(&st.bar->arrive) < G - 1) {
-        if ((++spins & 1023u) == 0 &&
-            (gtimer() - t0 > kSpinTimeoutNs || (*(volatile int *)st.err & kErrTimeout))) {
-          atomicOr(st.err, kErrTimeout);
+      while (ld_relaxed_gpu(&st.bar->arrive) < G - 1) {
+        if ((++spins & 4095u) == 0 && gtimer() - t0 > kSpinTimeoutNs) {
           ok = false;
           break;
         }
       }
-      st.bar->arrive = 0;
+      fence_acq_rel_gpu();
+      st_relaxed_gpu(&st.bar->arrive, 0u);
       if (cross && ok) {
-        __threadfence_system();
-        for (int r = 0; r < pb.world; ++r) *(volatile unsigned long long *)(st.peer_flags[r] + pb.rank) = seq;
+        for (int r = 0; r < pb.world; ++r) st_release_sys_u64(st.peer_flags[r] + pb.rank, seq);
         for (int r = 0; r < pb.world && ok; ++r) {
           spins = 0;
-          while (ld_volatile_u64(st.flags + r) < seq) {
+          while (ld_acquire_sys_u64(st.flags + r) < seq) {
             if ((++spins & 1023u) == 0 && gtimer() - t0 > kSpinTimeoutNs) {
-              atomicOr(st.err, kErrTimeout);
               ok = false;
               break;
             }
           }
         }
-        __threadfence_system();
+        fence_acq_rel_gpu();
       }
-      __threadfence();
-      *(volatile unsigned *)&st.bar->gen = target;
+      if (!ok) atomicOr(st.err, kErrTimeout);
+      st_relaxed_gpu(&st.bar->gen, ok ? target : (target | 0x80000000u));
     } else {
-      atomicAdd(&st.bar->arrive, 1u);
+      red_release_gpu(&st.bar->arrive, 1u);
       const unsigned long long t0 = gtimer();
-      unsigned spins = 0;
-      while ((int)(ld_volatile_u32(&st.bar->gen) - target) < 0) {
-        if ((++spins & 1023u) == 0 && gtimer() - t0 > 2 * kSpinTimeoutNs) {
+      unsigned spins = 0, g;
+      for (;;) {
+        g = ld_relaxed_gpu(&st.bar->gen);
+        if ((g & 0x80000000u) || (int)(((g & 0x7fffffffu) - target) << 1) >= 0) break;
+        if ((++spins & 4095u) == 0 && gtimer() - t0 > 2 * kSpinTimeoutNs) {
           atomicOr(st.err, kErrTimeout);
+          g = 0x80000000u;
           break;
         }
       }
+      if (g & 0x80000000u) ok = false;
     }
-    __threadfence();
-    if (*(volatile int *)st.err & kErrTimeout) ok = false;
     s_ok = ok;
   }
   __syncthreads();
@@ -609,9 +707,48 @@ __device__ __forceinline__ long long block_of(long long x, long long T, long lon
   return ((x + 1) * G + T - 1) / T - 1;
 }
 
-// exchange of iteration `pit` for the chains CTA b owns (replicated computation of the pair loop)
-__device__ void persistent_exchange(const DevProblem &pb, const DevState &st, int pit, int sched_iter0, int n_s,
-                                    bool fused, double *val, unsigned short *own, unsigned short *exch) {
+constexpr int kPGroups = 8;                      // proposal groups per CTA (128 threads each at most)
+constexpr int kPropCand = 2 * kPersistThreads;   // candidate slots shared by the groups
+constexpr int kMaxCtaSeg = 32;                   // chains (segments) one CTA may touch per iteration
+
+struct PersistSmem {
+  smm_logent logtab[1 << SMM_LOG_BITS];
+  // segment geometry of this CTA's share (iteration invariant)
+  int n_seg, total_units;
+  int seg_c[kMaxCtaSeg], seg_j0[kMaxCtaSeg], seg_j1[kMaxCtaSeg], seg_unit0[kMaxCtaSeg + 1];
+  int seg_slot[kMaxCtaSeg], seg_nseg[kMaxCtaSeg];   // partial slot of this CTA / CTAs sharing the chain
+  // per-iteration work queue
+  int next_unit;
+  int done[kMaxCtaSeg];
+  int nlev;  // levels of the prefetched exchange schedule
+  // proposals
+  double g_pp[kPGroups][SMM_MAX_PARAMS];
+  double g_mu01[kPGroups][SMM_MAX_PARAMS];
+  double cand[kPropCand];
+  unsigned char okf[kPropCand];
+  int g_first[kPGroups][SMM_MAX_PARAMS];
+  int g_resolved[kPGroups][SMM_MAX_PARAMS];
+};
+
+// Level schedule of exchange `pit` -> shared memory (called at the start of phase A of iteration pit, far
+// from the critical path).  dynamic smem: sij[n_s] u32 (i | j << 16) | soff[n_s + 1] i32
+__device__ __forceinline__ void prefetch_schedule(const DevState &st, int pit, int sched_iter0, int n_s, unsigned *sij,
+                                                  int *soff, int *nlev_out) {
+  const int sidx = pit - sched_iter0;
+  const int *ij = st.sched_ij + (size_t)sidx * n_s * 2;
+  const int *off = st.sched_off + (size_t)sidx * (n_s + 1);
+  for (int t = threadIdx.x; t < n_s; t += blockDim.x) sij[t] = (unsigned)ij[2 * t] | ((unsigned)ij[2 * t + 1] << 16);
+  for (int t = threadIdx.x; t <= n_s; t += blockDim.x) soff[t] = off[t];
+  if (threadIdx.x == 0) *nlev_out = st.sched_nlev[sidx];
+}
+
+// exchange of iteration `pit` for the chains this CTA owns.  The pair loop is replicated in every owner CTA
+// on the prefetched schedule: only the N values come from L2 here; one warp walks the levels (a __syncwarp
+// per level), then one warp per owned chain applies the outcome.
+// dynamic smem (persistent kernel): val[N] f64 | own[N] exch[N] u16 | sij | soff
+__device__ void persistent_exchange(const DevProblem &pb, const DevState &st, int pit, bool fused, double *val,
+                                    unsigned short *own, unsigned short *exch, const unsigned *sij, const int *soff,
+                                    int nlev) {
   const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
   const int N = pb.N, L = pb.L, R = rec_len(pb.P, pb.M);
   const int par = fused ? (pit & 1) : 0;
@@ -623,89 +760,239 @@ __device__ void persistent_exchange(const DevProblem &pb, const DevState &st, in
     exch[i] = 0;
   }
   __syncthreads();
-  const unsigned n_swaps = exchange_levels(pb, st, pit - sched_iter0, n_s, val, own, exch);
-  if (b == 0 && pb.chain0 == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
-  for (int c = b; c < L; c += G) {
+  if (tid < 32) {
+    unsigned n_swaps = 0;
+    for (int l = 0; l < nlev; ++l) {
+      const int lo = soff[l], hi = soff[l + 1];
+      for (int t = lo + tid; t < hi; t += 32) {
+        const int i = (int)(sij[t] & 0xffffu), j = (int)(sij[t] >> 16);
+        const double vi = val[i], vj = val[j];
+        if (__dsub_rn(vi, vj) > pb.min_improve[i]) {  // dist_fun(evi.value, evj.value) > min_improve[i]
+          val[i] = vj;
+          val[j] = vi;
+          const unsigned short oi = own[i];
+          own[i] = own[j];
+          own[j] = oi;
+          exch[i] = (unsigned short)(j + 1);
+          exch[j] = (unsigned short)(i + 1);
+          ++n_swaps;
+        }
+      }
+      __syncwarp();
+    }
+    if (b == 0 && pb.chain0 == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
+  }
+  __syncthreads();
+  const int warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int c = b + warp * G; c < L; c += nwarps * G) {  // one warp per owned chain
     const int gc = pb.chain0 + c;
     const int partner = exch[gc];
-    if (partner != 0 && tid < 32) exchange_apply_chain(pb, st, pit, c, partner, la_all + (size_t)own[gc] * R, tid);
+    if (partner != 0) exchange_apply_chain(pb, st, pit, c, partner, la_all + (size_t)own[gc] * R, tid & 31);
   }
   __syncthreads();
 }
 
-// dynamic smem: val[N] (double) own[N] exch[N] (u16)
-__global__ void __launch_bounds__(kEvalThreads, 8) bgp_persistent_kernel(DevProblem pb, DevState st, int iter0,
-                                                                      int n_iters, int sched_iter0, int n_s,
-                                                                      int part_len, int max_seg) {
-  __shared__ EvalSmem sm;
+// One warp completes segment s of its CTA: publish the CTA's exact partial sums; if this was the last CTA of
+// the chain, finish the chain (moments, distance, accept/reject, trace, record) -- all inside the warp, while
+// the other 31 warps keep simulating.
+__device__ void warp_publish_segment(const DevProblem &pb, const DevState &st, PersistSmem &sm, int s, int it,
+                                     bool fused, int part_len, int max_seg, const unsigned long long *acc,
+                                     double *pp_seg, double *fscratch, int fs_len) {
+  const int lane = threadIdx.x & 31, D = pb.P;
+  const int c = sm.seg_c[s];
+  double *part_base = st.partials + (size_t)c * max_seg * part_len;
+  unsigned long long *part = (unsigned long long *)(part_base + (size_t)sm.seg_slot[s] * part_len);
+  for (int e = lane; e < 2 * D; e += 32) part[e] = acc[(size_t)s * 2 * D + e];
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    const unsigned prev = atom_acq_rel_gpu(st.arrive + c, 1u);  // releases the warp's partial, acquires the others'
+    last = (prev == (unsigned)(sm.seg_nseg[s] - 1));
+    if (last) st_relaxed_gpu(st.arrive + c, 0u);  // re-arm (ordered before the next iteration by the grid barrier)
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  double *f = fscratch + (size_t)s * fs_len;
+  const FinScratch fs{pp_seg + (size_t)s * D, f, f + 2 * D, f + 2 * D + pb.M, (int *)(f + 2 * D + pb.M + 2)};
+  const Grp gw{lane, 32, 0};
+  group_finalize(pb, gw, fs, part_base, sm.seg_nseg[s], part_len);
+  group_accept_store(pb, st, gw, fs, c, pb.chain0 + c, it, fused);
+}
+
+// dynamic smem: val[N] (double) own[N] exch[N] (u16) | pp_seg[n][D] | acc[n][2D] (u64) | fscratch[n][2D+M+4]
+__global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevProblem pb, DevState st, int iter0,
+                                                                            int n_iters, int sched_iter0, int n_s,
+                                                                            int part_len, int max_seg, int cta_seg) {
+  __shared__ PersistSmem sm;
   extern __shared__ double smem_d[];
   const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
-  const int N = pb.N, L = pb.L, P = pb.P, R = rec_len(pb.P, pb.M);
+  const int lane = tid & 31;
+  const int N = pb.N, L = pb.L, P = pb.P, D = pb.P, S = pb.S;
   const bool fused = pb.world > 1;
   double *val = smem_d;
   unsigned short *own = (unsigned short *)(val + N), *exch = own + N;
+  const int fs_len = 2 * D + pb.M + 4;
+  unsigned *sij = (unsigned *)(own + 2 * N);  // [n_s]
+  int *soff = (int *)(sij + n_s);             // [n_s + 1]
+  double *pp_seg = val + N + (N + 1) / 2 + (n_s + 1);  // u16 arrays = N/2 doubles, schedule = n_s + 1/2 doubles
+  unsigned long long *acc = (unsigned long long *)(pp_seg + (size_t)cta_seg * D);
+  double *fscratch = (double *)(acc + (size_t)cta_seg * 2 * D);
   load_logtab(sm.logtab);
-  unsigned gen = ld_volatile_u32(&st.bar->gen);
+  unsigned gen = ld_volatile_u32(&st.bar->gen) & 0x7fffffffu;
   unsigned long long seq = ld_volatile_u64(st.sync_seq);
-  __syncthreads();
-  const int nb = (pb.S + 1) >> 1;
+  const int nb = (S + 1) >> 1;
+  const int n_full = S >> 1;
   const long long T = (long long)L * nb;
   const long long Gw = T < G ? T : G;  // CTAs that take a share of the draw space (all of them unless T is tiny)
   const long long lo = b < Gw ? (T * b) / Gw : 0, hi = b < Gw ? (T * (b + 1)) / Gw : 0;
-  const bool owner = b < L;  // owner CTAs handle chains b, b + G, ...
+  const int rows = 32 / D;                // Philox blocks one warp step covers (lanes >= rows*D idle if D does not divide 32)
+  const int unit_j = rows * kUnitSteps;   // blocks per work unit
+  if (tid == 0) {                         // this CTA's segments: one per chain its share touches
+    int n = 0, u0 = 0;
+    for (long long x = lo; x < hi && n < kMaxCtaSeg;) {
+      const int c = (int)(x / nb);
+      const long long cbase = (long long)c * nb;
+      const long long xe = (cbase + nb < hi) ? cbase + nb : hi;
+      const int b_first = (int)block_of(cbase, T, Gw), b_last = (int)block_of(cbase + nb - 1, T, Gw);
+      sm.seg_c[n] = c;
+      sm.seg_j0[n] = (int)(x - cbase);
+      sm.seg_j1[n] = (int)(xe - cbase);
+      sm.seg_unit0[n] = u0;
+      sm.seg_slot[n] = b - b_first;
+      sm.seg_nseg[n] = b_last - b_first + 1;
+      u0 += (sm.seg_j1[n] - sm.seg_j0[n] + unit_j - 1) / unit_j;
+      ++n;
+      x = xe;
+    }
+    sm.seg_unit0[n] = u0;
+    sm.n_seg = n;
+    sm.total_units = u0;
+  }
+  __syncthreads();
+  const int n_seg = sm.n_seg, total_units = sm.total_units;
+  const int n_owned = b < L ? (L - b + G - 1) / G : 0;  // chains b, b + G, ...
+  // proposal groups: as many threads per chain as the CTA can spare (more attempts per round)
+  int ngroups = 1;
+  while (ngroups < n_owned && ngroups < kPGroups) ngroups <<= 1;
+  const int gsize = kPersistThreads / ngroups;
+  const int gi = tid / gsize;
+  const Grp gprop{tid - gi * gsize, gsize, 1 + gi};
+  const int cand_per_group = kPropCand / ngroups;
+  const PropScratch ps{sm.g_pp[gi], sm.g_mu01[gi], sm.cand + (size_t)gi * cand_per_group,
+                       sm.okf + (size_t)gi * cand_per_group, sm.g_first[gi], sm.g_resolved[gi], sm.logtab};
+  const int k = lane % D, jo = lane / D;
+  const bool lane_on = lane < rows * D;
 
   for (int it = iter0; it < iter0 + n_iters; ++it) {
     // ---- exchange of iteration it-1 (AlgoBGP.jl:637), then this iteration's proposals ----
-    if (owner) {
-      if (N > 1 && it - 1 >= 2 && it > iter0) persistent_exchange(pb, st, it - 1, sched_iter0, n_s, fused, val, own, exch);
-      for (int c = b; c < L; c += G) {
-        block_proposal(pb, st, sm, c, pb.chain0 + c, it, true);
-        for (int k = tid; k < P; k += blockDim.x) st.pp[(size_t)c * P + k] = sm.pp[k];
-        __syncthreads();
+    if (n_owned > 0) {
+      if (N > 1 && it - 1 >= 2 && it > iter0) persistent_exchange(pb, st, it - 1, fused, val, own, exch, sij, soff, sm.nlev);
+      PHASE_STAMP((b * 2 + (it & 1)) * 2 + 1, 0);  // exchange done
+      for (int r = 0; r * ngroups < n_owned; ++r) {
+        const int o = r * ngroups + gi;  // index among the owned chains
+        if (o < n_owned) {
+          const int c = b + o * G;
+          group_proposal(pb, st, gprop, ps, c, pb.chain0 + c, it, true);
+          for (int q = gprop.tid; q < P; q += gsize) st.pp[(size_t)c * P + q] = ps.pp[q];
+        }
       }
     }
+    PHASE_STAMP((b * 2 + (it & 1)) * 2 + 1, 1);  // proposals done (group 0)
     if (!grid_barrier(pb, st, gen, false, seq)) return;
 
-    // ---- an equal share of the flattened (chain, Philox block) space; finish the chains we complete ----
-    PHASE_STAMP(b * 2 + (it & 1), 0);
+    // ---- phase A: this CTA's share of the flattened (chain, Philox block) space as a warp-level work queue ----
+    PHASE_STAMP((b * 2 + (it & 1)) * 2, 0);
+    for (int e = tid; e < n_seg * D; e += kPersistThreads) pp_seg[e] = __ldcg(st.pp + (size_t)sm.seg_c[e / D] * P + e % D);
+    for (int e = tid; e < n_seg * 2 * D; e += kPersistThreads) acc[e] = 0ull;
+    if (tid < n_seg) sm.done[tid] = 0;
+    if (tid == 0) sm.next_unit = 0;
+    if (n_owned > 0 && N > 1 && it >= 2) prefetch_schedule(st, it, sched_iter0, n_s, sij, soff, &sm.nlev);
+    __syncthreads();
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
-    for (long long x = lo; x < hi;) {
-      const int c = (int)(x / nb);
-      const long long cbase = (long long)c * nb;
-      const int j0 = (int)(x - cbase);
-      const long long xe = (cbase + nb < hi) ? cbase + nb : hi;
-      const int j1 = (int)(xe - cbase);
-      const int b_first = (int)block_of(cbase, T, Gw), b_last = (int)block_of(cbase + nb - 1, T, Gw);
-      const int n_seg = b_last - b_first + 1;
-      double *part_base = st.partials + (size_t)c * max_seg * part_len;
-      for (int k = tid; k < P; k += blockDim.x) sm.pp[k] = __ldcg(st.pp + (size_t)c * P + k);
-      __syncthreads();
-      if (pb.obj != SMM_OBJ_FAILS)
-        simulate_norm_segment(pb, sm, j0, j1, (uint32_t)(pb.chain0 + c), (uint32_t)it,
-                              part_base + (size_t)(b - b_first) * part_len);
-      PHASE_STAMP(b * 2 + (it & 1), 1);
-      if (tid == 0) {
-        __threadfence();
-        const unsigned prev = atomicAdd(st.arrive + c, 1u);
-        sm.is_last = (prev == (unsigned)(n_seg - 1));
-        if (sm.is_last) st.arrive[c] = 0u;
-        __threadfence();
+    {
+      const uint32_t c3base = SMM_STREAM_SIM << 28;
+      int cur = -1, units_cur = 0, j0 = 0, jfull = 0, j1 = 0;
+      uint32_t c2 = 0u, c3 = c3base;
+      double p = 0.0;
+      Acc a{0ull, 0ull};
+      int next = 0;
+      if (lane == 0) next = atomicAdd(&sm.next_unit, 1);
+      next = __shfl_sync(0xffffffffu, next, 0);
+      for (;;) {
+        const int u = next;
+        int s = cur;
+        if (u < total_units) {
+          if (s < 0 || u >= sm.seg_unit0[s + 1]) {
+            s = s < 0 ? 0 : s + 1;
+            while (u >= sm.seg_unit0[s + 1]) ++s;
+          }
+        } else {
+          s = -1;
+        }
+        if (s != cur) {
+          if (cur >= 0) {  // leave segment `cur`: add this warp's exact sums to the CTA's, count its units
+            for (int r = 1; r < rows; ++r) {
+              const unsigned long long os = __shfl_down_sync(0xffffffffu, a.sum, r * D);
+              const unsigned long long oq = __shfl_down_sync(0xffffffffu, a.sq, r * D);
+              if (lane < D) {
+                a.sum += os;
+                a.sq += oq;
+              }
+            }
+            if (lane < D) {
+              atomicAdd(acc + (size_t)cur * 2 * D + lane, a.sum);
+              atomicAdd(acc + (size_t)cur * 2 * D + D + lane, a.sq);
+            }
+            __syncwarp();
+            int complete = 0;
+            if (lane == 0) {
+              __threadfence_block();
+              const int n_units = sm.seg_unit0[cur + 1] - sm.seg_unit0[cur];
+              complete = (atomicAdd(&sm.done[cur], units_cur) + units_cur == n_units);
+              if (complete) __threadfence_block();
+            }
+            complete = __shfl_sync(0xffffffffu, complete, 0);
+            if (complete)
+              warp_publish_segment(pb, st, sm, cur, it, fused, part_len, max_seg, acc, pp_seg, fscratch, fs_len);
+          }
+          cur = s;
+          if (s >= 0) {
+            units_cur = 0;
+            a.sum = 0ull;
+            a.sq = 0ull;
+            j0 = sm.seg_j0[s];
+            j1 = sm.seg_j1[s];
+            jfull = j1 < n_full ? j1 : n_full;
+            p = lane_on ? pp_seg[(size_t)s * D + k] : 0.0;
+            c2 = pb.noseed ? (uint32_t)(pb.chain0 + sm.seg_c[s]) : 0u;
+            c3 = c3base | (pb.noseed ? ((uint32_t)it & SMM_ITER_MASK) : 0u);
+          }
+        }
+        if (s < 0) break;
+        if (lane == 0) next = atomicAdd(&sm.next_unit, 1);  // prefetch: the latency hides behind the math
+        ++units_cur;
+        if (lane_on && pb.obj != SMM_OBJ_FAILS) {
+          const int jb = j0 + (u - sm.seg_unit0[s]) * unit_j + jo;
+#pragma unroll 1
+          for (int q = 0; q < kUnitSteps; ++q) {
+            const int j = jb + q * rows;
+            if (j < jfull) add_pair(pb, sm.logtab, a, p, (uint32_t)j, (uint32_t)k, c2, c3, true);
+          }
+          if ((S & 1) && jb <= n_full && n_full < jb + unit_j && n_full < j1 && (n_full - jb) % rows == 0)
+            add_pair(pb, sm.logtab, a, p, (uint32_t)n_full, (uint32_t)k, c2, c3, false);  // odd S: the single last draw
+        }
+        next = __shfl_sync(0xffffffffu, next, 0);
       }
-      __syncthreads();
-      if (sm.is_last) {
-        reduce_and_finalize(pb, sm, part_base, n_seg, part_len);
-        accept_and_store(pb, st, sm, c, pb.chain0 + c, it, fused);
-      }
-      __syncthreads();
-      x = xe;
     }
-    PHASE_STAMP(b * 2 + (it & 1), 2);
+    PHASE_STAMP((b * 2 + (it & 1)) * 2, 1);  // warp 0 left the work loop
+    __syncthreads();
+    PHASE_STAMP((b * 2 + (it & 1)) * 2, 2);  // every warp of the CTA done (incl. chain finalisation)
     if (!grid_barrier(pb, st, gen, fused, seq)) return;
-    PHASE_STAMP(b * 2 + (it & 1), 3);
+    PHASE_STAMP((b * 2 + (it & 1)) * 2, 3);
   }
   // ---- exchange of the last iteration of this launch ----
   const int pit = iter0 + n_iters - 1;
-  if (owner && N > 1 && pit >= 2) persistent_exchange(pb, st, pit, sched_iter0, n_s, fused, val, own, exch);
+  if (n_owned > 0 && N > 1 && pit >= 2) persistent_exchange(pb, st, pit, fused, val, own, exch, sij, soff, sm.nlev);
   if (b == 0 && tid == 0) *st.sync_seq = seq;
 }
 
@@ -718,6 +1005,7 @@ __global__ void __launch_bounds__(kEvalThreads) objective_kernel(DevProblem pb, 
                                                                  double *moments, int *status) {
   __shared__ EvalSmem sm;
   const int bi = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
+  const Grp g{tid, (int)blockDim.x, 0};
   load_logtab(sm.logtab);
   for (int k = tid; k < pb.P; k += blockDim.x) sm.pp[k] = params[(size_t)bi * pb.P + k];
   __syncthreads();
@@ -729,7 +1017,8 @@ __global__ void __launch_bounds__(kEvalThreads) objective_kernel(DevProblem pb, 
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
     const int nb = (pb.S + 1) >> 1;
     const int j0 = (int)(((long long)nb * split) / n_split), j1 = (int)(((long long)nb * (split + 1)) / n_split);
-    simulate_norm_segment(pb, sm, j0, j1, (uint32_t)bi, rep0 + (uint32_t)bi, part_base + (size_t)split * part_len);
+    simulate_static(pb, g, sm.logtab, sm.pp, j0, j1, (uint32_t)bi, rep0 + (uint32_t)bi, sm.red,
+                    part_base + (size_t)split * part_len);
     if (n_split > 1) {
       if (tid == 0) {
         __threadfence();
@@ -742,10 +1031,10 @@ __global__ void __launch_bounds__(kEvalThreads) objective_kernel(DevProblem pb, 
       if (!sm.is_last) return;
     }
   }
-  reduce_and_finalize(pb, sm, part_base, n_split, part_len);
+  group_finalize(pb, g, fin_scratch(sm), part_base, n_split, part_len);
   if (tid == 0) {
-    value[bi] = sm.value;
-    status[bi] = sm.status;
+    value[bi] = sm.value[0];
+    status[bi] = sm.flags[1];
   }
   for (int k = tid; k < pb.M; k += blockDim.x) moments[(size_t)bi * pb.M + k] = sm.mom[k];
 }
@@ -871,11 +1160,112 @@ __global__ void __launch_bounds__(kEvalThreads) rng_throughput_kernel(long long 
   out[2 * gid + 1] = sq;
 }
 
+// grid-barrier latency alone: n barriers back to back, several implementations (debug aid)
+__global__ void __launch_bounds__(kPersistThreads, 1) barrier_bench_kernel(DevProblem pb, DevState st, int variant,
+                                                                           int n) {
+  unsigned gen = ld_volatile_u32(&st.bar->gen);
+  unsigned long long seq = 0;
+  __syncthreads();
+  for (int i = 0; i < n; ++i) {
+    if (variant == 0) {
+      if (!grid_barrier(pb, st, gen, false, seq)) return;
+    } else if (variant == 1) {  // no fences at all (lower bound: one RED + two polls)
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned target = ++gen;
+        if (blockIdx.x == 0) {
+          while (ld_relaxed_gpu(&st.bar->arrive) < gridDim.x - 1) {}
+          st_relaxed_gpu(&st.bar->arrive, 0u);
+          st_relaxed_gpu(&st.bar->gen, target);
+        } else {
+          asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(&st.bar->arrive), "r"(1u) : "memory");
+          while ((int)(ld_relaxed_gpu(&st.bar->gen) - target) < 0) {}
+        }
+      }
+      __syncthreads();
+    } else if (variant == 2) {  // release arrive, relaxed everything else
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned target = ++gen;
+        if (blockIdx.x == 0) {
+          while (ld_relaxed_gpu(&st.bar->arrive) < gridDim.x - 1) {}
+          st_relaxed_gpu(&st.bar->arrive, 0u);
+          fence_acq_rel_gpu();
+          st_relaxed_gpu(&st.bar->gen, target);
+        } else {
+          red_release_gpu(&st.bar->arrive, 1u);
+          while ((int)(ld_relaxed_gpu(&st.bar->gen) - target) < 0) {}
+        }
+      }
+      __syncthreads();
+    } else {  // classic: __threadfence + atomicAdd + volatile polls + __threadfence
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned target = ++gen;
+        __threadfence();
+        if (blockIdx.x == 0) {
+          while (ld_volatile_u32(&st.bar->arrive) < gridDim.x - 1) {}
+          st.bar->arrive = 0;
+          __threadfence();
+          *(volatile unsigned *)&st.bar->gen = target;
+        } else {
+          atomicAdd(&st.bar->arrive, 1u);
+          while ((int)(ld_volatile_u32(&st.bar->gen) - target) < 0) {}
+        }
+        __threadfence();
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// the simulate inner loop alone (add_pair with the handle's keys and accumulators), static or dynamic unit
+// distribution, any CTA size: the ceiling the evaluation kernels are measured against
+__global__ void __launch_bounds__(1024) sim_throughput_kernel(DevProblem pb, int n_per_thread, int dyn, double *out) {
+  __shared__ smm_logent tab[1 << SMM_LOG_BITS];
+  __shared__ int ctr;
+  load_logtab(tab);
+  if (threadIdx.x == 0) ctr = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, D = pb.P;
+  const uint32_t k = (uint32_t)(lane % D);
+  Acc a{0ull, 0ull};
+  const double p = 0.25 * (double)k;
+  if (!dyn) {
+    const uint32_t j0 = (blockIdx.x * blockDim.x + threadIdx.x) / D * (uint32_t)n_per_thread;
+    for (int j = 0; j < n_per_thread; ++j) add_pair(pb, tab, a, p, j0 + (uint32_t)j, k, 0u, SMM_STREAM_SIM << 28, true);
+  } else {
+    const int rows = 32 / D, unit = rows * kUnitSteps, jo = lane / D;
+    const int jmax = n_per_thread * (blockDim.x / D);
+    int next = 0;
+    if (lane == 0) next = atomicAdd(&ctr, unit);
+    next = __shfl_sync(0xffffffffu, next, 0);
+    while (next < jmax) {
+      const int base = next + jo;
+      if (lane == 0) next = atomicAdd(&ctr, unit);
+#pragma unroll 1
+      for (int u = 0; u < kUnitSteps; ++u) {
+        const int j = base + u * rows;
+        if (j < jmax) add_pair(pb, tab, a, p, (uint32_t)j + blockIdx.x * 1000003u, k, 0u, SMM_STREAM_SIM << 28, true);
+      }
+      next = __shfl_sync(0xffffffffu, next, 0);
+    }
+  }
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  out[2 * gid] = __longlong_as_double((long long)a.sum);
+  out[2 * gid + 1] = __longlong_as_double((long long)a.sq);
+}
+
 // ------------------------------------------------------------------------------------------------
 // launchers (called from smm_api.cu)
 // ------------------------------------------------------------------------------------------------
 size_t pairs_smem_bytes(int N, int n_s) { return sizeof(unsigned) * ((size_t)5 * n_s + 2 + N); }
 size_t exch_smem_bytes(int N) { return sizeof(double) * (size_t)N + sizeof(unsigned short) * 2 * (size_t)N; }
+// persistent kernel: exchange arrays (u16 part rounded up to whole doubles) + per-segment pp / sums / finalisation scratch
+size_t persist_smem_bytes(int N, int D, int M, int cta_seg) {
+  const int n_s = N < 3 ? (N > 1 ? N - 1 : 0) : N;
+  return sizeof(double) * ((size_t)N + (N + 1) / 2 + (n_s + 1) + (size_t)cta_seg * (D + 2 * D + 2 * D + M + 4));
+}
 
 cudaError_t configure_kernels(int N, int n_s) {
   cudaError_t e = cudaFuncSetAttribute(bgp_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -883,8 +1273,11 @@ cudaError_t configure_kernels(int N, int n_s) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(bgp_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exch_smem_bytes(N));
   if (e != cudaSuccess) return e;
+  return cudaSuccess;
+}
+cudaError_t configure_persistent(int N, int D, int M, int cta_seg) {
   return cudaFuncSetAttribute(bgp_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)exch_smem_bytes(N));
+                              (int)persist_smem_bytes(N, D, M, cta_seg));
 }
 
 int eval_max_blocks_per_sm() {
@@ -892,11 +1285,14 @@ int eval_max_blocks_per_sm() {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bgp_eval_kernel, kEvalThreads, 0);
   return n;
 }
-int persistent_max_blocks_per_sm(int N) {
+int persistent_max_blocks_per_sm(int N, int D, int M, int cta_seg) {
   int n = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bgp_persistent_kernel, kEvalThreads, exch_smem_bytes(N));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bgp_persistent_kernel, kPersistThreads,
+                                                persist_smem_bytes(N, D, M, cta_seg));
   return n;
 }
+int persistent_unit_blocks(int D) { return (32 / D) * kUnitSteps; }
+int persistent_max_cta_seg() { return kMaxCtaSeg; }
 
 void launch_eval(const DevProblem &pb, const DevState &st, int iter, int n_split, int part_len, cudaStream_t s) {
   dim3 grid(n_split, pb.L);
@@ -909,12 +1305,12 @@ void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sch
   bgp_exchange_kernel<<<1, kExchThreads, exch_smem_bytes(pb.N), s>>>(pb, st, iter, sched_idx, n_s);
 }
 cudaError_t launch_persistent(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int sched_iter0,
-                              int n_s, int part_len, int max_seg, int grid, cudaStream_t s) {
+                              int n_s, int part_len, int max_seg, int cta_seg, int grid, cudaStream_t s) {
   DevProblem pbc = pb;
   DevState stc = st;
-  void *args[] = {&pbc, &stc, &iter0, &n_iters, &sched_iter0, &n_s, &part_len, &max_seg};
-  return cudaLaunchCooperativeKernel((void *)bgp_persistent_kernel, dim3(grid), dim3(kEvalThreads), args,
-                                     exch_smem_bytes(pb.N), s);
+  void *args[] = {&pbc, &stc, &iter0, &n_iters, &sched_iter0, &n_s, &part_len, &max_seg, &cta_seg};
+  return cudaLaunchCooperativeKernel((void *)bgp_persistent_kernel, dim3(grid), dim3(kPersistThreads), args,
+                                     persist_smem_bytes(pb.N, pb.P, pb.M, cta_seg), s);
 }
 void launch_objective(const DevProblem &pb, const double *params, int B, int noseed, uint32_t rep0, int n_split,
                       int part_len, double *partials, unsigned *arrive, double *value, double *moments, int *status,
@@ -929,6 +1325,16 @@ void launch_debug_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, i
 }
 void launch_rng_throughput(long long n_per_thread, int blocks, double *out, cudaStream_t s) {
   rng_throughput_kernel<<<blocks, kEvalThreads, 0, s>>>(n_per_thread, out);
+}
+cudaError_t launch_barrier_bench(const DevProblem &pb, const DevState &st, int variant, int n, int grid, cudaStream_t s) {
+  DevProblem pbc = pb;
+  DevState stc = st;
+  void *args[] = {&pbc, &stc, &variant, &n};
+  return cudaLaunchCooperativeKernel((void *)barrier_bench_kernel, dim3(grid), dim3(kPersistThreads), args, 0, s);
+}
+void launch_sim_throughput(const DevProblem &pb, int n_per_thread, int blocks, int threads, int dyn, double *out,
+                           cudaStream_t s) {
+  sim_throughput_kernel<<<blocks, threads, 0, s>>>(pb, n_per_thread, dyn, out);
 }
 
 }  // namespace smm

@@ -22,17 +22,19 @@ with _lib.BGPHandle(cfg) as h:
     else:
         ms = h.step(100)
         print("us/iter", ms * 10)
-        ts = h.phase_ts().astype(np.int64).reshape(-1, 2, 4)     # [block][parity][stamp]
+        ts = h.phase_ts().astype(np.int64).reshape(-1, 2, 2, 4)     # [block][parity][half][stamp]
         last_par = h.iteration & 1
-        cur, prev = ts[:, last_par, :], ts[:, 1 - last_par, :]
-        t0 = prev[:, 0].min()
+        cur, prev = ts[:, last_par], ts[:, 1 - last_par]
+        t0 = prev[:, 0, 0].min()
         f = lambda a: (a - t0) / 1e3
-        print("prev iter: A start  us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 0])))
-        print("prev iter: first segment simulated us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 1])))
-        print("prev iter: A end    us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 2])))
-        print("prev iter: B2 exit  us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 3])))
-        print("last iter: A start  us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 0])))
-        print("last iter: A end    us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 2])))
-        print("last iter: B2 exit  us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 3])))
-        print("A duration per block us: min %.1f med %.1f p90 %.1f max %.1f" % pct((prev[:, 2] - prev[:, 0]) / 1e3))
-        print("X+P+B1 (B2 exit -> next A start) us: min %.1f med %.1f p90 %.1f max %.1f" % pct((cur[:, 0] - prev[:, 3]) / 1e3))
+        own = cur[:, 1, 1] > 0
+        print("prev: A start            us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 0, 0])))
+        print("prev: warp0 out of units us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 0, 1])))
+        print("prev: CTA all warps done us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 0, 2])))
+        print("prev: B2 exit            us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[:, 0, 3])))
+        print("last: exchange done      us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[own, 1, 0])))
+        print("last: proposals done     us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[own, 1, 1])))
+        print("last: A start (B1 exit)  us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 0, 0])))
+        print("last: warp0 out of units us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 0, 1])))
+        print("last: CTA all warps done us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 0, 2])))
+        print("last: B2 exit            us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 0, 3])))
