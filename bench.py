@@ -178,7 +178,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=950)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -225,42 +225,56 @@ def main():
         torch.cuda.synchronize()
 
     K, W = args.steps, args.warmup
-    cfg = bench_config(world, K + W)
-    cfg.device, cfg.world_size, cfg.rank, cfg.nccl_id = local_rank, world, rank, fresh_id()
-    cfg.n_split, cfg.exchange_mode = args.n_split, args.exchange_mode
-    n_chains = cfg.n_chains
+    # The C2 workload is run!(MAlgoBGP) with maxiter = RUN_ITERS (I = 1000).  K timed steps are
+    # iterations W+1.. of such a run, continued in fresh runs when K + W exceeds one run: the reference's sigma
+    # adaptation (AlgoBGP.jl:381-390) lets the hot chains' proposal variance grow without bound, so a single
+    # ensemble cannot be iterated for ever (its rejection sampler eventually fails, :409).
+    RUN_ITERS = 1000
+    W = min(W, RUN_ITERS // 2)
+    n_chains = CHAINS_PER_GPU * world
     L = n_chains // world
 
+    def make_handle(n_iters):
+        cfg = bench_config(world, n_iters)
+        cfg.device, cfg.world_size, cfg.rank, cfg.nccl_id = local_rank, world, rank, fresh_id()
+        cfg.n_split, cfg.exchange_mode = args.n_split, args.exchange_mode
+        return _lib.BGPHandle(cfg), cfg
+
     # ---- device-resident timing: K iterations, state already in HBM -----------------------------
-    h = _lib.BGPHandle(cfg)
-    h.step(W)
-    launches0 = h.counters()["kernel_launches"]
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    t0 = time.perf_counter()
-    ms = h.step(K)                      # CUDA events on the library's stream around exactly K iterations
-    barrier()
-    wall = time.perf_counter() - t0
+    ms, wall, launches, left, first = 0.0, 0.0, 0, K, True
+    ctr = None
+    while left > 0:
+        warm = W if first else 0
+        n = min(left, RUN_ITERS - warm)
+        h, cfg = make_handle(warm + n)
+        if warm:
+            h.step(warm)
+        launches0 = h.counters()["kernel_launches"]
+        if first and rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        t0 = time.perf_counter()
+        ms += h.step(n)                 # CUDA events on the library's stream around exactly n iterations
+        barrier()
+        wall += time.perf_counter() - t0
+        ctr = h.counters()
+        launches += ctr["kernel_launches"] - launches0
+        h.close()
+        left -= n
+        first = False
     clocks = sampler.stop() if rank == 0 else None
-    ctr = h.counters()
-    launches = ctr["kernel_launches"] - launches0
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = n_chains * K / (ms * 1e-3)
-    h.close()
 
     # ---- per-kernel durations (separate short pass with event brackets around every launch) ------
     Kp = min(K, 300)
-    cfgp = bench_config(world, Kp + W)
-    cfgp.device, cfgp.world_size, cfgp.rank, cfgp.nccl_id = local_rank, world, rank, fresh_id()
-    cfgp.n_split, cfgp.exchange_mode = args.n_split, args.exchange_mode
     barrier()
-    hp = _lib.BGPHandle(cfgp)
+    hp, _ = make_handle(Kp + W)
     hp.step(W)
     hp.set_profiling(True)
     hp.step(Kp)
@@ -272,12 +286,12 @@ def main():
     # algorithmic bytes one launch processes: B_alg per evaluation x local chains x iterations in the launch
     bytes_per_launch = b_alg() * L * iters_per_launch
     achieved = bytes_per_launch / (eval_ms * 1e-3) / 1e9     # GB/s
-    traffic = None
+    traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.exchange_mode == 1:
         try:
             with open(tp) as f:
-                traffic = json.load(f).get(("bgp_persistent_kernel" if args.exchange_mode else "bgp_eval_kernel") + "_dram_bytes_per_launch")
+                traffic = json.load(f)["bgp_persistent_kernel_dram_bytes_per_iteration"] * iters_per_launch
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -299,9 +313,9 @@ def main():
     for k in range(N_MOMENTS):
         api.addMoment(m, f"m{k + 1}", cfg.data_mom[k], cfg.data_w[k])
     api.addEvalFunc(m, api.objfunc_norm_mv)
-    Ke = min(K, 500)
+    Ke = min(K, 500, RUN_ITERS - W)
     opts = {"N": n_chains, "maxiter": Ke + W, "maxtemp": 5.0, "sigma": 0.05, "acc_tuners": list(np.asarray(cfg.acc_tuner)),
-            "min_improve": [0.0] * n_chains, "seed": cfg.seed_algo, "device": local_rank, "world_size": world, "rank": rank,
+            "min_improve": [0.0] * n_chains, "smpl_iters": cfg.smpl_iters, "seed": cfg.seed_algo, "device": local_rank, "world_size": world, "rank": rank,
             "nccl_id": fresh_id(), "n_split": args.n_split, "exchange_mode": args.exchange_mode}
     pinned = {}
     barrier()
@@ -359,7 +373,7 @@ def main():
                        "exchange_mode": args.exchange_mode,
                        "l2": "no input is re-read between iterations: every draw is generated in registers; the only "
                              "carried data is the chains' own state (~60 KB), which the algorithm's data dependence requires",
-                       "normals_per_eval": N_PARAMS * N_SIM},
+                       "run_iters": RUN_ITERS, "normals_per_eval": N_PARAMS * N_SIM},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),
