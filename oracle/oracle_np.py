@@ -101,6 +101,44 @@ def objective(cfg, p, uid=0, rep=0, noseed=None):
     return float(np.mean(d * d)), sim
 
 
+def panel_objective(cfg, p, uid=0, rep=0, noseed=None):
+    """the dynamic-panel objective (SURVEY.md 8d, oracle/smm_oracle.cpp::objfunc_panel) re-derived with numpy:
+    the panel is materialised as arrays y[i,t], x[k,i,t] and every moment is a plain centred numpy average.
+    (numpy has no fma, so this agrees with the C++ oracle to rounding, not to the bit.)"""
+    K, T, NI = cfg.panel_K, cfg.panel_T, cfg.panel_N
+    noseed = cfg.noseed if noseed is None else noseed
+    p = np.asarray(p, float)
+    rho, beta, phi = p[0], p[1:1 + K], p[1 + K:1 + 2 * K]
+    sig_a, sig_e, mu0 = p[1 + 2 * K], p[2 + 2 * K], p[3 + 2 * K]
+    nz = 1 + K + T * (K + 1)
+    Z = np.stack([sim_normals(cfg.seed_sim, i, nz, noseed, uid, rep) for i in range(NI)])   # [NI][nz]
+    alpha = mu0 + sig_a * Z[:, 0]
+    y = np.zeros((NI, T + 1))
+    x = np.zeros((K, NI, T + 1))
+    y[:, 0] = alpha / (1.0 - rho)
+    x[:, :, 0] = (Z[:, 1:1 + K] / np.sqrt(1.0 - phi * phi)).T
+    for t in range(1, T + 1):
+        zt = Z[:, 1 + K + (t - 1) * (K + 1): 1 + K + t * (K + 1)]
+        x[:, :, t] = phi[:, None] * x[:, :, t - 1] + zt[:, :K].T
+        y[:, t] = alpha + rho * y[:, t - 1] + (beta[:, None] * x[:, :, t]).sum(axis=0) + sig_e * zt[:, K]
+    n = NI * T
+    my = y[:, 1:].sum() / n
+    mx = x[:, :, 1:].sum(axis=(1, 2)) / n
+    sim = [my]
+    for l in range(7):
+        lo = max(l, 1)
+        sim.append(((y[:, lo:] - my) * (y[:, lo - l:T + 1 - l] - my)).sum() / n)
+    yc = y[:, 1:] - my
+    xc = x - mx[:, None, None]
+    sim += [(yc * xc[k, :, 1:]).sum() / n for k in range(K)]
+    sim += [(yc * xc[k, :, :-1]).sum() / n for k in range(K)]
+    sim += [(xc[k, :, 1:] * xc[k, :, :-1]).sum() / n for k in range(K)]
+    sim += [(xc[k, :, 1:] ** 2).sum() / n for k in range(K)]
+    sim = np.array(sim)
+    d = (sim - np.asarray(cfg.data_mom, float)) / np.asarray(cfg.data_w, float)
+    return float(np.mean(d * d)), sim
+
+
 def run(cfg, n_iters):
     """run!(MAlgoBGP) as plain loops; returns dict of arrays shaped [n_iters][N](...)"""
     N, P, M = cfg.n_chains, cfg.n_params, cfg.n_moments
@@ -151,7 +189,7 @@ def run(cfg, n_iters):
                             x01[b0:b0 + bs] = cand
                             break
                 pp = x01 * (ub - lb) + lb
-            value, sim = objective(cfg, pp, c, it)
+            value, sim = (panel_objective if cfg.panel_K else objective)(cfg, pp, c, it)
             status = 1
             if it == 1:
                 prob, accepted = 1.0, True

@@ -144,11 +144,13 @@ void objfunc_panel(const MProb &m, Eval &ev, uint32_t uid, uint32_t rep) {
   std::vector<double> y((size_t)NI * (T + 1)), x((size_t)K * NI * (T + 1)), z(nz + 1);
   for (int i = 0; i < NI; ++i) {
     fill_normals_row(m, (uint32_t)i, nz, uid, rep, z.data());
-    const double alpha = mu0 + sig_a * z[0];
+    // the recurrences are DEFINED with fused multiply-adds (the spec is ours; Julia's `fma`), so that the
+    // device's DFMA and this loop round identically
+    const double alpha = std::fma(sig_a, z[0], mu0);
     double yc = alpha / (1.0 - rho);
     std::vector<double> xc(K);
     for (int k = 0; k < K; ++k) {
-      xc[k] = z[1 + k] / std::sqrt(1.0 - phi[k] * phi[k]);
+      xc[k] = z[1 + k] / std::sqrt(std::fma(-phi[k], phi[k], 1.0));
       x[((size_t)k * NI + i) * (T + 1)] = xc[k];
     }
     y[(size_t)i * (T + 1)] = yc;
@@ -156,11 +158,11 @@ void objfunc_panel(const MProb &m, Eval &ev, uint32_t uid, uint32_t rep) {
       const double *zt = z.data() + 1 + K + (t - 1) * (K + 1);
       double xb = 0.0;
       for (int k = 0; k < K; ++k) {
-        xc[k] = phi[k] * xc[k] + zt[k];
+        xc[k] = std::fma(phi[k], xc[k], zt[k]);
         x[((size_t)k * NI + i) * (T + 1) + t] = xc[k];
-        xb += beta[k] * xc[k];
+        xb = std::fma(beta[k], xc[k], xb);
       }
-      yc = alpha + rho * yc + xb + sig_e * zt[K];
+      yc = std::fma(sig_e, zt[K], std::fma(rho, yc, alpha) + xb);
       y[(size_t)i * (T + 1) + t] = yc;
     }
   }

@@ -74,3 +74,55 @@ def slow_normal(n_chains: int = 64, niter: int = 2000, slow_seconds: float = 0.1
     )
     args.update(kw)
     return BGPConfig(**args)
+
+
+def panel_box(K: int = 8):
+    """C4 parameter box: theta = (rho, beta[K], phi[K], sigma_alpha, sigma_eps, mu0)."""
+    lb = [0.0] + [-2.0] * K + [0.0] * K + [0.1, 0.1, -2.0]
+    ub = [0.95] + [2.0] * K + [0.95] * K + [2.0, 2.0, 2.0]
+    return np.array(lb), np.array(ub)
+
+
+def dynamic_panel(n_chains: int = 512, niter: int = 200, K: int = 8, T: int = 50, n_ind: int = 5000,
+                  data_mom=None, **kw) -> BGPConfig:
+    """C4: dynamic-panel SMM, P = 2K+4 params, M = 4K+8 moments, panel of n_ind individuals x T periods.
+
+    `data_mom` are the moments the chains are matched to: the simulation at theta0 = mid-box with sim seed 4321
+    (`panel_data_moments`); weights = max(|data|, 0.1).  Without them the config carries placeholders (zeros,
+    unit weights) and is only good for bare objective evaluations."""
+    lb, ub = panel_box(K)
+    M = 4 * K + 8
+    dm = np.zeros(M) if data_mom is None else np.asarray(data_mom, dtype=np.float64)
+    w = np.ones(M) if data_mom is None else np.maximum(np.abs(dm), 0.1)
+    temps = temperature_ladder(n_chains, 5.0)
+    tuners = np.geomspace(20.0, 1.0, n_chains) if n_chains > 1 else np.array([20.0])
+    args = dict(
+        lb=lb, ub=ub, init=lb + 0.4 * (ub - lb), data_mom=dm, data_w=w,
+        n_chains=n_chains, max_iter=niter,
+        sigma0=0.02 * temps, acc_tuner=tuners, min_improve=[0.0] * n_chains,
+        objective_id=SMM_OBJ_PANEL, panel_K=K, panel_T=T, panel_N=n_ind,
+        n_sim=2, seed_sim=1234, seed_algo=20261017, smpl_iters=100000, exchange_mode=0,
+    )
+    args.update(kw)
+    return BGPConfig(**args)
+
+
+def panel_data_moments(evaluate, K: int = 8, T: int = 50, n_ind: int = 5000) -> np.ndarray:
+    """Moments of the panel simulated at theta0 = mid-box with sim seed 4321.  `evaluate(cfg, params)`
+    returns (value, moments, status) of the bare objective -- the GPU's `BGPHandle.eval_batch` in the product
+    (`panel_data_moments_gpu`), the oracle's in the CPU tests."""
+    lb, ub = panel_box(K)
+    cfg = dynamic_panel(1, 1, K, T, n_ind, seed_sim=4321)
+    _, mom, status = evaluate(cfg, 0.5 * (lb + ub))
+    assert int(np.asarray(status).reshape(-1)[0]) == 1
+    return np.asarray(mom, dtype=np.float64).reshape(-1)
+
+
+def panel_data_moments_gpu(K: int = 8, T: int = 50, n_ind: int = 5000, device: int = 0) -> np.ndarray:
+    from . import _lib
+
+    def ev(cfg, params):
+        cfg.device = device
+        with _lib.BGPHandle(cfg) as h:
+            return h.eval_batch(params)
+    return panel_data_moments(ev, K, T, n_ind)

@@ -30,6 +30,14 @@ void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sch
 void launch_objective(const DevProblem &pb, const double *params, int B, int noseed, uint32_t rep0, int n_split,
                       int part_len, double *partials, unsigned *arrive, double *value, double *moments, int *status,
                       cudaStream_t s);
+size_t panel_smem_bytes(int K, int P);
+cudaError_t configure_panel(int K, int P);
+int panel_max_blocks_per_sm(int K, int P);
+void launch_propose(const DevProblem &pb, const DevState &st, int iter, int zero_len, cudaStream_t s);
+void launch_panel_chains(const DevProblem &pb, const DevState &st, int iter, int grid, cudaStream_t s);
+void launch_panel_batch(const DevProblem &pb, const DevState &st, const double *params, int B, int noseed, uint32_t uid0,
+                        uint32_t rep0, unsigned long long *acc, unsigned *done, unsigned *unit_ctr, double *value,
+                        double *moments, int *status, int grid, cudaStream_t s);
 void launch_debug_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, double *out,
                           cudaStream_t s);
 void launch_rng_throughput(long long n_per_thread, int blocks, double *out, cudaStream_t s);
@@ -85,6 +93,9 @@ struct smm_bgp {
   int n_s = 0;       // pairs per iteration
   int n_split = 1, part_len = 0;
   double eval_param_limit = 0.0;  // |param| bound for which the fixed-point accumulators are sized
+  bool panel = false;     // SMM_OBJ_PANEL: propose kernel + panel simulation kernel instead of bgp_eval_kernel
+  int panel_grid = 0;     // CTAs of the panel simulation kernel (one resident wave)
+  std::vector<double> h_lb, h_ub;
   int mode = 0;           // 0 = multi-launch (+ NCCL), 1 = persistent kernel (+ fused peer-store all-gather)
   int grid = 0, max_seg = 1, cta_seg = 1;  // persistent kernel: CTAs, partial slots per chain, chains per CTA share
   void *peer_ptrs[3 * kMaxWorld] = {nullptr};  // IPC-opened peer buffers (closed in release)
@@ -112,7 +123,7 @@ struct smm_bgp {
   DevBuf<uint8_t> t_acc;
   DevBuf<int> t_status, t_exch, t_bestid;
   DevBuf<double> partials;
-  DevBuf<unsigned> arrive;
+  DevBuf<unsigned> arrive, unit_ctr;
   DevBuf<int> sched_ij, sched_off, sched_nlev, err;
   DevBuf<unsigned long long> counters, phase_ts;
 
@@ -129,7 +140,7 @@ struct smm_bgp {
     n_noex.free(); n_acc.free();
     t_value.free(); t_prob.free(); t_curr.free(); t_best.free(); t_params.free(); t_mom.free();
     t_acc.free(); t_status.free(); t_exch.free(); t_bestid.free();
-    partials.free(); arrive.free(); sched_ij.free(); sched_off.free(); sched_nlev.free(); err.free();
+    partials.free(); arrive.free(); unit_ctr.free(); sched_ij.free(); sched_off.free(); sched_nlev.free(); err.free();
     counters.free(); phase_ts.free();
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
     prof_ev.clear();
@@ -166,8 +177,21 @@ int check_config(const smm_bgp_config *cfg) {
     case SMM_OBJ_NORM_MV:
       if (M != 2 * P) return fail(SMM_E_UNSUPPORTED_SHAPE, "norm_mv needs n_moments == 2*n_params");
       break;
-    case SMM_OBJ_PANEL:
-      return fail(SMM_E_UNSUPPORTED_SHAPE, "panel objective not built yet");
+    case SMM_OBJ_PANEL: {
+      const int K = cfg->panel_K;
+      if (K < 1 || K > kPanelMaxK || P != 2 * K + 4 || M != 4 * K + 8 || cfg->panel_T < 7 || cfg->panel_N < 1 ||
+          cfg->panel_N > (1 << 22))
+        return fail(SMM_E_UNSUPPORTED_SHAPE, "panel needs 1 <= K <= 16, P == 2K+4, M == 4K+8, T >= 7, 1 <= N_ind <= 2^22");
+      // theta = (rho, beta[K], phi[K], sigma_alpha, sigma_eps, mu0): the simulator is stationary only for |rho|, |phi| < 1
+      for (int k = 0; k <= 2 * K; ++k) {
+        if (k >= 1 && k <= K) continue;
+        if (!(std::fabs(cfg->lb[k]) < 1.0 && std::fabs(cfg->ub[k]) < 1.0))
+          return fail(SMM_E_UNSUPPORTED_SHAPE, "panel needs |rho| < 1 and |phi_k| < 1 over the whole sampling box");
+      }
+      if (cfg->exchange_mode != 0)
+        return fail(SMM_E_UNSUPPORTED_SHAPE, "the panel objective runs with exchange_mode 0 (its own simulation kernel)");
+      break;
+    }
     case SMM_OBJ_FAILS:
       break;
     default:
@@ -343,6 +367,19 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   const int n_blocks_philox = (cfg->n_sim + 1) / 2;
   h->n_split = choose_split(L, prop.multiProcessorCount, eval_max_blocks_per_sm(), n_blocks_philox, cfg->n_split);
   if (cfg->objective_id == SMM_OBJ_FAILS) h->n_split = 1;
+  h->panel = cfg->objective_id == SMM_OBJ_PANEL;
+  h->h_lb.assign(cfg->lb, cfg->lb + P);
+  h->h_ub.assign(cfg->ub, cfg->ub + P);
+  if (h->panel) {
+    h->n_split = 1;
+    h->part_len = 2 * panel_na(cfg->panel_K);  // (hi, lo) fixed-point words per raw sum
+    CUDA_TRY(configure_panel(cfg->panel_K, P));
+    const int per_sm = panel_max_blocks_per_sm(cfg->panel_K, P);
+    if (per_sm < 1) return fail(SMM_E_CUDA, "panel simulation kernel does not fit on an SM");
+    h->panel_grid = prop.multiProcessorCount * per_sm;
+    if (cfg->n_split > 0 && cfg->n_split < h->panel_grid) h->panel_grid = cfg->n_split;  // n_split caps the CTA count
+  }
+  if (int rc = fill(h->unit_ctr, 1, 0u)) return rc;
   if (N > 1) CUDA_TRY(configure_kernels(N, h->n_s));
   h->max_seg = h->n_split;
   if (h->mode == 1) {
@@ -412,6 +449,31 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     pb.scale_sq = std::ldexp(1.0, -f_sq);
     h->eval_param_limit = xmax - 9.0;
   }
+  if (h->panel) {
+    // Two-word fixed point of the per-individual sums (smm_panel.cuh).  Hard bounds from the sampling box with
+    // |z| <= sqrt(2 * 52 ln 2) < 8.5 (the Box-Muller radius of a 52-bit uniform): |x_k| <= zmax / (1 - |phi_k|),
+    // |y| <= (|mu0| + (sigma_alpha + sigma_eps) zmax + sum_k |beta_k| |x_k|) / (1 - |rho|); a per-individual sum has
+    // at most T + 2 such products (HG_l has 2T + 1 terms of |y|).  N_ind of them must stay below 2^62 at grid 2^-Fhi.
+    const int K = cfg->panel_K;
+    auto amax = [&](int k) { return std::fmax(std::fabs(cfg->lb[k]), std::fabs(cfg->ub[k])); };
+    const double zmax = 8.5;
+    double bx = 0.0, bxb = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double b = zmax / (1.0 - amax(1 + K + k));
+      bx = std::fmax(bx, b);
+      bxb += amax(1 + k) * b;
+    }
+    const double by = (amax(3 + 2 * K) + (amax(1 + 2 * K) + amax(2 + 2 * K)) * zmax + bxb) / (1.0 - amax(0));
+    const double term = std::fmax(std::fmax(by * by, bx * bx), std::fmax(by * bx, std::fmax(std::fmax(by, bx), 1.0)));
+    const double bound = (2.0 * cfg->panel_T + 2.0) * term;
+    const int fhi = 61 - (int)std::ceil(std::log2((double)cfg->panel_N)) - (int)std::ceil(std::log2(bound));
+    if (fhi < -8) return fail(SMM_E_UNSUPPORTED_SHAPE, "panel: the sampling box allows sums too large for the exact accumulators");
+    const int fh = fhi > 40 ? 40 : fhi;
+    pb.pan_hi_scale = std::ldexp(1.0, fh);
+    pb.pan_hi_inv = std::ldexp(1.0, -fh);
+    pb.pan_lo_scale = std::ldexp(1.0, fh + 40);
+    pb.pan_lo_inv = std::ldexp(1.0, -(fh + 40));
+  }
   pb.lb = h->lb.p; pb.ub = h->ub.p; pb.init = h->init.p; pb.data = h->data.p; pb.w = h->w.p;
   pb.acc_tuner = h->acc_tuner.p; pb.min_improve = h->min_improve.p;
 
@@ -421,7 +483,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   st.t_value = h->t_value.p; st.t_prob = h->t_prob.p; st.t_curr = h->t_curr.p; st.t_best = h->t_best.p;
   st.t_params = h->t_params.p; st.t_mom = h->t_mom.p; st.t_acc = h->t_acc.p; st.t_status = h->t_status.p;
   st.t_exch = h->t_exch.p; st.t_bestid = h->t_bestid.p;
-  st.partials = h->partials.p; st.arrive = h->arrive.p;
+  st.partials = h->partials.p; st.arrive = h->arrive.p; st.unit_ctr = h->unit_ctr.p;
   st.sched_ij = h->sched_ij.p; st.sched_off = h->sched_off.p; st.sched_nlev = h->sched_nlev.p;
   st.err = h->err.p; st.counters = h->counters.p;
   st.val_all = h->val_all.p; st.pp = h->pp.p; st.bar = h->bar.p; st.sync_seq = h->sync_seq.p; st.flags = h->flags.p;
@@ -564,7 +626,13 @@ int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
       h->ctr.kernel_launches++;
     }
     CUDA_TRY(prof_begin(0));
-    launch_eval(h->pb, h->st, it, h->n_split, h->part_len, s);
+    if (h->panel) {
+      launch_propose(h->pb, h->st, it, h->part_len, s);
+      launch_panel_chains(h->pb, h->st, it, h->panel_grid, s);
+      h->ctr.kernel_launches++;
+    } else {
+      launch_eval(h->pb, h->st, it, h->n_split, h->part_len, s);
+    }
     CUDA_TRY(prof_end());
     h->prof_iters += h->profiling ? 1 : 0;
     h->ctr.kernel_launches++;
@@ -650,11 +718,49 @@ int smm_bgp_eval_batch(smm_bgp *h, const double *params, int32_t B, int32_t nose
                        double *moments, int32_t *status) {
   if (!h || !params) return fail(SMM_E_ARG, "null argument");
   if (B < 1) return fail(SMM_E_ARG, "B must be positive");
-  for (int64_t i = 0; i < (int64_t)B * h->P; ++i)
-    if (!(std::fabs(params[i]) <= h->eval_param_limit))
-      return fail(SMM_E_ARG, "parameter far outside the sampling box (> 4x): accumulators are sized from the box");
+  if (h->panel) {
+    for (int64_t i = 0; i < (int64_t)B * h->P; ++i)
+      if (!(params[i] >= h->h_lb[i % h->P] && params[i] <= h->h_ub[i % h->P]))
+        return fail(SMM_E_ARG, "panel: parameter outside the sampling box (the exact accumulators are sized from the box)");
+  } else {
+    for (int64_t i = 0; i < (int64_t)B * h->P; ++i)
+      if (!(std::fabs(params[i]) <= h->eval_param_limit))
+        return fail(SMM_E_ARG, "parameter far outside the sampling box (> 4x): accumulators are sized from the box");
+  }
   CUDA_TRY(cudaSetDevice(h->device));
   const int P = h->P, M = h->M;
+  if (h->panel) {
+    DevBuf<double> d_params, d_value, d_mom;
+    DevBuf<unsigned long long> d_acc;
+    DevBuf<int> d_status;
+    DevBuf<unsigned> d_done;  // [B] + the queue head
+    struct FreeP {
+      DevBuf<double> &a, &b, &c;
+      DevBuf<unsigned long long> &d;
+      DevBuf<int> &e;
+      DevBuf<unsigned> &f;
+      ~FreeP() { a.free(); b.free(); c.free(); d.free(); e.free(); f.free(); }
+    } frp{d_params, d_value, d_mom, d_acc, d_status, d_done};
+    CUDA_TRY(d_params.alloc((size_t)B * P));
+    CUDA_TRY(d_value.alloc(B));
+    CUDA_TRY(d_mom.alloc((size_t)B * M));
+    CUDA_TRY(d_acc.alloc((size_t)B * h->part_len));
+    CUDA_TRY(d_status.alloc(B));
+    CUDA_TRY(d_done.alloc((size_t)B + 1));
+    cudaStream_t s = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(d_params.p, params, sizeof(double) * B * P, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(d_acc.p, 0, sizeof(unsigned long long) * (size_t)B * h->part_len, s));
+    CUDA_TRY(cudaMemsetAsync(d_done.p, 0, sizeof(unsigned) * ((size_t)B + 1), s));
+    launch_panel_batch(h->pb, h->st, d_params.p, B, noseed, 0u, rep0, d_acc.p, d_done.p, d_done.p + B, d_value.p, d_mom.p,
+                       d_status.p, h->panel_grid, s);
+    h->ctr.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (value) CUDA_TRY(cudaMemcpyAsync(value, d_value.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+    if (moments) CUDA_TRY(cudaMemcpyAsync(moments, d_mom.p, sizeof(double) * B * M, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, d_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+  }
   int n_split = h->n_split;
   DevBuf<double> d_params, d_value, d_mom, d_part;
   DevBuf<int> d_status;

@@ -15,6 +15,11 @@ constexpr int kPairThreads = 256;   // CTA size of the pair-schedule kernel
 constexpr int kMaxSplit = 64;       // CTAs cooperating on one evaluation (multi-launch mode)
 constexpr int kPairChunk = 128;     // iterations of pair schedules precomputed per launch
 constexpr int kMaxWorld = 8;        // GPUs of one box
+constexpr int kPanelThreads = 128;  // CTA size of the panel simulation kernel (4 warps, one individual per thread)
+constexpr int kPanelMaxK = 16;      // regressors of the dynamic-panel objective (P = 2K+4 <= 36)
+
+// pooled raw sums of the dynamic-panel objective (see smm_panel.cuh): 14 for y, 6 per regressor
+__host__ __device__ inline int panel_na(int K) { return 14 + 6 * K; }
 
 // Last-accepted record of a chain, one row of R = 3 + P + M doubles:
 //   [0] value  [1] prob  [2] status (as double)  [3..3+P) params  [3+P..3+P+M) simMoments
@@ -33,6 +38,8 @@ struct DevProblem {
   double sigma_adjust_by, slow_seconds;
   double magic_sum, magic_sq;               // 1.5 * 2^(52-F): fixed-point rounding constants of the accumulators
   double scale_sum, scale_sq;               // 2^-F
+  double pan_hi_scale, pan_hi_inv;          // panel: 2^Fhi, 2^-Fhi   (two-word fixed point of the per-individual sums)
+  double pan_lo_scale, pan_lo_inv;          //        2^Flo, 2^-Flo   (Flo = Fhi + 40)
   uint64_t seed_sim, seed_algo;
   uint32_t rk_sim0[10], rk_sim1[10];        // Philox round keys of seed_sim (constant-bank operands)
   const double *lb, *ub, *init, *data, *w;  // [P] x3, [M] x2
@@ -60,6 +67,7 @@ struct DevState {
   // evaluation scratch
   double *partials;            // [L][max segments][part_len]
   unsigned *arrive;            // [L]
+  unsigned *unit_ctr;          // work-queue head of the panel simulation kernel
   // exchange schedule for iterations [sched_iter0, sched_iter0 + kPairChunk)
   int *sched_ij;               // [kPairChunk][n_s][2], level order
   int *sched_off;              // [kPairChunk][n_s + 1]

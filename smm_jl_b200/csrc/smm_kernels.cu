@@ -284,6 +284,8 @@ __device__ void simulate_static(const DevProblem &pb, const Grp &g, const smm_lo
 
 constexpr int kUnitSteps = 4;  // warp steps per work unit of the persistent kernel (sim_throughput_kernel too)
 
+__device__ void group_distance(const DevProblem &pb, const Grp &g, const FinScratch &fs);
+
 // Sum the n_seg partials of an evaluation (integer adds: exact), then moments + weighted distance.
 // Result in fs.mom, fs.value[0], fs.flags[1] (status).
 __device__ void group_finalize(const DevProblem &pb, const Grp &g, const FinScratch &fs, const double *part_base,
@@ -321,7 +323,14 @@ __device__ void group_finalize(const DevProblem &pb, const Grp &g, const FinScra
     }
   }
   gsync(g);
-  if (tid < 32) {  // value = mean_k ((sim_k - data_k) / w_k)^2, divisions in parallel, summed in moment order
+  group_distance(pb, g, fs);
+}
+
+// value = mean_k ((sim_k - data_k) / w_k)^2 (ObjExamples.jl:90-101) of the moments in fs.mom -> fs.value[0],
+// fs.flags[1] = 1.  Divisions in parallel, summed in moment order.
+__device__ void group_distance(const DevProblem &pb, const Grp &g, const FinScratch &fs) {
+  const int tid = g.tid;
+  if (tid < 32) {
     double acc = 0.0;
     for (int k0 = 0; k0 < pb.M; k0 += 32) {
       const int k = k0 + tid;
@@ -1255,6 +1264,11 @@ __global__ void __launch_bounds__(1024) sim_throughput_kernel(DevProblem pb, int
   out[2 * gid] = __longlong_as_double((long long)a.sum);
   out[2 * gid + 1] = __longlong_as_double((long long)a.sq);
 }
+
+// ------------------------------------------------------------------------------------------------
+// dynamic-panel objective (C4): its kernels use the device functions above
+// ------------------------------------------------------------------------------------------------
+#include "smm_panel.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // launchers (called from smm_api.cu)

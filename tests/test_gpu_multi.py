@@ -20,7 +20,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_chains, n_iter, mode, q):
+def _make_cfg(kind, n_chains, n_iter, data_mom=None, **kw):
+    from smm_jl_b200 import configs
+    if kind == "panel":
+        return configs.dynamic_panel(n_chains, n_iter, 8, 10, 150, data_mom=data_mom, sigma_update_steps=5, **kw)
+    return configs.mvnormal(n_chains, n_iter, **kw)
+
+
+def _worker(rank, world, port, n_chains, n_iter, mode, q, kind="mvnormal", data_mom=None):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -29,7 +36,8 @@ def _worker(rank, world, port, n_chains, n_iter, mode, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         idb = sd.broadcast_id(_lib.nccl_unique_id)
-        cfg = configs.mvnormal(n_chains, n_iter, device=rank, world_size=world, rank=rank, nccl_id=idb, exchange_mode=mode)
+        cfg = _make_cfg(kind, n_chains, n_iter, data_mom, device=rank, world_size=world, rank=rank, nccl_id=idb,
+                        exchange_mode=mode)
         with _lib.BGPHandle(cfg) as h:
             h.step(n_iter // 2)
             h.step(n_iter - n_iter // 2)
@@ -68,3 +76,27 @@ def test_two_gpus_match_the_oracle(smm, oracle, mode):
     np.testing.assert_array_equal(res[0][3], ref.sigma)
     assert res[0][4]["swaps"] == ref.swaps
     assert res[0][4]["collectives"] == (n_iter - 1 if mode == 0 else 0)
+
+
+def test_two_gpus_panel_match_the_oracle(smm, oracle):
+    """dynamic-panel objective sharded over 2 GPUs (ncclAllGather per iteration) = the oracle's single-process run"""
+    from smm_jl_b200 import configs
+    if smm.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n_chains, n_iter = 2, 12, 20
+    dm = configs.panel_data_moments(lambda c, p: oracle.eval_batch(c, p), 8, 10, 150)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_chains, n_iter, 0, q, "panel", dm)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == ["ok"] * world, [r[1] for r in res]
+    from tests.parity import assert_trace_parity
+    ref = oracle.run(_make_cfg("panel", n_chains, n_iter, dm), n_iter, n_threads=8)
+    assert_trace_parity(res[0][2], ref.trace)
+    np.testing.assert_array_equal(res[0][3], ref.sigma)
+    assert res[0][4]["swaps"] == ref.swaps

@@ -43,6 +43,33 @@ def test_objective_numpy_vs_cpp(oracle):
     np.testing.assert_allclose(m[0], m_np, rtol=1e-11, atol=1e-13)
 
 
+@pytest.mark.parametrize("K,T,NI", [(1, 7, 5), (2, 9, 33), (3, 12, 64), (8, 50, 40)])
+def test_panel_objective_numpy_vs_cpp(oracle, K, T, NI):
+    """the C++ panel simulator (two-pass centred moments over the materialised panel) against numpy"""
+    cfg = configs.dynamic_panel(1, 1, K, T, NI)
+    lb, ub = configs.panel_box(K)
+    rng = np.random.default_rng(K * 100 + T)
+    for noseed in (0, 1):
+        p = lb + rng.uniform(0.05, 0.95, lb.size) * (ub - lb)
+        v, m, st = oracle.eval_batch(cfg, p[None, :], noseed=noseed, rep0=7)
+        v_np, m_np = oracle_np.panel_objective(cfg, p, uid=0, rep=7, noseed=noseed)
+        assert st[0] == 1
+        np.testing.assert_allclose(m[0], m_np, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(v[0], v_np, rtol=1e-10)
+
+
+def test_panel_full_algorithm_numpy_vs_cpp(oracle):
+    K, T, NI = 2, 8, 24
+    dm = configs.panel_data_moments(lambda c, p: oracle.eval_batch(c, p), K, T, NI)
+    cfg = configs.dynamic_panel(3, 10, K, T, NI, data_mom=dm, sigma_update_steps=3)
+    r = oracle.run(cfg, 10)
+    w = oracle_np.run(cfg, 10)
+    for f in ("accepted", "status", "exchanged", "best_id"):
+        np.testing.assert_array_equal(getattr(r.trace, f), w[f], err_msg=f)
+    for f in ("value", "prob", "curr_val", "best_val", "params", "sim_moments"):
+        np.testing.assert_allclose(getattr(r.trace, f), w[f], rtol=1e-8, atol=1e-11, err_msg=f)
+
+
 @pytest.mark.parametrize("name", ["c1", "mv_batch1"])
 def test_full_algorithm_numpy_vs_cpp(oracle, name):
     if name == "c1":
