@@ -140,6 +140,14 @@ void smm_bgp_destroy(smm_bgp *h);
  * device error flag was checked).  elapsed_ms (may be NULL) receives the CUDA-event time of the
  * region on the library's stream. */
 int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms);
+/* run!(algo) (AlgoAbstract.jl:27-76) with the trace streamed to the host: iterations i+1 .. i+n_iters are enqueued
+ * in windows of `window` iterations (0 = default); the rows of a finished window are copied into host_out
+ * (row 0 = iteration i+1; [n_iters][L] layout as in smm_bgp_read_trace; NULL = no read-back) on a second stream
+ * while the next window computes.  Blocking.  Pinned host memory (smm_host_alloc, or the host language's own
+ * pinned allocator) makes the copies asynchronous; pageable memory works but serialises them. */
+int smm_bgp_run(smm_bgp *h, int32_t n_iters, int32_t window, const smm_trace_view *host_out, float *elapsed_ms);
+int smm_host_alloc(int64_t nbytes, void **out); /* page-locked host memory for smm_bgp_run / read_trace */
+void smm_host_free(void *p);
 int smm_bgp_iteration(const smm_bgp *h); /* iterations completed so far (algo.i) */
 int smm_bgp_local_chains(const smm_bgp *h);
 void *smm_bgp_stream(smm_bgp *h); /* cudaStream_t the kernels run on */

@@ -22,6 +22,7 @@ EXPORTS = [
     "smm_bgp_state_bytes", "smm_bgp_export_state", "smm_bgp_import_state", "smm_debug_normals",
     "smm_debug_pairs", "smm_debug_rng_throughput", "smm_stream_acc_uniforms", "smm_bgp_set_profiling",
     "smm_bgp_kernel_times", "smm_debug_phase_ts", "smm_debug_sim_throughput", "smm_debug_barrier_bench",
+    "smm_bgp_run", "smm_host_alloc", "smm_host_free",
 ]
 
 
@@ -54,6 +55,10 @@ def lib():
     L.smm_bgp_destroy.restype = None
     L.smm_bgp_step.argtypes = [vp, C.c_int32, C.POINTER(C.c_float)]
     L.smm_bgp_iteration.argtypes = [vp]
+    L.smm_bgp_run.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(smm_trace_view), C.POINTER(C.c_float)]
+    L.smm_host_alloc.argtypes = [C.c_int64, C.POINTER(vp)]
+    L.smm_host_free.argtypes = [vp]
+    L.smm_host_free.restype = None
     L.smm_bgp_local_chains.argtypes = [vp]
     L.smm_bgp_stream.argtypes = [vp]
     L.smm_bgp_stream.restype = vp
@@ -93,6 +98,59 @@ def nccl_unique_id() -> bytes:
     return bytes(buf)
 
 
+class PinnedTrace(Trace):
+    """A `Trace` whose columns live in page-locked host memory (smm_host_alloc), so that smm_bgp_run /
+    smm_bgp_read_trace copy into it asynchronously."""
+
+    def __init__(self, n: int, L: int, P: int, M: int):
+        self.n, self.L, self.P, self.M = n, L, P, M
+        shapes = {"value": (n, L), "prob": (n, L), "curr_val": (n, L), "best_val": (n, L), "params": (n, L, P),
+                  "sim_moments": (n, L, M), "accepted": (n, L), "status": (n, L), "exchanged": (n, L), "best_id": (n, L)}
+        dtypes = {"accepted": np.uint8, "status": np.int32, "exchanged": np.int32, "best_id": np.int32}
+        sizes = {f: int(np.prod(sh)) * np.dtype(dtypes.get(f, np.float64)).itemsize for f, sh in shapes.items()}
+        total = sum((v + 63) // 64 * 64 for v in sizes.values())
+        self._base = C.c_void_p()
+        check(lib().smm_host_alloc(total, C.byref(self._base)))
+        off = 0
+        for f, sh in shapes.items():
+            dt = np.dtype(dtypes.get(f, np.float64))
+            buf = (C.c_char * sizes[f]).from_address(self._base.value + off)
+            setattr(self, f, np.frombuffer(buf, dtype=dt).reshape(sh))
+            off += (sizes[f] + 63) // 64 * 64
+
+    _pool: dict = {}
+
+    @classmethod
+    def acquire(cls, n: int, L: int, P: int, M: int) -> "PinnedTrace":
+        """a buffer from the free list (page-locking 60 MB costs milliseconds; estimations are run repeatedly)"""
+        free = cls._pool.get((n, L, P, M))
+        return free.pop() if free else cls(n, L, P, M)
+
+    def release(self):
+        """back to the free list; the caller must not keep views into the columns"""
+        if getattr(self, "_base", None) is not None and self._base.value:
+            lst = PinnedTrace._pool.setdefault((self.n, self.L, self.P, self.M), [])
+            if len(lst) < 2:
+                lst.append(self)
+            else:
+                self.free()
+
+    def free(self):
+        if getattr(self, "_base", None) is not None and self._base.value:
+            for f in Trace.FLOAT_FIELDS + Trace.INT_FIELDS:   # detach the views first
+                setattr(self, f, np.array(getattr(self, f)))
+            lib().smm_host_free(self._base)
+            self._base = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_base", None) is not None and self._base.value:
+                lib().smm_host_free(self._base)
+                self._base = C.c_void_p()
+        except Exception:  # pragma: no cover
+            pass
+
+
 class BGPHandle:
     """Thin owner of an `smm_bgp*`: create / step / read_trace / destroy."""
 
@@ -128,6 +186,19 @@ class BGPHandle:
         """Run n_iters iterations; returns the CUDA-event time of the region in ms."""
         ms = C.c_float(0.0)
         check(lib().smm_bgp_step(self._h, n_iters, C.byref(ms)))
+        return ms.value
+
+    def run(self, n_iters: int, into: Trace | None = None, window: int = 0) -> float:
+        """Run n_iters iterations, streaming their trace rows into `into` (row 0 = the first new iteration)
+        while the device keeps computing; returns the CUDA-event time of the compute region in ms."""
+        ms = C.c_float(0.0)
+        if into is not None:
+            if into.n < n_iters or into.L != self.L:
+                raise ValueError("trace buffer too small for this run")
+            v = into.view()
+            check(lib().smm_bgp_run(self._h, n_iters, window, C.byref(v), C.byref(ms)))
+        else:
+            check(lib().smm_bgp_run(self._h, n_iters, window, None, C.byref(ms)))
         return ms.value
 
     def read_trace(self, iter_lo: int = 1, iter_hi: int | None = None, into: Trace | None = None) -> Trace:

@@ -374,8 +374,8 @@ class BGPChain:
 
         self._value, self._prob = col1(tr.value, np.nan), col1(tr.prob, np.nan)
         self._status = col1(tr.status, 0)
-        self._params = tr.params[:, col, :]
-        self._mom = tr.sim_moments[:, col, :]
+        self._params = tr.params[:, col, :].copy()      # copies: the trace buffer may be pinned memory that is
+        self._mom = tr.sim_moments[:, col, :].copy()     # recycled when the algo is closed
         self.best_id = col1(tr.best_id, -1).astype(int)
         self.best_val = col1(tr.best_val, np.inf)
         self.curr_val = col1(tr.curr_val, np.inf)
@@ -503,6 +503,11 @@ class MAlgoBGP:
         if self._h is not None:
             self._h.close()
             self._h = None
+        st = getattr(self, "_streamed", None)
+        if st is not None:            # chains already materialised hold copies, not views
+            self._trace = None
+            st.release()
+            self._streamed = None
 
     @property
     def chains(self) -> "list[BGPChain]":
@@ -520,8 +525,11 @@ class MAlgoBGP:
             sigma = np.asarray(cfg.sigma0, float)[c0:c0 + L]
             acc = np.zeros(L)
         else:
+            if self._h is None:
+                raise RuntimeError("this MAlgoBGP was closed: its device state and trace are gone (read algo.chains before close())")
             h = self._handle()
-            tr = h.read_trace(1, self.i)
+            st = getattr(self, "_streamed", None)
+            tr = st if (st is not None and st.n == self.i) else h.read_trace(1, self.i)
             sigma, acc = h.chain_state()
         self._trace = tr
         self._chains = []
@@ -541,14 +549,24 @@ def computeNextIteration(algo: MAlgoBGP, n: int = 1):
     algo.device_ms += h.step(n)
     algo.i = h.iteration
     algo._chains = None
+    algo._streamed = None
 
 
 def run(algo: MAlgoBGP):
-    """run!(algo) (AlgoAbstract.jl:27-76): iterations 1..maxiter, optional periodic save."""
+    """run!(algo) (AlgoAbstract.jl:27-76): iterations 1..maxiter, optional periodic save.  Without periodic saves
+    the whole run is one `smm_bgp_run` call: the trace streams into page-locked host memory window by window
+    while the device computes the next window, and `algo.chains` is served from that host copy."""
     t0 = _time.time()
     maxiter = int(algo["maxiter"])
     sf, fn = algo.opts.get("save_frequency"), algo.opts.get("filename")
     chunk = int(sf) if (sf and fn) else maxiter
+    if not (sf and fn) and algo.i == 0 and maxiter > 0:
+        h = algo._handle()
+        tr = _lib.PinnedTrace.acquire(maxiter, h.L, algo._cfg.n_params, algo._cfg.n_moments)
+        algo.device_ms += h.run(maxiter, into=tr)
+        algo.i = h.iteration
+        algo._chains = None
+        algo._streamed = tr
     while algo.i < maxiter:
         computeNextIteration(algo, min(chunk, maxiter - algo.i))
         if sf and fn and algo.i % int(sf) == 0:

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -31,13 +32,13 @@ void launch_objective(const DevProblem &pb, const double *params, int B, int nos
                       int part_len, double *partials, unsigned *arrive, double *value, double *moments, int *status,
                       cudaStream_t s);
 size_t panel_smem_bytes(int K, int P);
-cudaError_t configure_panel(int K, int P);
-int panel_max_blocks_per_sm(int K, int P);
+cudaError_t configure_panel(int K, int P, int variant);
+int panel_max_blocks_per_sm(int K, int P, int variant);
 void launch_propose(const DevProblem &pb, const DevState &st, int iter, int zero_len, cudaStream_t s);
-void launch_panel_chains(const DevProblem &pb, const DevState &st, int iter, int grid, cudaStream_t s);
+void launch_panel_chains(const DevProblem &pb, const DevState &st, int iter, int grid, int variant, cudaStream_t s);
 void launch_panel_batch(const DevProblem &pb, const DevState &st, const double *params, int B, int noseed, uint32_t uid0,
                         uint32_t rep0, unsigned long long *acc, unsigned *done, unsigned *unit_ctr, double *value,
-                        double *moments, int *status, int grid, cudaStream_t s);
+                        double *moments, int *status, int grid, int variant, cudaStream_t s);
 void launch_debug_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, double *out,
                           cudaStream_t s);
 void launch_rng_throughput(long long n_per_thread, int blocks, double *out, cudaStream_t s);
@@ -71,16 +72,41 @@ int fail(int code, const std::string &msg) {
       return fail(SMM_E_NCCL, std::string(#expr) + ": " + ncclGetErrorString(r__));             \
   } while (0)
 
+// Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync on the legacy stream)
+// whose release threshold is raised once per device, so that the memory of a destroyed handle stays mapped and
+// the next smm_bgp_create / smm_bgp_eval_batch gets it back in microseconds: estimations are run repeatedly
+// (cudaMalloc + cudaFree of the ~45 buffers of a handle cost tens to hundreds of milliseconds).  Buffers that are
+// exported over CUDA IPC (fused multi-GPU mode) must be plain cudaMalloc allocations: alloc(count, true).
+void pool_setup_once(int device) {
+  static bool done[64] = {false};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done[device] = true;
+}
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
-  cudaError_t alloc(size_t count) {
+  bool plain = false;
+  cudaError_t alloc(size_t count, bool ipc = false) {
     n = count;
-    return cudaMalloc((void **)&p, sizeof(T) * (count ? count : 1));
+    plain = ipc;
+    if (ipc) return cudaMalloc((void **)&p, sizeof(T) * (count ? count : 1));
+    return cudaMallocAsync((void **)&p, sizeof(T) * (count ? count : 1), (cudaStream_t)0);
   }
   void free() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (plain)
+        cudaFree(p);
+      else
+        cudaFreeAsync(p, (cudaStream_t)0);
+    }
     p = nullptr;
   }
 };
@@ -95,13 +121,15 @@ struct smm_bgp {
   double eval_param_limit = 0.0;  // |param| bound for which the fixed-point accumulators are sized
   bool panel = false;     // SMM_OBJ_PANEL: propose kernel + panel simulation kernel instead of bgp_eval_kernel
   int panel_grid = 0;     // CTAs of the panel simulation kernel (one resident wave)
+  int panel_variant = 2;  // register budget of the K = 8 instantiation (CTAs per SM)
   std::vector<double> h_lb, h_ub;
   int mode = 0;           // 0 = multi-launch (+ NCCL), 1 = persistent kernel (+ fused peer-store all-gather)
   int grid = 0, max_seg = 1, cta_seg = 1;  // persistent kernel: CTAs, partial slots per chain, chains per CTA share
   void *peer_ptrs[3 * kMaxWorld] = {nullptr};  // IPC-opened peer buffers (closed in release)
   int iter = 0;      // iterations completed (algo.i)
   int sched_iter0 = -1, sched_n = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  std::vector<cudaEvent_t> win_ev;  // window boundaries of smm_bgp_run
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   ncclComm_t comm = nullptr;
   DevProblem pb{};
@@ -128,6 +156,9 @@ struct smm_bgp {
   DevBuf<unsigned long long> counters, phase_ts;
 
   void release() {
+    // the buffers go back to the pool in legacy-stream order: drain this handle's own streams first
+    if (stream) cudaStreamSynchronize(stream);
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
     for (void *&q : peer_ptrs) {
       if (q) cudaIpcCloseMemHandle(q);
       q = nullptr;
@@ -144,6 +175,10 @@ struct smm_bgp {
     counters.free(); phase_ts.free();
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
     prof_ev.clear();
+    for (cudaEvent_t e : win_ev) cudaEventDestroy(e);
+    win_ev.clear();
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    copy_stream = nullptr;
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -218,10 +253,18 @@ int upload(DevBuf<T> &buf, const T *src, size_t n) {
 }
 
 template <typename T>
-int fill(DevBuf<T> &buf, size_t n, T v) {
-  CUDA_TRY(buf.alloc(n));
-  std::vector<T> h(n, v);
-  CUDA_TRY(cudaMemcpy(buf.p, h.data(), sizeof(T) * n, cudaMemcpyHostToDevice));
+__global__ void fill_kernel(T *p, size_t n, T v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// allocate + fill on the device (asynchronous on the legacy stream; smm_bgp_create synchronises at its end)
+template <typename T>
+int fill(DevBuf<T> &buf, size_t n, T v, bool ipc = false) {
+  CUDA_TRY(buf.alloc(n, ipc));
+  if (n == 0) return 0;
+  const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  fill_kernel<T><<<blocks, 256>>>(buf.p, n, v);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -292,11 +335,19 @@ void smm_bgp_destroy(smm_bgp *h) {
 
 int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   if (!out) return fail(SMM_E_ARG, "null output handle");
+  const bool timing = getenv("SMM_TIMING") != nullptr;
+  const auto tc0 = std::chrono::steady_clock::now();
+  auto stamp = [&](const char *what) {
+    if (timing)
+      fprintf(stderr, "[smm_bgp_create] %-28s %8.3f ms\n", what,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
+  };
   *out = nullptr;
   if (int rc = check_config(cfg)) return rc;
   if (smm_device_count() <= cfg->device || cfg->device < 0)
     return fail(SMM_E_CUDA, "no such CUDA device (this library has no CPU fallback)");
   CUDA_TRY(cudaSetDevice(cfg->device));
+  pool_setup_once(cfg->device);
   smm_bgp *h = new smm_bgp();
   struct Guard {
     smm_bgp *h;
@@ -325,6 +376,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
 
+  stamp("stream + events");
   if (int rc = upload(h->lb, cfg->lb, P)) return rc;
   if (int rc = upload(h->ub, cfg->ub, P)) return rc;
   if (int rc = upload(h->init, cfg->init, P)) return rc;
@@ -341,13 +393,13 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   if (int rc = fill(h->la_pub, (size_t)L * R, nan)) return rc;
   h->mode = cfg->exchange_mode ? 1 : 0;
   if (h->world > 1) {
-    if (int rc = fill(h->la_all, (size_t)(h->mode ? 2 : 1) * N * R, nan)) return rc;
+    if (int rc = fill(h->la_all, (size_t)(h->mode ? 2 : 1) * N * R, nan, h->mode == 1)) return rc;
   }
-  if (int rc = fill(h->val_all, (size_t)2 * N, nan)) return rc;
+  if (int rc = fill(h->val_all, (size_t)2 * N, nan, h->world > 1 && h->mode == 1)) return rc;
   if (int rc = fill(h->pp, (size_t)L * P, nan)) return rc;
   if (int rc = fill(h->bar, 1, GridBarrier{0u, 0u})) return rc;
   if (int rc = fill(h->sync_seq, 1, 0ull)) return rc;
-  if (int rc = fill(h->flags, (size_t)kMaxWorld, 0ull)) return rc;
+  if (int rc = fill(h->flags, (size_t)kMaxWorld, 0ull, h->world > 1 && h->mode == 1)) return rc;
   // trace: unrun slots look like a fresh BGPChain (AlgoBGP.jl:81-89); Eval slots are `undef` -> NaN
   const size_t IL = (size_t)I * L;
   if (int rc = fill(h->t_value, IL, nan)) return rc;
@@ -361,8 +413,11 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   if (int rc = fill(h->t_exch, IL, 0)) return rc;
   if (int rc = fill(h->t_bestid, IL, -1)) return rc;
 
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  stamp("buffers + trace fill");
+  struct {
+    int multiProcessorCount = 0;
+  } prop;  // (cudaGetDeviceProperties costs milliseconds; one attribute is all that is needed)
+  CUDA_TRY(cudaDeviceGetAttribute(&prop.multiProcessorCount, cudaDevAttrMultiProcessorCount, cfg->device));
   h->part_len = 2 * P;
   const int n_blocks_philox = (cfg->n_sim + 1) / 2;
   h->n_split = choose_split(L, prop.multiProcessorCount, eval_max_blocks_per_sm(), n_blocks_philox, cfg->n_split);
@@ -373,8 +428,9 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   if (h->panel) {
     h->n_split = 1;
     h->part_len = 2 * panel_na(cfg->panel_K);  // (hi, lo) fixed-point words per raw sum
-    CUDA_TRY(configure_panel(cfg->panel_K, P));
-    const int per_sm = panel_max_blocks_per_sm(cfg->panel_K, P);
+    if (const char *v = getenv("SMM_PANEL_VARIANT")) h->panel_variant = atoi(v) == 3 ? 3 : 2;
+    CUDA_TRY(configure_panel(cfg->panel_K, P, h->panel_variant));
+    const int per_sm = panel_max_blocks_per_sm(cfg->panel_K, P, h->panel_variant);
     if (per_sm < 1) return fail(SMM_E_CUDA, "panel simulation kernel does not fit on an SM");
     h->panel_grid = prop.multiProcessorCount * per_sm;
     if (cfg->n_split > 0 && cfg->n_split < h->panel_grid) h->panel_grid = cfg->n_split;  // n_split caps the CTA count
@@ -500,6 +556,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     st.phase_ts = h->phase_ts.p;
   }
 
+  stamp("kernel configuration");
   if (h->world > 1) {
     if (h->world > kMaxWorld) return fail(SMM_E_ARG, "world_size > 8");
     ncclUniqueId id;
@@ -514,8 +571,8 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
       CUDA_TRY(cudaIpcGetMemHandle(&mine.val, h->val_all.p));
       CUDA_TRY(cudaIpcGetMemHandle(&mine.flags, h->flags.p));
       DevBuf<char> d_mine, d_all;
-      CUDA_TRY(d_mine.alloc(sizeof(Handles)));
-      CUDA_TRY(d_all.alloc(sizeof(Handles) * h->world));
+      CUDA_TRY(d_mine.alloc(sizeof(Handles), true));
+      CUDA_TRY(d_all.alloc(sizeof(Handles) * h->world, true));
       CUDA_TRY(cudaMemcpy(d_mine.p, &mine, sizeof mine, cudaMemcpyHostToDevice));
       ncclResult_t nr = ncclAllGather(d_mine.p, d_all.p, sizeof(Handles), ncclChar, h->comm, h->stream);
       std::vector<Handles> all(h->world);
@@ -545,7 +602,9 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
       }
     }
   }
+  stamp("communicator");
   CUDA_TRY(cudaDeviceSynchronize());
+  stamp("device synchronize");
   guard.ok = true;
   *out = h;
   return 0;
@@ -555,31 +614,31 @@ int smm_bgp_iteration(const smm_bgp *h) { return h ? h->iter : -1; }
 int smm_bgp_local_chains(const smm_bgp *h) { return h ? h->L : -1; }
 void *smm_bgp_stream(smm_bgp *h) { return h ? (void *)h->stream : nullptr; }
 
-int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
-  if (!h) return fail(SMM_E_ARG, "null handle");
-  if (n_iters < 0 || h->iter + n_iters > h->max_iter)
-    return fail(SMM_E_ARG, "step would exceed max_iter (use restart!/extend to grow the chains)");
-  CUDA_TRY(cudaSetDevice(h->device));
+}  // extern "C"
+
+namespace {
+
+cudaError_t prof_begin(smm_bgp *h, int kind) {
+  if (!h->profiling) return cudaSuccess;
+  const size_t i = h->prof_kind.size();
+  while (h->prof_ev.size() < 2 * (i + 1)) {
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreate(&e);
+    if (rc != cudaSuccess) return rc;
+    h->prof_ev.push_back(e);
+  }
+  h->prof_kind.push_back(kind);
+  return cudaEventRecord(h->prof_ev[2 * i], h->stream);
+}
+cudaError_t prof_end(smm_bgp *h) {
+  if (!h->profiling) return cudaSuccess;
+  return cudaEventRecord(h->prof_ev[2 * (h->prof_kind.size() - 1) + 1], h->stream);
+}
+
+// enqueue iterations i+1 .. i+n_iters on the handle's stream (no synchronisation)
+int enqueue_iterations(smm_bgp *h, int n_iters) {
   cudaStream_t s = h->stream;
-  CUDA_TRY(cudaEventRecord(h->ev0, s));
   const bool exchange = h->N > 1;
-  h->prof_kind.clear();
-  auto prof_begin = [&](int kind) -> cudaError_t {
-    if (!h->profiling) return cudaSuccess;
-    const size_t i = h->prof_kind.size();
-    while (h->prof_ev.size() < 2 * (i + 1)) {
-      cudaEvent_t e;
-      cudaError_t rc = cudaEventCreate(&e);
-      if (rc != cudaSuccess) return rc;
-      h->prof_ev.push_back(e);
-    }
-    h->prof_kind.push_back(kind);
-    return cudaEventRecord(h->prof_ev[2 * i], s);
-  };
-  auto prof_end = [&]() -> cudaError_t {
-    if (!h->profiling) return cudaSuccess;
-    return cudaEventRecord(h->prof_ev[2 * (h->prof_kind.size() - 1) + 1], s);
-  };
   if (h->mode == 1) {
     int left = n_iters;
     while (left > 0) {
@@ -593,19 +652,19 @@ int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
             (h->sched_iter0 < 0 || first_ex < h->sched_iter0 || first_ex >= h->sched_iter0 + h->sched_n)) {
           int w = h->max_iter - first_ex + 1;
           if (w > kPairChunk) w = kPairChunk;
-          CUDA_TRY(prof_begin(2));
+          CUDA_TRY(prof_begin(h, 2));
           launch_pairs(h->pb, h->st, first_ex, w, h->n_s, s);
-          CUDA_TRY(prof_end());
+          CUDA_TRY(prof_end(h));
           h->ctr.kernel_launches++;
           h->sched_iter0 = first_ex;
           h->sched_n = w;
         }
         if (h->sched_iter0 >= 0 && it0 + n > h->sched_iter0 + h->sched_n) n = h->sched_iter0 + h->sched_n - it0;
       }
-      CUDA_TRY(prof_begin(0));
+      CUDA_TRY(prof_begin(h, 0));
       CUDA_TRY(launch_persistent(h->pb, h->st, it0, n, h->sched_iter0 < 0 ? 2 : h->sched_iter0, h->n_s, h->part_len,
                                  h->max_seg, h->cta_seg, h->grid, s));
-      CUDA_TRY(prof_end());
+      CUDA_TRY(prof_end(h));
       h->prof_iters += h->profiling ? n : 0;
       h->ctr.kernel_launches++;
       h->iter += n;
@@ -618,42 +677,44 @@ int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
       // precompute Pairs[it .. it+chunk) and their level schedules
       int n = h->max_iter - it + 1;
       if (n > kPairChunk) n = kPairChunk;
-      CUDA_TRY(prof_begin(2));
+      CUDA_TRY(prof_begin(h, 2));
       launch_pairs(h->pb, h->st, it, n, h->n_s, s);
-      CUDA_TRY(prof_end());
+      CUDA_TRY(prof_end(h));
       h->sched_iter0 = it;
       h->sched_n = n;
       h->ctr.kernel_launches++;
     }
-    CUDA_TRY(prof_begin(0));
+    CUDA_TRY(prof_begin(h, 0));
     if (h->panel) {
       launch_propose(h->pb, h->st, it, h->part_len, s);
-      launch_panel_chains(h->pb, h->st, it, h->panel_grid, s);
+      launch_panel_chains(h->pb, h->st, it, h->panel_grid, h->panel_variant, s);
       h->ctr.kernel_launches++;
     } else {
       launch_eval(h->pb, h->st, it, h->n_split, h->part_len, s);
     }
-    CUDA_TRY(prof_end());
+    CUDA_TRY(prof_end(h));
     h->prof_iters += h->profiling ? 1 : 0;
     h->ctr.kernel_launches++;
     if (exchange && it >= 2) {  // AlgoBGP.jl:637
       if (h->world > 1) {
-        CUDA_TRY(prof_begin(3));
+        CUDA_TRY(prof_begin(h, 3));
         NCCL_TRY(ncclAllGather(h->st.la_pub, h->st.la_all, (size_t)h->L * h->R, ncclDouble, h->comm, s));
-        CUDA_TRY(prof_end());
+        CUDA_TRY(prof_end(h));
         h->ctr.collectives++;
       }
-      CUDA_TRY(prof_begin(1));
+      CUDA_TRY(prof_begin(h, 1));
       launch_exchange(h->pb, h->st, it, it - h->sched_iter0, h->n_s, s);
-      CUDA_TRY(prof_end());
+      CUDA_TRY(prof_end(h));
       h->ctr.kernel_launches++;
     }
     h->iter = it;
   }
-  CUDA_TRY(cudaEventRecord(h->ev1, s));
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(s));
-  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  return 0;
+}
+
+// after the stream drained: per-kernel times (profiling), counters, the sticky device error flag
+int finish_step(smm_bgp *h) {
   for (size_t i = 0; i < h->prof_kind.size(); ++i) {
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
@@ -667,15 +728,14 @@ int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
   return device_error_to_rc(flags);
 }
 
-int smm_bgp_read_trace(smm_bgp *h, int32_t iter_lo, int32_t iter_hi, const smm_trace_view *out) {
-  if (!h || !out) return fail(SMM_E_ARG, "null argument");
-  if (iter_lo < 1 || iter_hi < iter_lo || iter_hi > h->max_iter) return fail(SMM_E_ARG, "bad iteration range");
-  CUDA_TRY(cudaSetDevice(h->device));
+// D2H of trace rows [iter_lo, iter_hi] into `out`, whose row 0 is iteration `out_iter0`, on stream s
+int enqueue_trace_copy(smm_bgp *h, int iter_lo, int iter_hi, int out_iter0, const smm_trace_view *out, cudaStream_t s) {
   const size_t L = h->L, off = (size_t)(iter_lo - 1) * L, n = (size_t)(iter_hi - iter_lo + 1) * L;
-  cudaStream_t s = h->stream;
+  const size_t ooff = (size_t)(iter_lo - out_iter0) * L;
 #define COPY(dst, src, T, mult)                                                                              \
   if (out->dst)                                                                                              \
-    CUDA_TRY(cudaMemcpyAsync(out->dst, h->st.src + off * (mult), sizeof(T) * n * (mult), cudaMemcpyDeviceToHost, s))
+    CUDA_TRY(cudaMemcpyAsync(out->dst + ooff * (mult), h->st.src + off * (mult), sizeof(T) * n * (mult),     \
+                             cudaMemcpyDeviceToHost, s))
   COPY(value, t_value, double, 1);
   COPY(prob, t_prob, double, 1);
   COPY(curr_val, t_curr, double, 1);
@@ -687,6 +747,87 @@ int smm_bgp_read_trace(smm_bgp *h, int32_t iter_lo, int32_t iter_hi, const smm_t
   COPY(exchanged, t_exch, int32_t, 1);
   COPY(best_id, t_bestid, int32_t, 1);
 #undef COPY
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
+  if (!h) return fail(SMM_E_ARG, "null handle");
+  if (n_iters < 0 || h->iter + n_iters > h->max_iter)
+    return fail(SMM_E_ARG, "step would exceed max_iter (use restart!/extend to grow the chains)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaEventRecord(h->ev0, s));
+  h->prof_kind.clear();
+  if (int rc = enqueue_iterations(h, n_iters)) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev1, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  return finish_step(h);
+}
+
+// run!(algo) with the trace streamed to the host: iterations are enqueued in windows; the rows of a finished
+// window travel to `host_out` on the copy stream while the next window computes.
+int smm_bgp_run(smm_bgp *h, int32_t n_iters, int32_t window, const smm_trace_view *host_out, float *elapsed_ms) {
+  if (!h) return fail(SMM_E_ARG, "null handle");
+  if (n_iters < 0 || h->iter + n_iters > h->max_iter)
+    return fail(SMM_E_ARG, "run would exceed max_iter (use restart!/extend to grow the chains)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (window <= 0) window = kPairChunk;
+  cudaStream_t s = h->stream;
+  if (!h->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventRecord(h->ev0, s));
+  h->prof_kind.clear();
+  const int first = h->iter + 1;
+  size_t wi = 0;
+  for (int left = n_iters; left > 0;) {
+    const int it0 = h->iter + 1;
+    int n = left < window ? left : window;
+    // keep windows aligned with the precomputed pair-schedule windows, so a launch never has to be cut in two
+    if (h->mode == 1 && h->N > 1 && h->sched_iter0 >= 0 && it0 >= h->sched_iter0 &&
+        it0 < h->sched_iter0 + h->sched_n && it0 + n > h->sched_iter0 + h->sched_n)
+      n = h->sched_iter0 + h->sched_n - it0;
+    if (int rc = enqueue_iterations(h, n)) return rc;
+    left -= n;
+    if (host_out) {
+      while (h->win_ev.size() <= wi) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->win_ev.push_back(e);
+      }
+      CUDA_TRY(cudaEventRecord(h->win_ev[wi], s));
+      CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->win_ev[wi], 0));
+      if (int rc = enqueue_trace_copy(h, it0, it0 + n - 1, first, host_out, h->copy_stream)) return rc;
+      ++wi;
+    }
+  }
+  CUDA_TRY(cudaEventRecord(h->ev1, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (host_out) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  return finish_step(h);
+}
+
+int smm_host_alloc(int64_t nbytes, void **out) {
+  if (!out || nbytes < 0) return fail(SMM_E_ARG, "bad argument");
+  *out = nullptr;
+  CUDA_TRY(cudaHostAlloc(out, (size_t)(nbytes ? nbytes : 1), cudaHostAllocDefault));
+  return 0;
+}
+
+void smm_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int smm_bgp_read_trace(smm_bgp *h, int32_t iter_lo, int32_t iter_hi, const smm_trace_view *out) {
+  if (!h || !out) return fail(SMM_E_ARG, "null argument");
+  if (iter_lo < 1 || iter_hi < iter_lo || iter_hi > h->max_iter) return fail(SMM_E_ARG, "bad iteration range");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  if (int rc = enqueue_trace_copy(h, iter_lo, iter_hi, iter_lo, out, s)) return rc;
   CUDA_TRY(cudaStreamSynchronize(s));
   return 0;
 }
@@ -739,20 +880,25 @@ int smm_bgp_eval_batch(smm_bgp *h, const double *params, int32_t B, int32_t nose
       DevBuf<unsigned long long> &d;
       DevBuf<int> &e;
       DevBuf<unsigned> &f;
-      ~FreeP() { a.free(); b.free(); c.free(); d.free(); e.free(); f.free(); }
-    } frp{d_params, d_value, d_mom, d_acc, d_status, d_done};
+      cudaStream_t st;
+      ~FreeP() {
+        cudaStreamSynchronize(st);
+        a.free(); b.free(); c.free(); d.free(); e.free(); f.free();
+      }
+    } frp{d_params, d_value, d_mom, d_acc, d_status, d_done, h->stream};
     CUDA_TRY(d_params.alloc((size_t)B * P));
     CUDA_TRY(d_value.alloc(B));
     CUDA_TRY(d_mom.alloc((size_t)B * M));
     CUDA_TRY(d_acc.alloc((size_t)B * h->part_len));
     CUDA_TRY(d_status.alloc(B));
     CUDA_TRY(d_done.alloc((size_t)B + 1));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));  // pool allocations are ordered on the legacy stream
     cudaStream_t s = h->stream;
     CUDA_TRY(cudaMemcpyAsync(d_params.p, params, sizeof(double) * B * P, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(d_acc.p, 0, sizeof(unsigned long long) * (size_t)B * h->part_len, s));
     CUDA_TRY(cudaMemsetAsync(d_done.p, 0, sizeof(unsigned) * ((size_t)B + 1), s));
     launch_panel_batch(h->pb, h->st, d_params.p, B, noseed, 0u, rep0, d_acc.p, d_done.p, d_done.p + B, d_value.p, d_mom.p,
-                       d_status.p, h->panel_grid, s);
+                       d_status.p, h->panel_grid, h->panel_variant, s);
     h->ctr.kernel_launches++;
     CUDA_TRY(cudaGetLastError());
     if (value) CUDA_TRY(cudaMemcpyAsync(value, d_value.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
@@ -769,14 +915,19 @@ int smm_bgp_eval_batch(smm_bgp *h, const double *params, int32_t B, int32_t nose
     DevBuf<double> &a, &b, &c, &d;
     DevBuf<int> &e;
     DevBuf<unsigned> &f;
-    ~Free() { a.free(); b.free(); c.free(); d.free(); e.free(); f.free(); }
-  } fr{d_params, d_value, d_mom, d_part, d_status, d_arrive};
+    cudaStream_t st;
+    ~Free() {
+      cudaStreamSynchronize(st);
+      a.free(); b.free(); c.free(); d.free(); e.free(); f.free();
+    }
+  } fr{d_params, d_value, d_mom, d_part, d_status, d_arrive, h->stream};
   CUDA_TRY(d_params.alloc((size_t)B * P));
   CUDA_TRY(d_value.alloc(B));
   CUDA_TRY(d_mom.alloc((size_t)B * M));
   CUDA_TRY(d_part.alloc((size_t)B * n_split * h->part_len));
   CUDA_TRY(d_status.alloc(B));
   CUDA_TRY(d_arrive.alloc(B));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));  // pool allocations are ordered on the legacy stream
   cudaStream_t s = h->stream;
   CUDA_TRY(cudaMemcpyAsync(d_params.p, params, sizeof(double) * B * P, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemsetAsync(d_arrive.p, 0, sizeof(unsigned) * B, s));
@@ -922,7 +1073,7 @@ int smm_debug_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, ui
   if (smm_device_count() <= device) return fail(SMM_E_CUDA, "no such CUDA device");
   CUDA_TRY(cudaSetDevice(device));
   DevBuf<double> d;
-  CUDA_TRY(d.alloc((size_t)2 * n_pairs));
+  CUDA_TRY(d.alloc((size_t)2 * n_pairs, true));
   launch_debug_normals(seed, k, c2, c3, n_pairs, d.p, 0);
   cudaError_t e = cudaMemcpy(out, d.p, sizeof(double) * 2 * n_pairs, cudaMemcpyDeviceToHost);
   d.free();
@@ -975,7 +1126,7 @@ int smm_debug_sim_throughput(smm_bgp *h, int32_t n_pairs_per_thread, int32_t blo
   if (!h || threads < 32 || threads > 1024 || threads % 32 || blocks < 1) return fail(SMM_E_ARG, "bad argument");
   CUDA_TRY(cudaSetDevice(h->device));
   DevBuf<double> d;
-  CUDA_TRY(d.alloc((size_t)blocks * threads * 2));
+  CUDA_TRY(d.alloc((size_t)blocks * threads * 2, true));
   cudaStream_t s = h->stream;
   launch_sim_throughput(h->pb, n_pairs_per_thread, blocks, threads, dynamic, d.p, s);  // warm-up
   CUDA_TRY(cudaEventRecord(h->ev0, s));
@@ -996,7 +1147,7 @@ int smm_debug_rng_throughput(int32_t device, int64_t n_pairs_per_thread, int32_t
   CUDA_TRY(cudaSetDevice(device));
   DevBuf<double> d;
   const size_t n = (size_t)blocks * kEvalThreads * 2;
-  CUDA_TRY(d.alloc(n));
+  CUDA_TRY(d.alloc(n, true));
   cudaEvent_t a, b;
   CUDA_TRY(cudaEventCreate(&a));
   CUDA_TRY(cudaEventCreate(&b));

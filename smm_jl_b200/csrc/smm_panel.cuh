@@ -237,8 +237,8 @@ __host__ __device__ inline size_t panel_warp_smem_doubles(int K, int P) {
   return (size_t)panel_na(K) * kPanelStageStride + (size_t)P;
 }
 
-template <int KT>
-__global__ void __launch_bounds__(kPanelThreads, KT > 0 ? 2 : 1)
+template <int KT, int MINB>
+__global__ void __launch_bounds__(kPanelThreads, MINB)
     panel_sim_kernel(DevProblem pb, DevState st, PanelWork w) {
   constexpr int KM = KT > 0 ? KT : kPanelMaxK;
   constexpr int NAM = 14 + 6 * KM;        // raw sums (compile-time bound)
@@ -362,26 +362,28 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_propose_kernel(DevProblem pb
 
 size_t panel_smem_bytes(int K, int P) { return sizeof(double) * panel_warp_smem_doubles(K, P) * (kPanelThreads / 32); }
 
-cudaError_t configure_panel(int K, int P) {
-  if (K == 8)
-    return cudaFuncSetAttribute(panel_sim_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)panel_smem_bytes(K, P));
-  return cudaFuncSetAttribute(panel_sim_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+// K = 8 (the C4 shape) has a register-resident instantiation; `variant` picks its register budget
+// (CTAs per SM the compiler must make room for: 2 -> 255 registers, 3 -> 168 with some spills)
+typedef void (*PanelKernel)(DevProblem, DevState, PanelWork);
+static PanelKernel panel_kernel(int K, int variant) {
+  if (K == 8) return variant == 3 ? panel_sim_kernel<8, 3> : panel_sim_kernel<8, 2>;
+  return panel_sim_kernel<0, 1>;
+}
+
+cudaError_t configure_panel(int K, int P, int variant) {
+  return cudaFuncSetAttribute(panel_kernel(K, variant), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)panel_smem_bytes(K, P));
 }
-int panel_max_blocks_per_sm(int K, int P) {
+int panel_max_blocks_per_sm(int K, int P, int variant) {
   int n = 0;
-  if (K == 8)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, panel_sim_kernel<8>, kPanelThreads, panel_smem_bytes(K, P));
-  else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, panel_sim_kernel<0>, kPanelThreads, panel_smem_bytes(K, P));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, panel_kernel(K, variant), kPanelThreads, panel_smem_bytes(K, P));
   return n;
 }
 void launch_propose(const DevProblem &pb, const DevState &st, int iter, int zero_len, cudaStream_t s) {
   bgp_propose_kernel<<<pb.L, kEvalThreads, 0, s>>>(pb, st, iter, zero_len);
 }
 // chain mode (iter >= 1): evaluations = the local chains' proposals in st.pp, sums in st.partials / st.arrive
-void launch_panel_chains(const DevProblem &pb, const DevState &st, int iter, int grid, cudaStream_t s) {
+void launch_panel_chains(const DevProblem &pb, const DevState &st, int iter, int grid, int variant, cudaStream_t s) {
   PanelWork w{};
   w.params = st.pp;
   w.acc = (unsigned long long *)st.partials;
@@ -394,16 +396,12 @@ void launch_panel_chains(const DevProblem &pb, const DevState &st, int iter, int
   w.rep0 = (uint32_t)iter;
   w.rep_stride = 0u;
   w.iter = iter;
-  const size_t smem = panel_smem_bytes(pb.panel_K, pb.P);
-  if (pb.panel_K == 8)
-    panel_sim_kernel<8><<<grid, kPanelThreads, smem, s>>>(pb, st, w);
-  else
-    panel_sim_kernel<0><<<grid, kPanelThreads, smem, s>>>(pb, st, w);
+  panel_kernel(pb.panel_K, variant)<<<grid, kPanelThreads, panel_smem_bytes(pb.panel_K, pb.P), s>>>(pb, st, w);
 }
 // batch mode: bare objective at params[B][P]
 void launch_panel_batch(const DevProblem &pb, const DevState &st, const double *params, int B, int noseed, uint32_t uid0,
                         uint32_t rep0, unsigned long long *acc, unsigned *done, unsigned *unit_ctr, double *value,
-                        double *moments, int *status, int grid, cudaStream_t s) {
+                        double *moments, int *status, int grid, int variant, cudaStream_t s) {
   PanelWork w{};
   w.params = params;
   w.acc = acc;
@@ -419,9 +417,5 @@ void launch_panel_batch(const DevProblem &pb, const DevState &st, const double *
   w.value = value;
   w.moments = moments;
   w.status = status;
-  const size_t smem = panel_smem_bytes(pb.panel_K, pb.P);
-  if (pb.panel_K == 8)
-    panel_sim_kernel<8><<<grid, kPanelThreads, smem, s>>>(pb, st, w);
-  else
-    panel_sim_kernel<0><<<grid, kPanelThreads, smem, s>>>(pb, st, w);
+  panel_kernel(pb.panel_K, variant)<<<grid, kPanelThreads, panel_smem_bytes(pb.panel_K, pb.P), s>>>(pb, st, w);
 }

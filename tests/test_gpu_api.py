@@ -101,3 +101,55 @@ def test_save_read_restart(tmp_path, oracle):
     assert_trace_parity(MB._trace, ref.trace)
     MA.close()
     MB.close()
+
+
+@pytest.mark.parametrize("mode,window", [(0, 0), (1, 0), (1, 7), (1, 50), (0, 13)])
+def test_streaming_run_equals_step_and_read(smm, mode, window):
+    """smm_bgp_run (windows computed while the previous window's rows travel to the host) = step + read_trace"""
+    import numpy as np
+    from smm_jl_b200 import configs
+    n = 150
+    cfg = configs.mvnormal(24, n, exchange_mode=mode)
+    with smm.BGPHandle(cfg) as h:
+        h.step(n)
+        want = h.read_trace(1, n)
+    buf = smm.PinnedTrace.acquire(n, 24, cfg.n_params, cfg.n_moments)
+    with smm.BGPHandle(cfg) as h:
+        h.run(40, into=buf, window=window)            # rows 0..39 = iterations 1..40
+        first = {f: np.array(getattr(buf, f)[:40]) for f in buf.FLOAT_FIELDS + buf.INT_FIELDS}
+        h.run(n - 40, into=buf, window=window)        # rows 0..109 = iterations 41..150
+        assert h.iteration == n
+        for f in buf.FLOAT_FIELDS + buf.INT_FIELDS:
+            w = getattr(want, f)
+            a, b = first[f], getattr(buf, f)[: n - 40]
+            if w.dtype.kind == "f":
+                assert np.array_equal(a.view(np.uint64), w[:40].view(np.uint64)), f
+                assert np.array_equal(b.view(np.uint64), w[40:].view(np.uint64)), f
+            else:
+                assert np.array_equal(a, w[:40]) and np.array_equal(b, w[40:]), f
+    buf.release()
+
+
+def test_run_serves_chains_from_the_streamed_trace(smm, oracle):
+    from smm_jl_b200 import api, configs
+    from oracle import oracle_lib  # noqa: F401
+    import numpy as np
+    m = api.MProb()
+    api.addSampledParam(m, "p1", 0.2, -3.0, 3.0)
+    api.addSampledParam(m, "p2", -0.2, -20.0, 20.0)
+    api.addMoment(m, "mu1", -1.0, 1.0)
+    api.addMoment(m, "mu2", 10.0, 1.0)
+    api.addEvalFunc(m, api.objfunc_norm)
+    opts = {"N": 3, "maxiter": 60, "maxtemp": 5.0, "sigma": 0.05, "acc_tuners": [20.0, 2.0, 1.0], "min_improve": [0.0] * 3,
+            "seed": 12, "exchange_mode": 1}
+    algo = api.MAlgoBGP(m, opts)
+    api.run(algo)
+    assert algo._streamed is not None and algo.i == 60
+    ref = oracle.run(configs.c1_serial_normal(60), 60)
+    for c in range(3):
+        ch = algo.chains[c]
+        assert np.array_equal(ch.accepted, ref.trace.accepted[:, c].astype(bool))
+        assert np.array_equal(ch.exchanged, ref.trace.exchanged[:, c])
+        np.testing.assert_allclose(ch.curr_val, ref.trace.curr_val[:, c], rtol=1e-9)
+    algo.close()
+    assert algo._streamed is None
