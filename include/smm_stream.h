@@ -138,7 +138,19 @@ static const smm_logent SMM_LOGTAB_HOST[1 << SMM_LOG_BITS] = SMM_LOG_TABLE;
 static const double SMM_SIN_HOST[SMM_SIN_DEG + 1] = SMM_SIN_COEFS;
 static const double SMM_COS_HOST[SMM_COS_DEG + 1] = SMM_COS_COEFS;
 static const double SMM_LOGQ_HOST[SMM_LOGQ_DEG + 1] = SMM_LOGQ_COEFS;
+/* ziggurat tables (see smm_zig_normal): 16-byte layer entries, so the fast path is one 128-bit load */
+typedef struct smm_zigent {
+  double w;    /* W[i]: outer edge of layer i (virtual width of the base strip for i = 0) */
+  uint32_t kh; /* 0x3FF00000 | floor(2^20 W[i+1]/W[i]): fast-accept bound on the high word of the uniform */
+  uint32_t pad;
+} smm_zigent;
+static const smm_zigent SMM_ZIGTAB_HOST[SMM_ZIG_LAYERS] = SMM_ZIG_TABLE;
+static const double SMM_ZIGF_HOST[SMM_ZIG_LAYERS + 1] = SMM_ZIG_F;
+static const double SMM_EXP_HOST[SMM_EXP_DEG + 1] = SMM_EXP_COEFS;
 #if defined(__CUDACC__)
+static __device__ const smm_zigent SMM_ZIGTAB_DEV[SMM_ZIG_LAYERS] = SMM_ZIG_TABLE;
+static __device__ const double SMM_ZIGF_DEV[SMM_ZIG_LAYERS + 1] = SMM_ZIG_F;
+static __constant__ double SMM_EXP_DEV[SMM_EXP_DEG + 1] = SMM_EXP_COEFS;
 static __device__ const smm_logent SMM_LOGTAB_DEV[1 << SMM_LOG_BITS] = SMM_LOG_TABLE;
 static __constant__ double SMM_SIN_DEV[SMM_SIN_DEG + 1] = SMM_SIN_COEFS;
 static __constant__ double SMM_COS_DEV[SMM_COS_DEG + 1] = SMM_COS_COEFS;
@@ -148,10 +160,14 @@ static __constant__ double SMM_LOGQ_DEV[SMM_LOGQ_DEG + 1] = SMM_LOGQ_COEFS;
 #define SMM_SIN_C(i) SMM_SIN_DEV[i]
 #define SMM_COS_C(i) SMM_COS_DEV[i]
 #define SMM_LOGQ_C(i) SMM_LOGQ_DEV[i]
+#define SMM_EXP_C(i) SMM_EXP_DEV[i]
+#define SMM_ZIGF(i) SMM_ZIGF_DEV[i]
 #else
 #define SMM_SIN_C(i) SMM_SIN_HOST[i]
 #define SMM_COS_C(i) SMM_COS_HOST[i]
 #define SMM_LOGQ_C(i) SMM_LOGQ_HOST[i]
+#define SMM_EXP_C(i) SMM_EXP_HOST[i]
+#define SMM_ZIGF(i) SMM_ZIGF_HOST[i]
 #endif
 
 SMM_HD const smm_logent *smm_logtab(void) {
@@ -159,6 +175,13 @@ SMM_HD const smm_logent *smm_logtab(void) {
   return SMM_LOGTAB_DEV;
 #else
   return SMM_LOGTAB_HOST;
+#endif
+}
+SMM_HD const smm_zigent *smm_zigtab(void) {
+#if defined(__CUDA_ARCH__)
+  return SMM_ZIGTAB_DEV;
+#else
+  return SMM_ZIGTAB_HOST;
 #endif
 }
 
@@ -221,6 +244,101 @@ SMM_HD void smm_normal_pair_tab(smm_u32x4 r, const smm_logent *tab, double *z0, 
 }
 SMM_HD void smm_normal_pair(smm_u32x4 r, double *z0, double *z1) {
   smm_normal_pair_tab(r, smm_logtab(), z0, z1);
+}
+
+/* ---- ziggurat normals: the simulator stream of the MvNormal objectives ------------------------
+ *
+ * Julia's randn -- what the reference's rand(MvNormal(..), ns) (ObjExamples.jl:78) bottoms out in -- is a
+ * 256-layer ziggurat; so is this, restated on counter-indexed bits so that it is a pure function:
+ *
+ *   one normal = Zig(a, b), (a, b) = 64 random bits (half a Philox block):
+ *     sign = bit 31 of a, layer i = bits 23..30 of a, u = 0.{a bits 0..19}{b} in [0,1)  (52 bits)
+ *     x = u W[i];  FAST PATH (98.5 % of draws): accept when the 20 high bits of u are below
+ *     floor(2^20 W[i+1]/W[i])  (x strictly inside the layer's core: 4 integer ops, one fp64 fma)
+ *     otherwise (smm_zig_slow):
+ *       i >= 1: wedge test  f(W[i]) + U (f(W[i+1]) - f(W[i])) < exp(-x^2/2); on rejection a NEW candidate
+ *       i == 0: x fell beyond R in the base strip -> Marsaglia's tail: repeat xt = -log(U1)/R, yt = -log(U2)
+ *               until 2 yt > xt^2, return R + xt
+ *     The extra uniforms and candidates come from auxiliary blocks Philox(a, b, n, TAG; ZIG key), n = 1, 2, ...
+ *     in the order the state machine consumes them -- a deterministic function of (a, b) alone.
+ *
+ * exp and log are the fma-only kernels of this header, so host and device agree to the bit. */
+#define SMM_ZIG_TAG 0x5A494721u
+#define SMM_ZIG_KEY0 0x736D6D5Au
+#define SMM_ZIG_KEY1 0x69676767u
+#define SMM_ZIG_MAX_AUX 4096u
+
+/* exp(t), t in [-700, 0]: t = n ln2 + r, |r| <= ln2/2 (+ rounding), Taylor degree 13, scaled by 2^n */
+SMM_HD double smm_exp_neg(double t) {
+  const double shift = 6755399441055744.0; /* 1.5 * 2^52: adding it rounds to the nearest integer */
+  const double nf = SMM_SUB(SMM_FMA(t, SMM_LOG2E, shift), shift);
+  double r = SMM_FMA(nf, -SMM_LN2_HI, t);
+  r = SMM_FMA(nf, -SMM_LN2_LO, r);
+  double p = SMM_EXP_C(SMM_EXP_DEG);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = SMM_EXP_DEG - 1; i >= 0; --i) p = SMM_FMA(p, r, SMM_EXP_C(i));
+  const int n = (int)nf;
+  return SMM_MUL(p, smm_bits_to_double((uint64_t)(n + 1023) << 52));
+}
+
+/* the fast path: candidate value and whether it is accepted outright */
+SMM_HD double smm_zig_fast(uint32_t a, uint32_t b, const smm_zigent *tab, int *ok) {
+  const smm_zigent t = tab[(a >> 23) & 0xFFu];
+  const uint32_t hi = (a & 0x000FFFFFu) | 0x3FF00000u;
+  const double d = smm_bits_to_double(((uint64_t)hi << 32) | (uint64_t)b); /* 1 + u */
+  const double x = SMM_FMA(d, t.w, -t.w);                                  /* u W[i], correctly rounded */
+  *ok = hi < t.kh;
+  return smm_bits_to_double(smm_double_to_bits(x) ^ ((uint64_t)(a & 0x80000000u) << 32));
+}
+
+/* u in [2^-52, 1 - 2^-52] from two words (odd 52-bit integer: never 0 or 1) */
+SMM_HD double smm_u01_open(uint32_t a, uint32_t b) {
+  return SMM_SUB(2.0, smm_bits_to_double(0x3FF0000000000000ull | smm_mant52(a, b) | 1ull));
+}
+
+/* everything after a failed fast test of candidate (a, b) */
+SMM_HD double smm_zig_slow(uint32_t a0, uint32_t b0, const smm_zigent *tab, const smm_logent *logtab) {
+  uint32_t a = a0, b = b0, n = 0;
+  for (;;) {
+    const uint32_t i = (a >> 23) & 0xFFu;
+    const uint64_t sign = (uint64_t)(a & 0x80000000u) << 32;
+    const smm_zigent t = tab[i];
+    const uint32_t hi = (a & 0x000FFFFFu) | 0x3FF00000u;
+    const double d = smm_bits_to_double(((uint64_t)hi << 32) | (uint64_t)b);
+    const double x = SMM_FMA(d, t.w, -t.w);
+    if (hi < t.kh) return smm_bits_to_double(smm_double_to_bits(x) ^ sign);
+    if (i == 0u) { /* tail beyond R */
+      for (;;) {
+        ++n;
+        const smm_u32x4 r = smm_philox4x32_10(a0, b0, n, SMM_ZIG_TAG, SMM_ZIG_KEY0, SMM_ZIG_KEY1);
+        const double xt = SMM_MUL(smm_neglog01(smm_u01_open(r.x, r.y), logtab), SMM_ZIG_RINV);
+        const double yt = smm_neglog01(smm_u01_open(r.z, r.w), logtab);
+        if (SMM_ADD(yt, yt) > SMM_MUL(xt, xt) || n >= SMM_ZIG_MAX_AUX)
+          return smm_bits_to_double(smm_double_to_bits(SMM_ADD(SMM_ZIG_R, xt)) ^ sign);
+      }
+    }
+    ++n;
+    const smm_u32x4 r = smm_philox4x32_10(a0, b0, n, SMM_ZIG_TAG, SMM_ZIG_KEY0, SMM_ZIG_KEY1);
+    const double f_lo = SMM_ZIGF(i), f_hi = SMM_ZIGF(i + 1u);
+    const double y = SMM_FMA(smm_u01(r.z, r.w), SMM_SUB(f_hi, f_lo), f_lo);
+    if (y < smm_exp_neg(SMM_MUL(SMM_MUL(x, x), -0.5)) || n >= SMM_ZIG_MAX_AUX)
+      return smm_bits_to_double(smm_double_to_bits(x) ^ sign);
+    a = r.x; /* rejected: start over with a fresh candidate */
+    b = r.y;
+  }
+}
+
+SMM_HD double smm_zig_normal_tab(uint32_t a, uint32_t b, const smm_zigent *tab, const smm_logent *logtab) {
+  int ok;
+  const double z = smm_zig_fast(a, b, tab, &ok);
+  return ok ? z : smm_zig_slow(a, b, tab, logtab);
+}
+/* the two normals of one Philox block: (x, y) -> z0, (z, w) -> z1 */
+SMM_HD void smm_zig_pair(smm_u32x4 r, double *z0, double *z1) {
+  *z0 = smm_zig_normal_tab(r.x, r.y, smm_zigtab(), smm_logtab());
+  *z1 = smm_zig_normal_tab(r.z, r.w, smm_zigtab(), smm_logtab());
 }
 
 /* ---- the four streams ----------------------------------------------------------------------- */

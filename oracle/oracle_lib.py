@@ -50,6 +50,12 @@ def lib():
     L.smm_oracle_normals.restype = None
     L.smm_oracle_normal_from_words.argtypes = [C.c_uint32] * 4 + [dp]
     L.smm_oracle_normal_from_words.restype = None
+    L.smm_oracle_zig_normals.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, dp]
+    L.smm_oracle_zig_normals.restype = None
+    L.smm_oracle_zig_from_words.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
+    L.smm_oracle_zig_from_words.restype = C.c_double
+    L.smm_oracle_exp_neg.argtypes = [C.c_double]
+    L.smm_oracle_exp_neg.restype = C.c_double
     L.smm_oracle_neglog01.argtypes = [C.c_double]
     L.smm_oracle_neglog01.restype = C.c_double
     L.smm_oracle_acc_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
@@ -122,6 +128,24 @@ def normal_from_words(x, y, z, w):
     out = np.zeros(2)
     lib().smm_oracle_normal_from_words(x, y, z, w, out.ctypes.data_as(C.POINTER(C.c_double)))
     return out
+
+
+def zig_normals(seed: int, k: int, c2: int, c3: int, n_pairs: int) -> np.ndarray:
+    """ziggurat normals of Philox blocks (j, k, c2, c3), j < n_pairs (the MvNormal simulator stream)"""
+    out = np.zeros(2 * n_pairs)
+    lib().smm_oracle_zig_normals(seed, k, c2, c3, n_pairs, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
+def zig_from_words(a: int, b: int):
+    """one ziggurat normal from its 64 bits -> (z, slow_path_taken)"""
+    slow = C.c_int(0)
+    z = lib().smm_oracle_zig_from_words(a, b, C.byref(slow))
+    return z, bool(slow.value)
+
+
+def exp_neg(t: float) -> float:
+    return lib().smm_oracle_exp_neg(t)
 
 
 def neglog01(u: float) -> float:

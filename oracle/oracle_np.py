@@ -2,8 +2,8 @@
 
 Purpose: pin oracle/smm_oracle.cpp (and the shared stream header it includes) against a second
 implementation that shares no code with it: Philox4x32-10 written in numpy integer arithmetic, the
-Box-Muller transform evaluated with libm (np.log / np.cos / np.sin, so it also checks the accuracy of the
-header's polynomial kernels), and the BGP algorithm written as plain Python loops following the same
+ziggurat re-derived with mpmath tables and libm exp/log, the Box-Muller transform evaluated with libm
+(np.log / np.cos / np.sin, so both also check the accuracy of the header's polynomial kernels), and the BGP algorithm written as plain Python loops following the same
 reference lines (AlgoBGP.jl:209-257, 272-471, 589-749; ObjExamples.jl:59-116; mprob.jl:246-272).
 Small cases only.
 """
@@ -51,13 +51,106 @@ def normal_pairs(x, y, z, w):
     return rad * c, rad * s
 
 
-def sim_normals(seed_sim, k, S, noseed=0, uid=0, rep=0):
+_ZIG = None
+
+
+def zig_tables():
+    """The 256-layer Marsaglia-Tsang ziggurat re-derived here with mpmath from its defining equations (equal-area
+    layers under exp(-x^2/2), closing condition solved for R by bisection) -- not read from the C header."""
+    global _ZIG
+    if _ZIG is None:
+        import mpmath as mp
+        with mp.workprec(160):
+            f = lambda x: mp.exp(-x * x / 2)
+
+            def build(R):
+                V = R * f(R) + mp.sqrt(mp.pi / 2) * mp.erfc(R / mp.sqrt(2))
+                xs = [V / f(R), R]
+                for i in range(1, 255):
+                    y = V / xs[i] + f(xs[i])
+                    if y >= 1:
+                        return None, xs
+                    xs.append(mp.sqrt(-2 * mp.log(y)))
+                return xs[255] * (1 - f(xs[255])) - V, xs
+
+            lo, hi = mp.mpf("3.5"), mp.mpf("3.8")
+            for _ in range(300):
+                mid = (lo + hi) / 2
+                res, xs = build(mid)
+                if res is None or res < 0:
+                    lo = mid
+                else:
+                    hi = mid
+            R = (lo + hi) / 2
+            _, xs = build(R)
+            xs.append(mp.mpf(0))
+            W = np.array([float(x) for x in xs])
+            KH = np.array([int(mp.floor(mp.mpf(2) ** 20 * xs[i + 1] / xs[i])) for i in range(256)], dtype=np.uint64)
+            F = np.array([float(f(x)) for x in xs])
+        _ZIG = (W, KH, F, float(R))
+    return _ZIG
+
+
+ZIG_TAG, ZIG_KEY0, ZIG_KEY1 = 0x5A494721, 0x736D6D5A, 0x69676767
+
+
+def _u52(a, b):
+    return ((int(a) << 20) | (int(b) >> 12))
+
+
+def zig_slow(a0, b0):
+    """the ziggurat's rare branch for one candidate (wedge test / tail / retry), with libm exp and log"""
+    W, KH, F, R = zig_tables()
+    a, b, n = int(a0), int(b0), 0
+    while True:
+        i = (a >> 23) & 0xFF
+        sgn = -1.0 if (a >> 31) else 1.0
+        hi20 = a & 0xFFFFF
+        u = ((hi20 << 32) | b) / 2.0 ** 52
+        x = u * W[i]
+        if hi20 < int(KH[i]):
+            return sgn * x
+        if i == 0:
+            while True:
+                n += 1
+                r = [int(v) for v in philox(a0, b0, n, ZIG_TAG, ZIG_KEY0, ZIG_KEY1)]
+                u1 = (2 ** 52 - (_u52(r[0], r[1]) | 1)) / 2.0 ** 52
+                u2 = (2 ** 52 - (_u52(r[2], r[3]) | 1)) / 2.0 ** 52
+                xt, yt = -math.log(u1) / R, -math.log(u2)
+                if yt + yt > xt * xt:
+                    return sgn * (R + xt)
+        n += 1
+        r = [int(v) for v in philox(a0, b0, n, ZIG_TAG, ZIG_KEY0, ZIG_KEY1)]
+        uw = _u52(r[2], r[3]) / 2.0 ** 52
+        if F[i] + uw * (F[i + 1] - F[i]) < math.exp(-0.5 * x * x):
+            return sgn * x
+        a, b = r[0], r[1]
+
+
+def zig_normals(a, b):
+    """ziggurat normals from arrays of 32-bit word pairs: numpy fast path, Python loop for the ~1.5 % rest"""
+    W, KH, _, _ = zig_tables()
+    a, b = np.asarray(a, dtype=np.uint64), np.asarray(b, dtype=np.uint64)
+    i = ((a >> np.uint64(23)) & np.uint64(0xFF)).astype(np.int64)
+    hi20 = a & np.uint64(0xFFFFF)
+    u = ((hi20 << np.uint64(32)) | b).astype(np.float64) / np.float64(2 ** 52)
+    z = np.where((a >> np.uint64(31)).astype(bool), -1.0, 1.0) * (u * W[i])
+    slow = np.nonzero(hi20 >= KH[i])[0]
+    for t in slow:
+        z[t] = zig_slow(a[t], b[t])
+    return z
+
+
+def sim_normals(seed_sim, k, S, noseed=0, uid=0, rep=0, transform="zig"):
     nb = (S + 1) // 2
     j = np.arange(nb, dtype=np.uint64)
     c2 = uid if noseed else 0
     c3 = (STREAM_SIM << 28) | ((rep & 0x0FFFFFFF) if noseed else 0)
     r = philox(j, k, c2, c3, seed_sim & MASK, seed_sim >> 32)
-    z0, z1 = normal_pairs(*r)
+    if transform == "zig":      # MvNormal objectives
+        z0, z1 = zig_normals(r[0], r[1]), zig_normals(r[2], r[3])
+    else:                       # dynamic panel
+        z0, z1 = normal_pairs(*r)
     return np.stack([z0, z1], axis=1).reshape(-1)[:S]
 
 
@@ -111,7 +204,7 @@ def panel_objective(cfg, p, uid=0, rep=0, noseed=None):
     rho, beta, phi = p[0], p[1:1 + K], p[1 + K:1 + 2 * K]
     sig_a, sig_e, mu0 = p[1 + 2 * K], p[2 + 2 * K], p[3 + 2 * K]
     nz = 1 + K + T * (K + 1)
-    Z = np.stack([sim_normals(cfg.seed_sim, i, nz, noseed, uid, rep) for i in range(NI)])   # [NI][nz]
+    Z = np.stack([sim_normals(cfg.seed_sim, i, nz, noseed, uid, rep, transform="bm") for i in range(NI)])   # [NI][nz]
     alpha = mu0 + sig_a * Z[:, 0]
     y = np.zeros((NI, T + 1))
     x = np.zeros((K, NI, T + 1))

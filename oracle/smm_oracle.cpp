@@ -67,11 +67,18 @@ struct MProb {
 };
 
 // ---- the simulator streams -----------------------------------------------------------------------
-// Z[k, s] for s in [0, S): normal #(s&1) of block (j = s>>1, row k).
+// Z[k, s] for s in [0, S): normal #(s&1) of block (j = s>>1, row k).  The transform is part of the simulator:
+// ziggurat (smm_zig_pair, the algorithm behind Julia's randn) for the MvNormal objectives, Box-Muller
+// (smm_normal_pair) for the dynamic panel.
 void fill_normals_row(const MProb &m, uint32_t k, int S, uint32_t uid, uint32_t rep, double *out) {
+  const bool zig = m.objective != SMM_OBJ_PANEL;
   for (int j = 0; 2 * j < S; ++j) {
     double z0, z1;
-    smm_normal_pair(smm_sim_block(m.seed_sim, (uint32_t)j, k, m.noseed, uid, rep), &z0, &z1);
+    const smm_u32x4 r = smm_sim_block(m.seed_sim, (uint32_t)j, k, m.noseed, uid, rep);
+    if (zig)
+      smm_zig_pair(r, &z0, &z1);
+    else
+      smm_normal_pair(r, &z0, &z1);
     out[2 * j] = z0;
     if (2 * j + 1 < S) out[2 * j + 1] = z1;
   }
@@ -682,6 +689,19 @@ void smm_oracle_normal_from_words(uint32_t x, uint32_t y, uint32_t z, uint32_t w
   smm_u32x4 r = {x, y, z, w};
   smm_normal_pair(r, &out[0], &out[1]);
 }
+void smm_oracle_zig_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, double *out) {
+  for (int j = 0; j < n_pairs; ++j)
+    smm_zig_pair(smm_philox4x32_10((uint32_t)j, k, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32)), &out[2 * j],
+                 &out[2 * j + 1]);
+}
+// one ziggurat normal from its 64 bits; *slow = 1 when the fast path rejected the candidate
+double smm_oracle_zig_from_words(uint32_t a, uint32_t b, int *slow) {
+  int ok;
+  const double z = smm_zig_fast(a, b, smm_zigtab(), &ok);
+  if (slow) *slow = !ok;
+  return ok ? z : smm_zig_slow(a, b, smm_zigtab(), smm_logtab());
+}
+double smm_oracle_exp_neg(double t) { return smm_exp_neg(t); }
 double smm_oracle_neglog01(double u) { return smm_neglog01(u, smm_logtab()); }
 double smm_oracle_acc_uniform(uint64_t seed, uint32_t chain, uint32_t iter) { return smm_acc_uniform(seed, chain, iter); }
 void smm_oracle_pair_unrank(uint32_t q, uint32_t *i, uint32_t *j) { smm_pair_unrank(q, i, j); }

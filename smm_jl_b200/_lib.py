@@ -19,7 +19,7 @@ EXPORTS = [
     "smm_abi_version", "smm_last_error", "smm_device_count", "smm_nccl_unique_id", "smm_bgp_create",
     "smm_bgp_destroy", "smm_bgp_step", "smm_bgp_iteration", "smm_bgp_local_chains", "smm_bgp_stream",
     "smm_bgp_read_trace", "smm_bgp_read_chain_state", "smm_bgp_get_counters", "smm_bgp_eval_batch",
-    "smm_bgp_state_bytes", "smm_bgp_export_state", "smm_bgp_import_state", "smm_debug_normals",
+    "smm_bgp_state_bytes", "smm_bgp_export_state", "smm_bgp_import_state", "smm_debug_normals", "smm_debug_zig_normals",
     "smm_debug_pairs", "smm_debug_rng_throughput", "smm_stream_acc_uniforms", "smm_bgp_set_profiling",
     "smm_bgp_kernel_times", "smm_debug_phase_ts", "smm_debug_sim_throughput", "smm_debug_barrier_bench",
     "smm_bgp_run", "smm_host_alloc", "smm_host_free",
@@ -71,6 +71,7 @@ def lib():
     L.smm_bgp_export_state.argtypes = [vp, vp, C.c_int64]
     L.smm_bgp_import_state.argtypes = [vp, vp, C.c_int64]
     L.smm_debug_normals.argtypes = [C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, dp]
+    L.smm_debug_zig_normals.argtypes = [C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, dp]
     L.smm_debug_pairs.argtypes = [vp, C.c_int32, ip, ip, ip]
     L.smm_debug_rng_throughput.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float), dp]
     L.smm_stream_acc_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, dp]
@@ -294,6 +295,13 @@ def acc_uniforms(seed_algo: int, chain: int, iter_lo: int, iter_hi: int) -> np.n
 def debug_normals(seed: int, k: int, c2: int, c3: int, n_pairs: int, device: int = 0) -> np.ndarray:
     out = np.zeros(2 * n_pairs)
     check(lib().smm_debug_normals(device, seed, k, c2, c3, n_pairs, out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def debug_zig_normals(seed: int, k: int, c2: int, c3: int, n_pairs: int, device: int = 0) -> np.ndarray:
+    """device evaluation of smm_zig_pair on Philox blocks (j, k, c2, c3), j < n_pairs"""
+    out = np.zeros(2 * n_pairs)
+    check(lib().smm_debug_zig_normals(device, seed, k, c2, c3, n_pairs, out.ctypes.data_as(C.POINTER(C.c_double))))
     return out
 
 

@@ -39,7 +39,7 @@ void launch_panel_chains(const DevProblem &pb, const DevState &st, int iter, int
 void launch_panel_batch(const DevProblem &pb, const DevState &st, const double *params, int B, int noseed, uint32_t uid0,
                         uint32_t rep0, unsigned long long *acc, unsigned *done, unsigned *unit_ctr, double *value,
                         double *moments, int *status, int grid, int variant, cudaStream_t s);
-void launch_debug_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, double *out,
+void launch_debug_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, int zig, double *out,
                           cudaStream_t s);
 void launch_rng_throughput(long long n_per_thread, int blocks, double *out, cudaStream_t s);
 cudaError_t launch_barrier_bench(const DevProblem &pb, const DevState &st, int variant, int n, int grid, cudaStream_t s);
@@ -484,14 +484,15 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   pb.sigma_adjust_by = cfg->sigma_adjust_by; pb.slow_seconds = cfg->slow_seconds;
   pb.seed_sim = cfg->seed_sim; pb.seed_algo = cfg->seed_algo;
   {
-    // fixed-point grids of the order-invariant accumulators (smm_kernels.cu): |x| <= xmax = box + 9 sigma-units,
+    // fixed-point grids of the order-invariant accumulators (smm_kernels.cu): |x| <= xmax = box + 14 sigma-units
+    // (a ziggurat draw is at most R + 52 ln2 / R < 13.6 in magnitude),
     // totals S*xmax and S*xmax^2 must stay below 2^62, single terms below 2^(51-F) (4x headroom for eval_batch)
     double box = 0.0;
     for (int k = 0; k < P; ++k) {
       box = std::fmax(box, std::fabs(cfg->lb[k]));
       box = std::fmax(box, std::fabs(cfg->ub[k]));
     }
-    const double xmax = 4.0 * (box + 9.0);
+    const double xmax = 4.0 * (box + 14.0);
     auto pick = [&](double term_max) {
       int f_total = 62 - (int)std::ceil(std::log2((double)cfg->n_sim * term_max));
       int f_term = 51 - (int)std::ceil(std::log2(term_max));
@@ -503,7 +504,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     pb.magic_sq = std::ldexp(1.5, 52 - f_sq);
     pb.scale_sum = std::ldexp(1.0, -f_sum);
     pb.scale_sq = std::ldexp(1.0, -f_sq);
-    h->eval_param_limit = xmax - 9.0;
+    h->eval_param_limit = xmax - 14.0;
   }
   if (h->panel) {
     // Two-word fixed point of the per-individual sums (smm_panel.cuh).  Hard bounds from the sampling box with
@@ -1067,18 +1068,26 @@ int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes) {
 }
 
 // ---- diagnostics ---------------------------------------------------------------------------------
-int smm_debug_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_pairs,
-                      double *out) {
+static int debug_normals_impl(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_pairs,
+                              int zig, double *out) {
   if (!out || n_pairs < 1) return fail(SMM_E_ARG, "bad argument");
   if (smm_device_count() <= device) return fail(SMM_E_CUDA, "no such CUDA device");
   CUDA_TRY(cudaSetDevice(device));
   DevBuf<double> d;
   CUDA_TRY(d.alloc((size_t)2 * n_pairs, true));
-  launch_debug_normals(seed, k, c2, c3, n_pairs, d.p, 0);
+  launch_debug_normals(seed, k, c2, c3, n_pairs, zig, d.p, 0);
   cudaError_t e = cudaMemcpy(out, d.p, sizeof(double) * 2 * n_pairs, cudaMemcpyDeviceToHost);
   d.free();
   CUDA_TRY(e);
   return 0;
+}
+int smm_debug_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_pairs,
+                      double *out) {
+  return debug_normals_impl(device, seed, k, c2, c3, n_pairs, 0, out);
+}
+int smm_debug_zig_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_pairs,
+                          double *out) {
+  return debug_normals_impl(device, seed, k, c2, c3, n_pairs, 1, out);
 }
 
 int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij, int32_t *level_offsets, int32_t *n_levels) {

@@ -238,51 +238,217 @@ struct Acc {
   unsigned long long sum, sq;  // sums of raw bit patterns; the n * bits(M) offset is removed at the end
 };
 
-__device__ __forceinline__ void add_pair(const DevProblem &pb, const smm_logent *logtab, Acc &a, double p, uint32_t j,
-                                         uint32_t k, uint32_t c2, uint32_t c3, bool both) {
-  double z0, z1;
-  smm_normal_pair_tab(philox_sim(pb, j, k, c2, c3), logtab, &z0, &z1);
-  const double x0 = __dadd_rn(p, z0);
-  a.sum += (unsigned long long)__double_as_longlong(__dadd_rn(x0, pb.magic_sum));
-  a.sq += (unsigned long long)__double_as_longlong(__fma_rn(x0, x0, pb.magic_sq));
-  if (both) {
-    const double x1 = __dadd_rn(p, z1);
-    a.sum += (unsigned long long)__double_as_longlong(__dadd_rn(x1, pb.magic_sum));
-    a.sq += (unsigned long long)__double_as_longlong(__fma_rn(x1, x1, pb.magic_sq));
+// ------------------------------------------------------------------------------------------------
+// Zsim of the MvNormal objectives is a ziggurat (include/smm_stream.h): 98.5 % of the draws take the FAST path
+// (one 16-byte table entry from shared memory, 4 integer ops, one DFMA).  The rest -- wedge test with exp, tail
+// with two logs, retries -- would cost every warp a divergent detour on more than half of its steps, so it is
+// DEFERRED: the fast path always accumulates its candidate; a lane whose candidate was not accepted pushes the
+// 64 random bits and the row onto its warp's queue (ballot + popc), and when 32 entries have gathered the whole
+// warp runs smm_zig_slow on them, one entry per lane, and adds [pattern(true x) - pattern(candidate x)] to the
+// accumulators with 64-bit integer atomics.  Integer accumulation is exact and order-free, so the totals are
+// bit-identical to the sequential definition (oracle: smm_zig_pair draw by draw).
+// ------------------------------------------------------------------------------------------------
+constexpr int kZigQCap = 96;                  // entries per warp: < 32 before a step, <= 95 after its two pushes
+constexpr int kZigQWords = 3 * kZigQCap;      // a[], b[], row[]
+constexpr int kZigSigned = 2 * SMM_ZIG_LAYERS;  // shared-memory table: one entry per (sign, layer)
+
+// Everything the hot loop needs lives in 32-bit registers (shared-window addresses, not generic pointers).
+struct ZigCtx {
+  uint32_t ztab;  // shared address of the signed layer table: entry (a >> 23) = {+-W[i], kh[i]}, on an 8 KB boundary
+  uint32_t c3ff;  // 0x3FF00000 held in a register (so that (a & 0xFFFFF) | 0x3FF00000 is ONE LOP3)
+  uint32_t q;     // shared address of this warp's queue
+  uint32_t lt;    // %lanemask_lt
+  uint32_t pvec;  // shared address: [D] parameters of the evaluation being simulated (f64)
+  uint32_t fix;   // shared address: [2D] u64 where corrections are added
+  int D;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// The signed copy of the layer table (index = sign << 8 | layer; -W for negative draws, so the sign costs nothing)
+// must start on an 8 KB boundary of the shared window, because zig_fast_dev forms entry addresses with OR.  A
+// declared __align__(8192) is not enough: static shared memory starts 1 KB into the window on sm_100, and the
+// compiler aligns relative to that.  So the kernels reserve 16 KB and use the aligned half.
+constexpr int kZigBufEntries = 2 * kZigSigned;
+__device__ __forceinline__ uint32_t zig_table_addr(const uint4 *buf) { return (smem_addr(buf) + 8191u) & ~8191u; }
+__device__ __forceinline__ void load_zigtab(uint4 *buf) {
+  uint4 *dst = buf + (zig_table_addr(buf) - smem_addr(buf)) / 16u;
+  const uint4 *src = reinterpret_cast<const uint4 *>(smm_zigtab());
+  for (int i = threadIdx.x; i < kZigSigned; i += blockDim.x) {
+    uint4 e = src[i & (SMM_ZIG_LAYERS - 1)];
+    if (i >= SMM_ZIG_LAYERS) e.y ^= 0x80000000u;
+    dst[i] = e;
+  }
+}
+// `opaque` is any kernel argument known to be non-negative: OR-ing its sign bit into the constants keeps ptxas from
+// folding them back into immediates (a LOP3 takes one immediate; with both operands in registers the mask-and-merge
+// of the fast path is a single instruction)
+__device__ __forceinline__ ZigCtx zig_ctx(const uint4 *zbuf, uint32_t *q_warp, int opaque) {
+  ZigCtx cx;
+  const uint32_t zero = (uint32_t)opaque >> 31;
+  cx.ztab = zig_table_addr(zbuf) | zero;
+  cx.c3ff = 0x3FF00000u | zero;
+  cx.q = smem_addr(q_warp);
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(cx.lt));
+  cx.pvec = 0;
+  cx.fix = 0;
+  cx.D = 0;
+  return cx;
+}
+
+// candidate of the fast path (same value as smm_zig_fast) and whether it is final:
+// SHF, LOP3, LDS.128, LOP3, DFMA, ISETP
+__device__ __forceinline__ double zig_fast_dev(uint32_t a, uint32_t b, const ZigCtx &cx, bool &ok) {
+  uint32_t addr, hi, e0, e1, e2, e3;  // e3: padding word of the entry
+  asm("lop3.b32 %0, %1, 0x1FF0, %2, 0xEA;" : "=r"(addr) : "r"(a >> 19), "r"(cx.ztab));
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3) : "r"(addr));
+  asm("lop3.b32 %0, %1, 0xFFFFF, %2, 0xEA;" : "=r"(hi) : "r"(a), "r"(cx.c3ff));
+  const double w = __hiloint2double((int)e1, (int)e0);
+  ok = hi < e2;
+  return __fma_rn(__hiloint2double((int)hi, (int)b), w, -w);
+}
+
+// the warp resolves `cnt` (<= 32) queued draws starting at entry `first`
+__device__ __noinline__ void zig_drain(const ZigCtx cx, double magic_sum, double magic_sq, int first, int cnt) {
+  const int lane = threadIdx.x & 31;
+  if (lane < cnt) {
+    uint32_t a, b, kk;
+    const uint32_t qa = cx.q + 4u * (uint32_t)(first + lane);
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(qa) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(b) : "r"(qa), "n"(4 * kZigQCap) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(kk) : "r"(qa), "n"(8 * kZigQCap) : "memory");
+    bool ok;
+    const double zf = zig_fast_dev(a, b, cx, ok);
+    const double zs = smm_zig_slow(a, b, smm_zigtab(), smm_logtab());  // global tables: this path is rare
+    double p;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(p) : "r"(cx.pvec + 8u * kk) : "memory");
+    const double xf = __dadd_rn(p, zf), xs = __dadd_rn(p, zs);
+    const unsigned long long dsum = (unsigned long long)__double_as_longlong(__dadd_rn(xs, magic_sum)) -
+                                    (unsigned long long)__double_as_longlong(__dadd_rn(xf, magic_sum));
+    const unsigned long long dsq = (unsigned long long)__double_as_longlong(__fma_rn(xs, xs, magic_sq)) -
+                                   (unsigned long long)__double_as_longlong(__fma_rn(xf, xf, magic_sq));
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(cx.fix + 8u * kk), "l"(dsum) : "memory");
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(cx.fix + 8u * ((uint32_t)cx.D + kk)), "l"(dsq) : "memory");
+  }
+  __syncwarp();
+}
+
+// all 32 lanes call this together (qn is warp-uniform)
+__device__ __forceinline__ void zig_push(const ZigCtx &cx, int &qn, bool slow, uint32_t a, uint32_t b, uint32_t k) {
+  const unsigned m = __ballot_sync(0xffffffffu, slow);
+  if (m) {
+    if (slow) {
+      const uint32_t qa = cx.q + 4u * (uint32_t)(qn + __popc(m & cx.lt));
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(a) : "memory");
+      asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(qa), "r"(b), "n"(4 * kZigQCap) : "memory");
+      asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(qa), "r"(k), "n"(8 * kZigQCap) : "memory");
+    }
+    qn += __popc(m);
+  }
+}
+// between steps: bring the queue back below 32 entries (full warps of work only)
+__device__ __forceinline__ void zig_relieve(const ZigCtx &cx, int &qn, double magic_sum, double magic_sq) {
+  while (qn >= 32) {
+    __syncwarp();
+    zig_drain(cx, magic_sum, magic_sq, qn - 32, 32);
+    qn -= 32;
+  }
+}
+__device__ __forceinline__ void zig_flush(const ZigCtx &cx, int &qn, double magic_sum, double magic_sq) {
+  zig_relieve(cx, qn, magic_sum, magic_sq);
+  if (qn > 0) {
+    __syncwarp();
+    zig_drain(cx, magic_sum, magic_sq, 0, qn);
+    qn = 0;
+  }
+}
+
+// One Philox block of row k: X = p + Z for its two draws, added to the accumulators.  Called by all 32 lanes of
+// a warp; act0/act1 say whether this lane's two draws count (kMasked = false: both always do).  Needs qn < 32 on
+// entry; the caller runs zig_relieve between steps (kept out of here so that hot loops contain no call).
+template <bool kMasked>
+__device__ __forceinline__ void add_pair(const DevProblem &pb, const ZigCtx &cx, int &qn, Acc &a, double p, uint32_t j,
+                                         uint32_t k, uint32_t c2, uint32_t c3, bool act0, bool act1) {
+  const smm_u32x4 r = philox_sim(pb, j, k, c2, c3);
+  bool ok0, ok1;
+  const double x0 = __dadd_rn(p, zig_fast_dev(r.x, r.y, cx, ok0));
+  const double x1 = __dadd_rn(p, zig_fast_dev(r.z, r.w, cx, ok1));
+  const unsigned long long s0 = (unsigned long long)__double_as_longlong(__dadd_rn(x0, pb.magic_sum));
+  const unsigned long long q0 = (unsigned long long)__double_as_longlong(__fma_rn(x0, x0, pb.magic_sq));
+  const unsigned long long s1 = (unsigned long long)__double_as_longlong(__dadd_rn(x1, pb.magic_sum));
+  const unsigned long long q1 = (unsigned long long)__double_as_longlong(__fma_rn(x1, x1, pb.magic_sq));
+  bool slow0 = !ok0, slow1 = !ok1;
+  if (kMasked) {
+    if (act0) {
+      a.sum += s0;
+      a.sq += q0;
+    }
+    if (act1) {
+      a.sum += s1;
+      a.sq += q1;
+    }
+    slow0 = slow0 && act0;
+    slow1 = slow1 && act1;
+  } else {
+    a.sum += s0 + s1;
+    a.sq += q0 + q1;
+  }
+  if (__any_sync(0xffffffffu, slow0 || slow1)) {
+    zig_push(cx, qn, slow0, r.x, r.y, k);
+    zig_push(cx, qn, slow1, r.z, r.w, k);
   }
 }
 
 // Static mapping, any D <= g.n: thread t owns row k = t % D and blocks j0 + t/D, +lanes, ...
-// red: shared [2 * g.n] u64.  Writes the group's partial sums [2][D] (u64 patterns) to `part`.
-__device__ void simulate_static(const DevProblem &pb, const Grp &g, const smm_logent *logtab, const double *pp, int j0,
-                                int j1, uint32_t uid, uint32_t rep, unsigned long long *red, double *part) {
+// zt: the 16 KB buffer holding the signed layer table (shared); red: shared [2 * g.n] u64; zfix: shared [2 * D] u64 (zeroed
+// here); zq: shared [g.n / 32][kZigQWords]; pp: shared.
+// Writes the group's partial sums [2][D] (u64 patterns) to `part`.
+__device__ void simulate_static(const DevProblem &pb, const Grp &g, const uint4 *zt, const double *pp, int j0, int j1,
+                                uint32_t uid, uint32_t rep, unsigned long long *red, unsigned long long *zfix,
+                                uint32_t *zq, double *part) {
   const int D = pb.P, S = pb.S, tid = g.tid;
   const int lanes = g.n / D;
   const int n_full = S >> 1;  // blocks whose two normals are both used
   const uint32_t c2 = pb.noseed ? uid : 0u;
   const uint32_t c3 = (SMM_STREAM_SIM << 28) | (pb.noseed ? (rep & SMM_ITER_MASK) : 0u);
+  for (int e = tid; e < 2 * D; e += g.n) zfix[e] = 0ull;
+  gsync(g);
   Acc a{0ull, 0ull};
-  if (tid < lanes * D) {
-    const int k = tid % D, ln = tid / D;
-    const double p = pp[k];
-    const int jend = j1 < n_full ? j1 : n_full;
-    for (int j = j0 + ln; j < jend; j += lanes) add_pair(pb, logtab, a, p, (uint32_t)j, (uint32_t)k, c2, c3, true);
-    if ((S & 1) && ln == 0 && j0 <= n_full && n_full < j1)  // odd S: the last block contributes one draw
-      add_pair(pb, logtab, a, p, (uint32_t)n_full, (uint32_t)k, c2, c3, false);
+  ZigCtx cx = zig_ctx(zt, zq + (size_t)(tid >> 5) * kZigQWords, S);
+  cx.pvec = smem_addr(pp);
+  cx.fix = smem_addr(zfix);
+  cx.D = D;
+  int qn = 0;
+  const bool on = tid < lanes * D;
+  const int k = tid % D, ln = tid / D;
+  const double p = pp[k];
+  const int jend = j1 < n_full ? j1 : n_full;
+  // every warp runs the same number of steps (the ballots inside add_pair need all 32 lanes)
+  const int n_steps = jend > j0 ? (jend - j0 + lanes - 1) / lanes : 0;
+  for (int t = 0; t < n_steps; ++t) {
+    const int j = j0 + ln + t * lanes;
+    const bool act = on && j < jend;
+    add_pair<true>(pb, cx, qn, a, p, (uint32_t)j, (uint32_t)k, c2, c3, act, act);
+    if (qn >= 32) zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
   }
+  if ((S & 1) && j0 <= n_full && n_full < j1)  // odd S: the last block contributes one draw
+    add_pair<true>(pb, cx, qn, a, p, (uint32_t)n_full, (uint32_t)k, c2, c3, on && ln == 0, false);
+  zig_flush(cx, qn, pb.magic_sum, pb.magic_sq);
   red[2 * tid] = a.sum;
   red[2 * tid + 1] = a.sq;
   gsync(g);
   if (tid < 2 * D) {
-    const int k = tid % D, which = tid / D;
-    unsigned long long acc = 0ull;
-    for (int ln = 0; ln < lanes; ++ln) acc += red[2 * (ln * D + k) + which];
-    ((unsigned long long *)part)[which * D + k] = acc;
+    const int kk = tid % D, which = tid / D;
+    unsigned long long acc = zfix[which * D + kk];
+    for (int l = 0; l < lanes; ++l) acc += red[2 * (l * D + kk) + which];
+    ((unsigned long long *)part)[which * D + kk] = acc;
   }
   gsync(g);
 }
 
-constexpr int kUnitSteps = 4;  // warp steps per work unit of the persistent kernel (sim_throughput_kernel too)
+constexpr int kUnitSteps = 1;   // warp steps per work unit of the persistent kernel
+constexpr int kMaxGrab = 16;    // units a warp takes from its CTA's queue at once (guided: fewer towards the end)
+constexpr int kTputSteps = 8;   // sim_throughput_kernel: steps per queue access
 
 __device__ void group_distance(const DevProblem &pb, const Grp &g, const FinScratch &fs);
 
@@ -553,6 +719,8 @@ struct EvalSmem {
   double tot[2 * SMM_MAX_PARAMS];
   double mom[SMM_MAX_MOMENTS];
   smm_logent logtab[1 << SMM_LOG_BITS];
+  unsigned long long zfix[2 * SMM_MAX_PARAMS];
+  uint32_t zq[(kEvalThreads / 32) * kZigQWords];
   unsigned char okf[2 * kEvalThreads];
   int first[SMM_MAX_PARAMS];
   int resolved[SMM_MAX_PARAMS];
@@ -571,12 +739,14 @@ __device__ __forceinline__ FinScratch fin_scratch(EvalSmem &sm) {
 __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, DevState st, int iter, int n_split,
                                                                 int part_len) {
   __shared__ EvalSmem sm;
+  __shared__ uint4 s_zigtab[kZigBufEntries];  // 16 KB: the 8 KB-aligned half holds the table (see load_zigtab)
   const int c = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
   const int gc = pb.chain0 + c;
   const Grp g{tid, (int)blockDim.x, 0};
   const size_t stamp = (size_t)c * n_split + split;
   PHASE_STAMP(stamp, 0);
   load_logtab(sm.logtab);
+  load_zigtab(s_zigtab);
   __syncthreads();
   group_proposal(pb, st, g, prop_scratch(sm), c, gc, iter, split == 0);
   PHASE_STAMP(stamp, 1);
@@ -587,7 +757,7 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, D
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
     const int nb = (pb.S + 1) >> 1;
     const int j0 = (int)(((long long)nb * split) / n_split), j1 = (int)(((long long)nb * (split + 1)) / n_split);
-    simulate_static(pb, g, sm.logtab, sm.pp, j0, j1, (uint32_t)gc, (uint32_t)iter, sm.red,
+    simulate_static(pb, g, s_zigtab, sm.pp, j0, j1, (uint32_t)gc, (uint32_t)iter, sm.red, sm.zfix, sm.zq,
                     part_base + (size_t)split * part_len);
     PHASE_STAMP(stamp, 2);
     if (n_split > 1) {
@@ -733,8 +903,6 @@ struct PersistSmem {
   // proposals
   double g_pp[kPGroups][SMM_MAX_PARAMS];
   double g_mu01[kPGroups][SMM_MAX_PARAMS];
-  double cand[kPropCand];
-  unsigned char okf[kPropCand];
   int g_first[kPGroups][SMM_MAX_PARAMS];
   int g_resolved[kPGroups][SMM_MAX_PARAMS];
 };
@@ -828,11 +996,14 @@ __device__ void warp_publish_segment(const DevProblem &pb, const DevState &st, P
   group_accept_store(pb, st, gw, fs, c, pb.chain0 + c, it, fused);
 }
 
-// dynamic smem: val[N] (double) own[N] exch[N] (u16) | pp_seg[n][D] | acc[n][2D] (u64) | fscratch[n][2D+M+4]
+// dynamic smem: val[N] (double) own[N] exch[N] (u16) | pp_seg[n][D] | acc[n][2D] (u64) | fscratch[n][2D+M+4] |
+//               cand[kPropCand] (proposal candidates) | zq[32 warps][kZigQWords] (u32: deferred ziggurat draws) |
+//               okf[kPropCand] (u8)
 __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevProblem pb, DevState st, int iter0,
                                                                             int n_iters, int sched_iter0, int n_s,
                                                                             int part_len, int max_seg, int cta_seg) {
   __shared__ PersistSmem sm;
+  __shared__ uint4 s_zigtab[kZigBufEntries];  // 16 KB: the 8 KB-aligned half holds the table (see load_zigtab)
   extern __shared__ double smem_d[];
   const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
   const int lane = tid & 31;
@@ -846,7 +1017,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
   double *pp_seg = val + N + (N + 1) / 2 + (n_s + 1);  // u16 arrays = N/2 doubles, schedule = n_s + 1/2 doubles
   unsigned long long *acc = (unsigned long long *)(pp_seg + (size_t)cta_seg * D);
   double *fscratch = (double *)(acc + (size_t)cta_seg * 2 * D);
+  double *cand = fscratch + (size_t)cta_seg * fs_len;                      // [kPropCand] proposal candidates
+  uint32_t *zq = (uint32_t *)(cand + kPropCand) + (size_t)(tid >> 5) * kZigQWords;
+  unsigned char *okf = (unsigned char *)((uint32_t *)(cand + kPropCand) + (kPersistThreads / 32) * kZigQWords);  // [kPropCand]
   load_logtab(sm.logtab);
+  load_zigtab(s_zigtab);
   unsigned gen = ld_volatile_u32(&st.bar->gen) & 0x7fffffffu;
   unsigned long long seq = ld_volatile_u64(st.sync_seq);
   const int nb = (S + 1) >> 1;
@@ -887,10 +1062,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
   const int gi = tid / gsize;
   const Grp gprop{tid - gi * gsize, gsize, 1 + gi};
   const int cand_per_group = kPropCand / ngroups;
-  const PropScratch ps{sm.g_pp[gi], sm.g_mu01[gi], sm.cand + (size_t)gi * cand_per_group,
-                       sm.okf + (size_t)gi * cand_per_group, sm.g_first[gi], sm.g_resolved[gi], sm.logtab};
+  const PropScratch ps{sm.g_pp[gi], sm.g_mu01[gi], cand + (size_t)gi * cand_per_group,
+                       okf + (size_t)gi * cand_per_group, sm.g_first[gi], sm.g_resolved[gi], sm.logtab};
   const int k = lane % D, jo = lane / D;
   const bool lane_on = lane < rows * D;
+  const bool all_on = rows * D == 32;
 
   for (int it = iter0; it < iter0 + n_iters; ++it) {
     // ---- exchange of iteration it-1 (AlgoBGP.jl:637), then this iteration's proposals ----
@@ -924,11 +1100,26 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       uint32_t c2 = 0u, c3 = c3base;
       double p = 0.0;
       Acc a{0ull, 0ull};
-      int next = 0;
-      if (lane == 0) next = atomicAdd(&sm.next_unit, 1);
-      next = __shfl_sync(0xffffffffu, next, 0);
+      ZigCtx cx = zig_ctx(s_zigtab, zq, S);
+      cx.D = D;
+      const uint32_t pp_seg_s = smem_addr(pp_seg), acc_s = smem_addr(acc);
+      int qn = 0;  // deferred ziggurat draws of this warp (all of the current segment)
+      // Guided self-scheduling: a warp takes (remaining / 2 warps-worth, at most kMaxGrab, at least 1) consecutive units
+      // from the CTA's queue, so the CTA's 32 warps finish within one step of each other.
+      int u = 0, uend = 0;
       for (;;) {
-        const int u = next;
+        if (u >= uend) {
+          int start = 0, g = 0;
+          if (lane == 0) {
+            const int rem = total_units - *(volatile int *)&sm.next_unit;
+            g = rem > 64 * kMaxGrab ? kMaxGrab : (rem > 64 ? rem >> 6 : 1);
+            start = atomicAdd(&sm.next_unit, g);
+          }
+          start = __shfl_sync(0xffffffffu, start, 0);
+          g = __shfl_sync(0xffffffffu, g, 0);
+          u = start;
+          uend = start + g < total_units ? start + g : total_units;
+        }
         int s = cur;
         if (u < total_units) {
           if (s < 0 || u >= sm.seg_unit0[s + 1]) {
@@ -940,6 +1131,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
         }
         if (s != cur) {
           if (cur >= 0) {  // leave segment `cur`: add this warp's exact sums to the CTA's, count its units
+            zig_flush(cx, qn, pb.magic_sum, pb.magic_sq);
             for (int r = 1; r < rows; ++r) {
               const unsigned long long os = __shfl_down_sync(0xffffffffu, a.sum, r * D);
               const unsigned long long oq = __shfl_down_sync(0xffffffffu, a.sq, r * D);
@@ -973,24 +1165,45 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
             j1 = sm.seg_j1[s];
             jfull = j1 < n_full ? j1 : n_full;
             p = lane_on ? pp_seg[(size_t)s * D + k] : 0.0;
+            cx.pvec = pp_seg_s + 8u * (uint32_t)(s * D);
+            cx.fix = acc_s + 8u * (uint32_t)(s * 2 * D);
             c2 = pb.noseed ? (uint32_t)(pb.chain0 + sm.seg_c[s]) : 0u;
             c3 = c3base | (pb.noseed ? ((uint32_t)it & SMM_ITER_MASK) : 0u);
           }
         }
         if (s < 0) break;
-        if (lane == 0) next = atomicAdd(&sm.next_unit, 1);  // prefetch: the latency hides behind the math
-        ++units_cur;
-        if (lane_on && pb.obj != SMM_OBJ_FAILS) {
-          const int jb = j0 + (u - sm.seg_unit0[s]) * unit_j + jo;
+        // the part of the grabbed range that lies in this segment: units [u, ue)
+        const int ue = uend < sm.seg_unit0[s + 1] ? uend : sm.seg_unit0[s + 1];
+        units_cur += ue - u;
+        if (pb.obj != SMM_OBJ_FAILS) {  // every lane of the warp walks the steps (ballots inside add_pair)
+          const int ju = j0 + (u - sm.seg_unit0[s]) * unit_j;   // first block of the range
+          const int jue = j0 + (ue - sm.seg_unit0[s]) * unit_j;  // one past its last block
+          const int n_steps = (ue - u) * kUnitSteps;
+          const int jb = ju + jo;
+          if (all_on && jue <= jfull) {
+            int q = 0;
+            while (q < n_steps) {  // the inner loop is call-free: it leaves when 32 deferred draws have gathered
 #pragma unroll 1
-          for (int q = 0; q < kUnitSteps; ++q) {
-            const int j = jb + q * rows;
-            if (j < jfull) add_pair(pb, sm.logtab, a, p, (uint32_t)j, (uint32_t)k, c2, c3, true);
+              for (; q < n_steps && qn < 32; ++q)
+                add_pair<false>(pb, cx, qn, a, p, (uint32_t)(jb + q * rows), (uint32_t)k, c2, c3, true, true);
+              zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
+            }
+          } else {
+#pragma unroll 1
+            for (int q = 0; q < n_steps; ++q) {
+              const int j = jb + q * rows;
+              const bool act = lane_on && j < jfull;
+              add_pair<true>(pb, cx, qn, a, p, (uint32_t)j, (uint32_t)k, c2, c3, act, act);
+              zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
+            }
           }
-          if ((S & 1) && jb <= n_full && n_full < jb + unit_j && n_full < j1 && (n_full - jb) % rows == 0)
-            add_pair(pb, sm.logtab, a, p, (uint32_t)n_full, (uint32_t)k, c2, c3, false);  // odd S: the single last draw
+          if ((S & 1) && n_full < j1 && ju <= n_full && n_full < jue) {  // odd S: the single last draw
+            const bool act = lane_on && jb <= n_full && (n_full - jb) % rows == 0;
+            add_pair<true>(pb, cx, qn, a, p, (uint32_t)n_full, (uint32_t)k, c2, c3, act, false);
+            zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
+          }
         }
-        next = __shfl_sync(0xffffffffu, next, 0);
+        u = ue;
       }
     }
     PHASE_STAMP((b * 2 + (it & 1)) * 2, 1);  // warp 0 left the work loop
@@ -1013,9 +1226,11 @@ __global__ void __launch_bounds__(kEvalThreads) objective_kernel(DevProblem pb, 
                                                                  double *partials, unsigned *arrive, double *value,
                                                                  double *moments, int *status) {
   __shared__ EvalSmem sm;
+  __shared__ uint4 s_zigtab[kZigBufEntries];
   const int bi = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
   const Grp g{tid, (int)blockDim.x, 0};
   load_logtab(sm.logtab);
+  load_zigtab(s_zigtab);
   for (int k = tid; k < pb.P; k += blockDim.x) sm.pp[k] = params[(size_t)bi * pb.P + k];
   __syncthreads();
   pb.noseed = noseed;
@@ -1026,7 +1241,7 @@ __global__ void __launch_bounds__(kEvalThreads) objective_kernel(DevProblem pb, 
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
     const int nb = (pb.S + 1) >> 1;
     const int j0 = (int)(((long long)nb * split) / n_split), j1 = (int)(((long long)nb * (split + 1)) / n_split);
-    simulate_static(pb, g, sm.logtab, sm.pp, j0, j1, (uint32_t)bi, rep0 + (uint32_t)bi, sm.red,
+    simulate_static(pb, g, s_zigtab, sm.pp, j0, j1, (uint32_t)bi, rep0 + (uint32_t)bi, sm.red, sm.zfix, sm.zq,
                     part_base + (size_t)split * part_len);
     if (n_split > 1) {
       if (tid == 0) {
@@ -1141,11 +1356,16 @@ __global__ void __launch_bounds__(kPairThreads) bgp_pairs_kernel(DevProblem pb, 
 // ------------------------------------------------------------------------------------------------
 // diagnostics
 // ------------------------------------------------------------------------------------------------
-__global__ void debug_normals_kernel(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, double *out) {
+__global__ void debug_normals_kernel(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, int zig,
+                                     double *out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_pairs) return;
   double z0, z1;
-  smm_normal_pair(smm_philox4x32_10((uint32_t)j, k, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32)), &z0, &z1);
+  const smm_u32x4 r = smm_philox4x32_10((uint32_t)j, k, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  if (zig)
+    smm_zig_pair(r, &z0, &z1);
+  else
+    smm_normal_pair(r, &z0, &z1);
   out[2 * j] = z0;
   out[2 * j + 1] = z1;
 }
@@ -1231,38 +1451,59 @@ __global__ void __launch_bounds__(kPersistThreads, 1) barrier_bench_kernel(DevPr
 // the simulate inner loop alone (add_pair with the handle's keys and accumulators), static or dynamic unit
 // distribution, any CTA size: the ceiling the evaluation kernels are measured against
 __global__ void __launch_bounds__(1024) sim_throughput_kernel(DevProblem pb, int n_per_thread, int dyn, double *out) {
-  __shared__ smm_logent tab[1 << SMM_LOG_BITS];
+  __shared__ uint4 ztab[kZigBufEntries];
+  extern __shared__ uint32_t zq[];  // [blockDim.x / 32][kZigQWords]
+  __shared__ unsigned long long fix[2 * SMM_MAX_PARAMS];
+  __shared__ double pvec[SMM_MAX_PARAMS];
   __shared__ int ctr;
-  load_logtab(tab);
+  load_zigtab(ztab);
   if (threadIdx.x == 0) ctr = 0;
-  __syncthreads();
   const int lane = threadIdx.x & 31, D = pb.P;
+  for (int e = threadIdx.x; e < D; e += blockDim.x) pvec[e] = 0.25 * (double)e;
+  for (int e = threadIdx.x; e < 2 * D; e += blockDim.x) fix[e] = 0ull;
+  __syncthreads();
   const uint32_t k = (uint32_t)(lane % D);
   Acc a{0ull, 0ull};
-  const double p = 0.25 * (double)k;
+  const double p = pvec[k];
+  ZigCtx cx = zig_ctx(ztab, zq + (size_t)(threadIdx.x >> 5) * kZigQWords, pb.S);
+  cx.pvec = smem_addr(pvec);
+  cx.fix = smem_addr(fix);
+  cx.D = D;
+  int qn = 0;
   if (!dyn) {
     const uint32_t j0 = (blockIdx.x * blockDim.x + threadIdx.x) / D * (uint32_t)n_per_thread;
-    for (int j = 0; j < n_per_thread; ++j) add_pair(pb, tab, a, p, j0 + (uint32_t)j, k, 0u, SMM_STREAM_SIM << 28, true);
+    int j = 0;
+    while (j < n_per_thread) {
+#pragma unroll 1
+      for (; j < n_per_thread && qn < 32; ++j)
+        add_pair<false>(pb, cx, qn, a, p, j0 + (uint32_t)j, k, 0u, SMM_STREAM_SIM << 28, true, true);
+      zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
+    }
   } else {
-    const int rows = 32 / D, unit = rows * kUnitSteps, jo = lane / D;
-    const int jmax = n_per_thread * (blockDim.x / D);
+    const int rows = 32 / D, unit = rows * kTputSteps, jo = lane / D;
+    const int jmax = n_per_thread * (blockDim.x / D) / unit * unit;
     int next = 0;
     if (lane == 0) next = atomicAdd(&ctr, unit);
     next = __shfl_sync(0xffffffffu, next, 0);
     while (next < jmax) {
       const int base = next + jo;
       if (lane == 0) next = atomicAdd(&ctr, unit);
+      int u = 0;
+      while (u < kTputSteps) {
 #pragma unroll 1
-      for (int u = 0; u < kUnitSteps; ++u) {
-        const int j = base + u * rows;
-        if (j < jmax) add_pair(pb, tab, a, p, (uint32_t)j + blockIdx.x * 1000003u, k, 0u, SMM_STREAM_SIM << 28, true);
+        for (; u < kTputSteps && qn < 32; ++u)
+          add_pair<false>(pb, cx, qn, a, p, (uint32_t)(base + u * rows) + blockIdx.x * 1000003u, k, 0u,
+                          SMM_STREAM_SIM << 28, true, true);
+        zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
       }
       next = __shfl_sync(0xffffffffu, next, 0);
     }
   }
+  zig_flush(cx, qn, pb.magic_sum, pb.magic_sq);
+  __syncthreads();
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  out[2 * gid] = __longlong_as_double((long long)a.sum);
-  out[2 * gid + 1] = __longlong_as_double((long long)a.sq);
+  out[2 * gid] = __longlong_as_double((long long)(a.sum + fix[k]));
+  out[2 * gid + 1] = __longlong_as_double((long long)(a.sq + fix[D + k]));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1278,7 +1519,8 @@ size_t exch_smem_bytes(int N) { return sizeof(double) * (size_t)N + sizeof(unsig
 // persistent kernel: exchange arrays (u16 part rounded up to whole doubles) + per-segment pp / sums / finalisation scratch
 size_t persist_smem_bytes(int N, int D, int M, int cta_seg) {
   const int n_s = N < 3 ? (N > 1 ? N - 1 : 0) : N;
-  return sizeof(double) * ((size_t)N + (N + 1) / 2 + (n_s + 1) + (size_t)cta_seg * (D + 2 * D + 2 * D + M + 4));
+  return sizeof(double) * ((size_t)N + (N + 1) / 2 + (n_s + 1) + (size_t)cta_seg * (D + 2 * D + 2 * D + M + 4)) +
+         sizeof(double) * kPropCand + sizeof(uint32_t) * (size_t)(kPersistThreads / 32) * kZigQWords + kPropCand;
 }
 
 cudaError_t configure_kernels(int N, int n_s) {
@@ -1333,9 +1575,9 @@ void launch_objective(const DevProblem &pb, const double *params, int B, int nos
   objective_kernel<<<grid, kEvalThreads, 0, s>>>(pb, params, noseed, rep0, n_split, part_len, partials, arrive, value,
                                                  moments, status);
 }
-void launch_debug_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, double *out,
+void launch_debug_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, int zig, double *out,
                           cudaStream_t s) {
-  debug_normals_kernel<<<(n_pairs + 255) / 256, 256, 0, s>>>(seed, k, c2, c3, n_pairs, out);
+  debug_normals_kernel<<<(n_pairs + 255) / 256, 256, 0, s>>>(seed, k, c2, c3, n_pairs, zig, out);
 }
 void launch_rng_throughput(long long n_per_thread, int blocks, double *out, cudaStream_t s) {
   rng_throughput_kernel<<<blocks, kEvalThreads, 0, s>>>(n_per_thread, out);
@@ -1348,7 +1590,9 @@ cudaError_t launch_barrier_bench(const DevProblem &pb, const DevState &st, int v
 }
 void launch_sim_throughput(const DevProblem &pb, int n_per_thread, int blocks, int threads, int dyn, double *out,
                            cudaStream_t s) {
-  sim_throughput_kernel<<<blocks, threads, 0, s>>>(pb, n_per_thread, dyn, out);
+  const size_t dyn_smem = sizeof(uint32_t) * (threads / 32) * kZigQWords;
+  cudaFuncSetAttribute(sim_throughput_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+  sim_throughput_kernel<<<blocks, threads, dyn_smem, s>>>(pb, n_per_thread, dyn, out);
 }
 
 }  // namespace smm

@@ -17,7 +17,8 @@ sys.path.insert(0, ROOT)
 from oracle import oracle_lib  # noqa: E402
 from smm_jl_b200 import configs  # noqa: E402
 
-out = {"normals_bits": oracle_lib.normals(1234, 0, 0, 1 << 28, 64).view(np.uint64)}
+out = {"normals_bits": oracle_lib.normals(1234, 0, 0, 1 << 28, 64).view(np.uint64),
+       "zig_normals_bits": oracle_lib.zig_normals(1234, 0, 0, 1 << 28, 4096).view(np.uint64)}
 for tag, cfg, n in (("c1", configs.c1_serial_normal(40), 40), ("mv", configs.mvnormal(8, 10), 10)):
     r = oracle_lib.run(cfg, n)
     for f in r.trace.FLOAT_FIELDS + r.trace.INT_FIELDS:

@@ -26,6 +26,35 @@ def test_normals_bit_exact(smm, oracle):
         assert np.array_equal(g.view(np.uint64), o.view(np.uint64))
 
 
+def test_ziggurat_normals_bit_exact(smm, oracle):
+    """the simulator stream of the MvNormal objectives (fast path, wedges, tails, retries: 1.5 % of 400 000 draws leave
+    the fast path) is bit-identical on host and device"""
+    for (seed, k, c2, c3) in [(1234, 0, 0, 1 << 28), (1234, 7, 0, 1 << 28), (99, 3, 17, (1 << 28) | 5)]:
+        g = smm.debug_zig_normals(seed, k, c2, c3, 200000)
+        o = oracle.zig_normals(seed, k, c2, c3, 200000)
+        assert np.array_equal(g.view(np.uint64), o.view(np.uint64))
+        assert np.abs(g).max() > 3.6541528853610088      # the tail branch was exercised
+
+
+@pytest.mark.parametrize("n_sim", [1, 2, 63, 64, 65, 1001, 4096])
+def test_deferred_ziggurat_matches_sequential_definition(smm, oracle, n_sim):
+    """the kernels resolve rejected fast-path candidates later, in warp-sized batches, and patch the exact integer
+    accumulators; the totals must equal the oracle's draw-by-draw evaluation for ragged draw counts, in both modes"""
+    rng = np.random.default_rng(n_sim)
+    for P in (1, 3, 8):
+        cfg = configs.mvnormal(1, 1, n_params=P, n_sim=max(n_sim, 2))
+        p = rng.uniform(-3, 3, (24, P))
+        for noseed in (0, 1):
+            with smm.BGPHandle(cfg) as h:
+                v, m, st = h.eval_batch(p, noseed=noseed, rep0=5)
+            vo, mo, so = oracle.eval_batch(cfg, p, noseed=noseed, rep0=5, n_threads=4)
+            np.testing.assert_array_equal(st, so)
+            # the fixed-point grids (2^-43 for x, 2^-37 for x^2) bound the absolute error of a moment; a sample variance
+            # of two or three draws can be tiny, so the bound is absolute here (north star: 1e-6 relative)
+            np.testing.assert_allclose(m, mo, rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(v, vo, rtol=1e-7, atol=1e-9)
+
+
 @pytest.mark.parametrize("niter", [1, 2, 50])
 def test_c1_serial_normal_parity(smm, oracle, niter):
     cfg = configs.c1_serial_normal(niter)
@@ -119,6 +148,7 @@ def test_golden_vectors_on_gpu(smm):
     from smm_jl_b200._abi import Trace
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bgp_golden.npz"))
     assert np.array_equal(smm.debug_normals(1234, 0, 0, 1 << 28, 64).view(np.uint64), g["normals_bits"])
+    assert np.array_equal(smm.debug_zig_normals(1234, 0, 0, 1 << 28, 4096).view(np.uint64), g["zig_normals_bits"])
     for tag, cfg, n in (("c1", configs.c1_serial_normal(40), 40), ("mv", configs.mvnormal(8, 10), 10)):
         tr, sigma, *_ = run_gpu(smm, cfg, n)
         for f in Trace.INT_FIELDS:

@@ -91,3 +91,15 @@ def test_persistent_other_objectives(smm, oracle):
     cfg = configs.slow_normal(8, 6, slow_seconds=0.01, exchange_mode=1)
     tr, *_ = run_gpu(smm, cfg, 6)
     assert_trace_parity(tr, oracle.run(configs.slow_normal(8, 6, slow_seconds=0.0), 6).trace)
+
+
+@pytest.mark.parametrize("n_params,n_sim", [(1, 777), (3, 1000), (5, 4001), (16, 512), (20, 999), (32, 300)])
+def test_persistent_ragged_shapes(smm, oracle, n_params, n_sim):
+    """rows that do not tile a warp (masked lanes), odd draw counts, units that end inside a step: the deferred
+    ziggurat queue and the exact accumulators must still reproduce the oracle's sequential sums"""
+    niter = 12
+    cfg = configs.mvnormal(12, niter, n_params=n_params, exchange_mode=1, n_sim=n_sim)
+    tr, sigma, acc, ctr = run_gpu(smm, cfg, niter)
+    ref = oracle.run(cfg, niter, n_threads=8)
+    assert_trace_parity(tr, ref.trace)
+    np.testing.assert_array_equal(sigma, ref.sigma)

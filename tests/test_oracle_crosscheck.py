@@ -22,9 +22,21 @@ def test_philox_numpy_vs_cpp(oracle):
 
 
 def test_normals_numpy_vs_cpp(oracle):
-    z = oracle.normals(1234, 3, 0, 1 << 28, 4000)
-    want = oracle_np.sim_normals(1234, 3, 8000)
+    z = oracle.normals(1234, 3, 0, 1 << 28, 4000)                      # Box-Muller (proposals, panel)
+    want = oracle_np.sim_normals(1234, 3, 8000, transform="bm")
     np.testing.assert_allclose(z, want, rtol=0, atol=4e-15)
+
+
+def test_ziggurat_numpy_vs_cpp(oracle):
+    """the simulator stream of the MvNormal objectives: header (fma-only exp/log, generated tables) against the
+    numpy re-derivation (tables from mpmath, libm exp/log).  The fast path must agree to the bit."""
+    n_pairs = 100_000
+    z = oracle.zig_normals(1234, 5, 0, 1 << 28, n_pairs)
+    want = oracle_np.sim_normals(1234, 5, 2 * n_pairs)
+    np.testing.assert_allclose(z, want, rtol=0, atol=2e-15)
+    assert np.mean(z == want) > 0.9995
+    W, KH, F, R = oracle_np.zig_tables()
+    assert R == 3.6541528853610088          # Marsaglia & Tsang's published constant for 256 layers
 
 
 def test_streams_numpy_vs_cpp(oracle):
@@ -89,6 +101,7 @@ def test_golden_vectors(oracle):
     """committed fixtures (tests/golden/make_golden.py): regression pins of the stream + algorithm"""
     g = np.load(os.path.join(GOLDEN, "bgp_golden.npz"))
     np.testing.assert_array_equal(oracle.normals(1234, 0, 0, 1 << 28, 64).view(np.uint64), g["normals_bits"])
+    np.testing.assert_array_equal(oracle.zig_normals(1234, 0, 0, 1 << 28, 4096).view(np.uint64), g["zig_normals_bits"])
     cfg = configs.c1_serial_normal(40)
     tr = oracle.run(cfg, 40).trace
     for f in tr.INT_FIELDS:

@@ -64,6 +64,83 @@ def test_normals_are_standard_normal(oracle):
     assert abs(np.corrcoef(z, z2)[0, 1]) < 5e-3
 
 
+def test_exp_accuracy(oracle):
+    mp.mp.prec = 120
+    rng = np.random.default_rng(3)
+    ts = list(-rng.random(1500) * 8) + [0.0, -1e-300, -0.34657359027997264, -0.3465735902799727, -6.68, -50.0, -700.0]
+    worst = max(abs(mp.mpf(oracle.exp_neg(float(t))) / mp.exp(mp.mpf(float(t))) - 1) for t in ts)
+    assert worst < 4e-16
+
+
+def _zig_reference(a, b):
+    """the definition of the fast path in exact arithmetic, from independently derived tables"""
+    from oracle import oracle_np
+    W, KH, _, _ = oracle_np.zig_tables()
+    i = (a >> 23) & 0xFF
+    hi20 = a & 0xFFFFF
+    u = mp.mpf((hi20 << 32) | b) / 2 ** 52
+    x = u * mp.mpf(float(W[i]))
+    return (-x if a >> 31 else x), hi20 < int(KH[i]), i
+
+
+def test_ziggurat_fast_path_matches_its_definition(oracle):
+    mp.mp.prec = 120
+    rng = np.random.default_rng(4)
+    n_slow = 0
+    for _ in range(4000):
+        a, b = [int(v) for v in rng.integers(0, 2 ** 32, 2)]
+        z, slow = oracle.zig_from_words(a, b)
+        want, ok, _ = _zig_reference(a, b)
+        assert slow == (not ok)
+        if ok:
+            assert abs(mp.mpf(z) - want) <= abs(want) * 2.0 ** -53      # one correctly rounded multiplication
+        n_slow += slow
+    assert 20 <= n_slow <= 110                                            # 1.49 % of 4000
+
+
+def test_ziggurat_slow_path_by_layer(oracle):
+    """every layer's wedge and the tail, with words chosen to fail the fast test: the result must lie in the layer
+    (or a retry's), be finite, carry the drawn sign when it is the original candidate, and the tail lies beyond R"""
+    from oracle import oracle_np
+    W, KH, _, R = oracle_np.zig_tables()
+    for i in range(256):
+        for sign in (0, 1):
+            a = (sign << 31) | (i << 23) | 0xFFFFF            # u = 1 - 2^-20...: outermost sliver of the layer
+            z, slow = oracle.zig_from_words(a, 0x12345678)
+            assert slow and np.isfinite(z)
+            if i == 0:
+                assert abs(z) > R and (z < 0) == bool(sign)
+            want = oracle_np.zig_slow(a, 0x12345678)
+            assert abs(z - want) < 2e-15
+
+
+def test_extreme_ziggurat_words(oracle):
+    for a in (0, 0xffffffff, 0x80000000, 0x7fffffff, 0x000fffff, 0x7f800000):
+        for b in (0, 0xffffffff):
+            z, _ = oracle.zig_from_words(a, b)
+            assert np.isfinite(z) and abs(z) < 13.6
+
+
+def test_ziggurat_normals_are_standard_normal(oracle):
+    z = oracle.zig_normals(1234, 0, 0, 1 << 28, 2_000_000)
+    n = z.size
+    assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.var() - 1) < 4 * np.sqrt(2 / n)
+    assert abs((z ** 4).mean() - 3) < 4 * np.sqrt(96 / n)
+    assert stats.kstest(z[:500_000], "norm").pvalue > 1e-3
+    # chi-square over 200 equiprobable cells (cuts fall inside layers, wedges and the tail alike)
+    cuts = stats.norm.ppf(np.linspace(0, 1, 201)[1:-1])
+    cnt = np.bincount(np.searchsorted(cuts, z), minlength=200)
+    assert stats.chisquare(cnt).pvalue > 1e-3
+    # the tail beyond R and far tails
+    R = 3.6541528853610088
+    for t in (R, 4.0, 4.5):
+        k, p = (np.abs(z) > t).sum(), 2 * stats.norm.sf(t)
+        assert abs(k - n * p) < 5 * np.sqrt(n * p) + 1
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 4 / np.sqrt(n / 2)   # the two halves of a block
+    z2 = oracle.zig_normals(1234, 1, 0, 1 << 28, 2_000_000)                # another row: independent stream
+    assert abs(np.corrcoef(z, z2)[0, 1]) < 4 / np.sqrt(n)
+
+
 def test_acc_uniform_range_and_determinism(oracle):
     u = np.array([oracle.acc_uniform(12, c, it) for c in range(3) for it in range(1, 400)])
     assert (u >= 0).all() and (u < 1).all() and abs(u.mean() - 0.5) < 0.05
