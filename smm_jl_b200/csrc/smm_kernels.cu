@@ -289,6 +289,7 @@ __device__ __forceinline__ ZigCtx zig_ctx(const uint4 *zbuf, uint32_t *q_warp, i
   cx.ztab = zig_table_addr(zbuf) | zero;
   cx.c3ff = 0x3FF00000u | zero;
   cx.q = smem_addr(q_warp);
+  asm volatile("" : "+r"(cx.q));  // opaque: keep the address in a register instead of recomputing it from %tid per push
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(cx.lt));
   cx.pvec = 0;
   cx.fix = 0;
@@ -333,18 +334,10 @@ __device__ __noinline__ void zig_drain(const ZigCtx cx, double magic_sum, double
   __syncwarp();
 }
 
-// all 32 lanes call this together (qn is warp-uniform)
-__device__ __forceinline__ void zig_push(const ZigCtx &cx, int &qn, bool slow, uint32_t a, uint32_t b, uint32_t k) {
-  const unsigned m = __ballot_sync(0xffffffffu, slow);
-  if (m) {
-    if (slow) {
-      const uint32_t qa = cx.q + 4u * (uint32_t)(qn + __popc(m & cx.lt));
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(a) : "memory");
-      asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(qa), "r"(b), "n"(4 * kZigQCap) : "memory");
-      asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(qa), "r"(k), "n"(8 * kZigQCap) : "memory");
-    }
-    qn += __popc(m);
-  }
+__device__ __forceinline__ void zig_store(uint32_t qa, uint32_t a, uint32_t b, uint32_t k) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(a) : "memory");
+  asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(qa), "r"(b), "n"(4 * kZigQCap) : "memory");
+  asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(qa), "r"(k), "n"(8 * kZigQCap) : "memory");
 }
 // between steps: bring the queue back below 32 entries (full warps of work only)
 __device__ __forceinline__ void zig_relieve(const ZigCtx &cx, int &qn, double magic_sum, double magic_sq) {
@@ -393,9 +386,13 @@ __device__ __forceinline__ void add_pair(const DevProblem &pb, const ZigCtx &cx,
     a.sum += s0 + s1;
     a.sq += q0 + q1;
   }
-  if (__any_sync(0xffffffffu, slow0 || slow1)) {
-    zig_push(cx, qn, slow0, r.x, r.y, k);
-    zig_push(cx, qn, slow1, r.z, r.w, k);
+  if (__any_sync(0xffffffffu, slow0 || slow1)) {  // 62 % of the steps: some lane of the 64 draws left the fast path
+    const unsigned m0 = __ballot_sync(0xffffffffu, slow0), m1 = __ballot_sync(0xffffffffu, slow1);
+    const int n0 = __popc(m0);
+    const uint32_t base = cx.q + 4u * (uint32_t)qn;
+    if (slow0) zig_store(base + 4u * (uint32_t)__popc(m0 & cx.lt), r.x, r.y, k);
+    if (slow1) zig_store(base + 4u * (uint32_t)(n0 + __popc(m1 & cx.lt)), r.z, r.w, k);
+    qn += n0 + __popc(m1);
   }
 }
 
@@ -447,7 +444,8 @@ __device__ void simulate_static(const DevProblem &pb, const Grp &g, const uint4 
 }
 
 constexpr int kUnitSteps = 1;   // warp steps per work unit of the persistent kernel
-constexpr int kMaxGrab = 16;    // units a warp takes from its CTA's queue at once (guided: fewer towards the end)
+constexpr int kMaxGrab = 8;     // units a warp takes from its CTA's queue at once (guided: fewer towards the end)
+constexpr int kStaticNum = 3, kStaticDen = 4;  // share of a CTA's units that is split statically over its warps
 constexpr int kTputSteps = 8;   // sim_throughput_kernel: steps per queue access
 
 __device__ void group_distance(const DevProblem &pb, const Grp &g, const FinScratch &fs);
@@ -1054,6 +1052,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
   }
   __syncthreads();
   const int n_seg = sm.n_seg, total_units = sm.total_units;
+  // work distribution inside the CTA: every warp first walks a fixed share (kStaticNum/kStaticDen of an equal split,
+  // one queue access instead of many), the rest is handed out dynamically in shrinking grabs so that all 32 warps
+  // finish within a step of each other whatever the warp scheduler favours
+  const int static_units = (int)(((long long)total_units * kStaticNum / kStaticDen) / (kPersistThreads / 32));
   const int n_owned = b < L ? (L - b + G - 1) / G : 0;  // chains b, b + G, ...
   // proposal groups: as many threads per chain as the CTA can spare (more attempts per round)
   int ngroups = 1;
@@ -1090,7 +1092,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
     for (int e = tid; e < n_seg * D; e += kPersistThreads) pp_seg[e] = __ldcg(st.pp + (size_t)sm.seg_c[e / D] * P + e % D);
     for (int e = tid; e < n_seg * 2 * D; e += kPersistThreads) acc[e] = 0ull;
     if (tid < n_seg) sm.done[tid] = 0;
-    if (tid == 0) sm.next_unit = 0;
+    if (tid == 0) sm.next_unit = static_units * (kPersistThreads / 32);
     if (n_owned > 0 && N > 1 && it >= 2) prefetch_schedule(st, it, sched_iter0, n_s, sij, soff, &sm.nlev);
     __syncthreads();
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
@@ -1104,9 +1106,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       cx.D = D;
       const uint32_t pp_seg_s = smem_addr(pp_seg), acc_s = smem_addr(acc);
       int qn = 0;  // deferred ziggurat draws of this warp (all of the current segment)
-      // Guided self-scheduling: a warp takes (remaining / 2 warps-worth, at most kMaxGrab, at least 1) consecutive units
-      // from the CTA's queue, so the CTA's 32 warps finish within one step of each other.
-      int u = 0, uend = 0;
+      // Guided self-scheduling of what the static shares leave: a warp takes (remaining / 2 warps-worth, at most
+      // kMaxGrab, at least 1) consecutive units from the CTA's queue.
+      int u = (tid >> 5) * static_units, uend = u + static_units;  // this warp's fixed share comes first
       for (;;) {
         if (u >= uend) {
           int start = 0, g = 0;
