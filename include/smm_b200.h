@@ -98,7 +98,9 @@ typedef struct smm_bgp_config {
   uint8_t nccl_id[SMM_NCCL_ID_BYTES]; /* from smm_nccl_unique_id on rank 0 (ignored if world == 1)   */
   int32_t exchange_mode; /* 0 = one launch per iteration (+ ncclAllGather + exchange kernel when world > 1);
                             1 = persistent cooperative kernel; with world > 1 the all-gather is fused into it
-                            as peer stores over NVLink (CUDA IPC) and a flag exchange inside the grid barrier  */
+                            as peer stores over NVLink (CUDA IPC) and a flag exchange inside the grid barrier;
+                            2 = the same persistent kernel without any grid barrier: every CTA waits for per-chain
+                            completion tags (written by the warp that finished the chain, to every rank) instead    */
   int32_t n_split;       /* mode 0: CTAs per chain evaluation; mode 1: cap on CTAs per SM; 0 = automatic      */
 } smm_bgp_config;
 

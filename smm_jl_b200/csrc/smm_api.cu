@@ -24,7 +24,7 @@ int persistent_max_blocks_per_sm(int N, int D, int M, int cta_seg);
 int persistent_max_cta_seg();
 cudaError_t configure_persistent(int N, int D, int M, int cta_seg);
 cudaError_t launch_persistent(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int sched_iter0,
-                              int n_s, int part_len, int max_seg, int cta_seg, int grid, cudaStream_t s);
+                              int n_s, int part_len, int max_seg, int cta_seg, int grid, bool flow, cudaStream_t s);
 void launch_eval(const DevProblem &pb, const DevState &st, int iter, int n_split, int part_len, cudaStream_t s);
 void launch_pairs(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int n_s, cudaStream_t s);
 void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sched_idx, int n_s, cudaStream_t s);
@@ -123,7 +123,8 @@ struct smm_bgp {
   int panel_grid = 0;     // CTAs of the panel simulation kernel (one resident wave)
   int panel_variant = 2;  // register budget of the K = 8 instantiation (CTAs per SM)
   std::vector<double> h_lb, h_ub;
-  int mode = 0;           // 0 = multi-launch (+ NCCL), 1 = persistent kernel (+ fused peer-store all-gather)
+  int mode = 0;           // 0 = multi-launch (+ NCCL), 1 = persistent kernel (+ fused peer-store all-gather),
+                          // 2 = persistent kernel without grid barriers (per-chain completion tags)
   int grid = 0, max_seg = 1, cta_seg = 1;  // persistent kernel: CTAs, partial slots per chain, chains per CTA share
   void *peer_ptrs[3 * kMaxWorld] = {nullptr};  // IPC-opened peer buffers (closed in release)
   int iter = 0;      // iterations completed (algo.i)
@@ -151,7 +152,7 @@ struct smm_bgp {
   DevBuf<uint8_t> t_acc;
   DevBuf<int> t_status, t_exch, t_bestid;
   DevBuf<double> partials;
-  DevBuf<unsigned> arrive, unit_ctr;
+  DevBuf<unsigned> arrive, unit_ctr, applied;
   DevBuf<int> sched_ij, sched_off, sched_nlev, err;
   DevBuf<unsigned long long> counters, phase_ts;
 
@@ -165,7 +166,7 @@ struct smm_bgp {
     }
     if (comm) ncclCommDestroy(comm);
     comm = nullptr;
-    val_all.free(); pp.free(); bar.free(); sync_seq.free(); flags.free();
+    val_all.free(); pp.free(); bar.free(); sync_seq.free(); flags.free(); applied.free();
     lb.free(); ub.free(); init.free(); data.free(); w.free(); acc_tuner.free(); min_improve.free();
     sigma.free(); accept_rate.free(); la_cur.free(); la_pub.free(); la_all.free();
     n_noex.free(); n_acc.free();
@@ -391,15 +392,19 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   const double nan = std::numeric_limits<double>::quiet_NaN(), inf = std::numeric_limits<double>::infinity();
   if (int rc = fill(h->la_cur, (size_t)L * R, nan)) return rc;
   if (int rc = fill(h->la_pub, (size_t)L * R, nan)) return rc;
-  h->mode = cfg->exchange_mode ? 1 : 0;
-  if (h->world > 1) {
-    if (int rc = fill(h->la_all, (size_t)(h->mode ? 2 : 1) * N * R, nan, h->mode == 1)) return rc;
+  if (cfg->exchange_mode < 0 || cfg->exchange_mode > 2) return fail(SMM_E_ARG, "exchange_mode must be 0, 1 or 2");
+  h->mode = cfg->exchange_mode;
+  if (h->world > 1 || h->mode == 2) {
+    if (int rc = fill(h->la_all, (size_t)(h->mode ? 2 : 1) * N * R, nan, h->world > 1 && h->mode >= 1)) return rc;
   }
-  if (int rc = fill(h->val_all, (size_t)2 * N, nan, h->world > 1 && h->mode == 1)) return rc;
+  // [2][N] values by iteration parity, followed by [N] 64-bit completion tags (exchange_mode 2), zero = nothing done
+  if (int rc = fill(h->val_all, (size_t)3 * N, nan, h->world > 1 && h->mode >= 1)) return rc;
+  CUDA_TRY(cudaMemset(h->val_all.p + 2 * (size_t)N, 0, sizeof(double) * N));
+  if (int rc = fill(h->applied, (size_t)L, 0u)) return rc;
   if (int rc = fill(h->pp, (size_t)L * P, nan)) return rc;
   if (int rc = fill(h->bar, 1, GridBarrier{0u, 0u})) return rc;
   if (int rc = fill(h->sync_seq, 1, 0ull)) return rc;
-  if (int rc = fill(h->flags, (size_t)kMaxWorld, 0ull, h->world > 1 && h->mode == 1)) return rc;
+  if (int rc = fill(h->flags, (size_t)kMaxWorld, 0ull, h->world > 1 && h->mode >= 1)) return rc;
   // trace: unrun slots look like a fresh BGPChain (AlgoBGP.jl:81-89); Eval slots are `undef` -> NaN
   const size_t IL = (size_t)I * L;
   if (int rc = fill(h->t_value, IL, nan)) return rc;
@@ -438,12 +443,12 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   if (int rc = fill(h->unit_ctr, 1, 0u)) return rc;
   if (N > 1) CUDA_TRY(configure_kernels(N, h->n_s));
   h->max_seg = h->n_split;
-  if (h->mode == 1) {
+  if (h->mode >= 1) {
     int coop = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
     if (!coop) return fail(SMM_E_CUDA, "device does not support cooperative launches (exchange_mode 1)");
     if (P > 32)
-      return fail(SMM_E_UNSUPPORTED_SHAPE, "exchange_mode 1 (persistent kernel) needs n_params <= 32; use exchange_mode 0");
+      return fail(SMM_E_UNSUPPORTED_SHAPE, "exchange_mode 1/2 (persistent kernel) needs n_params <= 32; use exchange_mode 0");
     h->grid = prop.multiProcessorCount;  // one 1024-thread CTA per SM
     if (cfg->n_split > 0 && cfg->n_split < h->grid) h->grid = cfg->n_split;  // n_split caps the CTA count in this mode
     const long long Tj = (long long)L * n_blocks_philox;
@@ -536,7 +541,9 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
 
   DevState &st = h->st;
   st.sigma = h->sigma.p; st.accept_rate = h->accept_rate.p; st.n_noex = h->n_noex.p; st.n_acc = h->n_acc.p;
-  st.la_cur = h->la_cur.p; st.la_pub = h->la_pub.p; st.la_all = h->world > 1 ? h->la_all.p : h->la_pub.p;
+  st.la_cur = h->la_cur.p; st.la_pub = h->la_pub.p;
+  st.la_all = (h->world > 1 || h->mode == 2) ? h->la_all.p : h->la_pub.p;
+  st.applied = h->applied.p;
   st.t_value = h->t_value.p; st.t_prob = h->t_prob.p; st.t_curr = h->t_curr.p; st.t_best = h->t_best.p;
   st.t_params = h->t_params.p; st.t_mom = h->t_mom.p; st.t_acc = h->t_acc.p; st.t_status = h->t_status.p;
   st.t_exch = h->t_exch.p; st.t_bestid = h->t_bestid.p;
@@ -548,6 +555,10 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     st.peer_la_all[r] = nullptr;
     st.peer_val_all[r] = nullptr;
     st.peer_flags[r] = nullptr;
+  }
+  if (h->mode == 2) {  // the barrier-free kernel always uses the gather layout; with one rank the "peer" is this GPU
+    st.peer_la_all[0] = h->la_all.p;
+    st.peer_val_all[0] = h->val_all.p;
   }
   st.phase_ts = nullptr;
   if (getenv("SMM_PHASE_TS")) {
@@ -563,7 +574,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     ncclUniqueId id;
     memcpy(&id, cfg->nccl_id, sizeof id);
     NCCL_TRY(ncclCommInitRank(&h->comm, h->world, id, h->rank));
-    if (h->mode == 1) {
+    if (h->mode >= 1) {
       // fused all-gather: map every peer's gather buffers (CUDA IPC); the handles travel over the communicator
       struct Handles {
         cudaIpcMemHandle_t la, val, flags;
@@ -640,7 +651,7 @@ cudaError_t prof_end(smm_bgp *h) {
 int enqueue_iterations(smm_bgp *h, int n_iters) {
   cudaStream_t s = h->stream;
   const bool exchange = h->N > 1;
-  if (h->mode == 1) {
+  if (h->mode >= 1) {
     int left = n_iters;
     while (left > 0) {
       const int it0 = h->iter + 1;
@@ -664,7 +675,7 @@ int enqueue_iterations(smm_bgp *h, int n_iters) {
       }
       CUDA_TRY(prof_begin(h, 0));
       CUDA_TRY(launch_persistent(h->pb, h->st, it0, n, h->sched_iter0 < 0 ? 2 : h->sched_iter0, h->n_s, h->part_len,
-                                 h->max_seg, h->cta_seg, h->grid, s));
+                                 h->max_seg, h->cta_seg, h->grid, h->mode == 2, s));
       CUDA_TRY(prof_end(h));
       h->prof_iters += h->profiling ? n : 0;
       h->ctr.kernel_launches++;
@@ -788,7 +799,7 @@ int smm_bgp_run(smm_bgp *h, int32_t n_iters, int32_t window, const smm_trace_vie
     const int it0 = h->iter + 1;
     int n = left < window ? left : window;
     // keep windows aligned with the precomputed pair-schedule windows, so a launch never has to be cut in two
-    if (h->mode == 1 && h->N > 1 && h->sched_iter0 >= 0 && it0 >= h->sched_iter0 &&
+    if (h->mode >= 1 && h->N > 1 && h->sched_iter0 >= 0 && it0 >= h->sched_iter0 &&
         it0 < h->sched_iter0 + h->sched_n && it0 + n > h->sched_iter0 + h->sched_n)
       n = h->sched_iter0 + h->sched_n - it0;
     if (int rc = enqueue_iterations(h, n)) return rc;
@@ -1061,6 +1072,9 @@ int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes) {
   IN(h->st.t_exch, int, n);
   IN(h->st.t_bestid, int, n);
 #undef IN
+  // completion tags / applied marks of exchange_mode 2 refer to iterations of the run that is being replaced
+  CUDA_TRY(cudaMemset(h->val_all.p + 2 * (size_t)h->N, 0, sizeof(double) * h->N));
+  CUDA_TRY(cudaMemset(h->applied.p, 0, sizeof(unsigned) * L));
   h->iter = (int)hd.iter;
   h->sched_iter0 = -1;
   h->sched_n = 0;
@@ -1109,7 +1123,7 @@ int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij, int32_t *level_offset
 int smm_debug_phase_ts(smm_bgp *h, uint64_t *out, int64_t n) {
   if (!h || !out) return fail(SMM_E_ARG, "null argument");
   if (!h->st.phase_ts) return fail(SMM_E_STATE, "set SMM_PHASE_TS=1 before smm_bgp_create");
-  const int64_t blocks = h->mode == 1 ? (int64_t)h->grid * 4 : (int64_t)h->L * h->n_split;
+  const int64_t blocks = h->mode >= 1 ? (int64_t)h->grid * 4 : (int64_t)h->L * h->n_split;
   const int64_t have = blocks * 4;
   CUDA_TRY(cudaMemcpy(out, h->st.phase_ts, sizeof(uint64_t) * (n < have ? n : have), cudaMemcpyDeviceToHost));
   return (int)blocks;

@@ -58,7 +58,8 @@ struct DevState {
   double *la_cur;              // [L][R] last accepted record = proposal centre for the next iteration
   double *la_pub;              // [L][R] record published to the exchange step
   double *la_all;              // gathered records: [N][R] (multi-launch) or [2][N][R] by iteration parity (fused)
-  double *val_all;             // [2][N] compact values of la_all (fused mode)
+  double *val_all;             // [2][N] compact values of la_all (fused mode) | [N] u64 completion tags (exchange_mode 2)
+  unsigned *applied;           // [L] last exchange iteration applied to the chain's state (exchange_mode 2)
   double *pp;                  // [L][P] proposals of the current iteration (persistent kernel)
   // trace, [max_iter][L] (+[P], +[M])
   double *t_value, *t_prob, *t_curr, *t_best, *t_params, *t_mom;

@@ -102,6 +102,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
   return v;
 }
 
+constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;  // 4 s: a stuck peer becomes an error, not a hang
+
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -143,7 +145,7 @@ __device__ __forceinline__ smm_u32x4 philox_sim(const DevProblem &pb, uint32_t c
 // Result in ps.pp.
 // ------------------------------------------------------------------------------------------------
 __device__ void group_proposal(const DevProblem &pb, const DevState &st, const Grp &g, const PropScratch &ps, int c,
-                               int gc, int iter, bool count) {
+                               int gc, int iter, bool count, const double *centre = nullptr) {
   const int P = pb.P, tid = g.tid, nthr = g.n;
   if (iter == 1) {
     for (int k = tid; k < P; k += nthr) ps.pp[k] = pb.init[k];
@@ -151,7 +153,7 @@ __device__ void group_proposal(const DevProblem &pb, const DevState &st, const G
     return;
   }
   const int R = rec_len(pb.P, pb.M);
-  const double *la = st.la_cur + (size_t)c * R;
+  const double *la = centre ? centre : st.la_cur + (size_t)c * R;  // record of the last accepted evaluation
   const double sigma = __ldcg(st.sigma + c);
   const int kp = (P + 1) >> 1;
   const int A = nthr / kp;  // attempts per round
@@ -527,21 +529,70 @@ __device__ __forceinline__ void slow_spin(double seconds) {
 // the published record (la_pub) and -- fused multi-GPU mode -- the record and its value into every
 // rank's gather buffer (peer stores over NVLink).
 // ------------------------------------------------------------------------------------------------
+// flow (barrier-free persistent kernel): wait_applied != 0 -> first wait until the owner CTA has applied the exchange
+// of iteration iter-1 to this chain (st.applied[c] >= iter-1); at the end publish the chain's completion tag (= iter)
+// to every rank, which is what the next iteration of every CTA waits for instead of a grid barrier.
+__device__ __forceinline__ unsigned long long *done_tags(const DevProblem &pb, double *val_all) {
+  return (unsigned long long *)(val_all + 2 * (size_t)pb.N);
+}
+// The chain state doAcceptReject!/set_eval! read, fetched ahead of time by a 32-lane group (persistent kernel: before
+// the arrival atomic of the partial sums, so that the loads travel together with it instead of after it).
+constexpr int kPreRec = (3 + SMM_MAX_PARAMS + SMM_MAX_MOMENTS + 31) / 32;
+struct AcceptPre {
+  double old_value, sigma0, curr_prev, best_prev, u_acc;  // lane 0
+  int n_noex0, n_acc0, bestid_prev;                       // lane 0
+  double la[kPreRec];                                     // record entries lane, lane + 32, ... of la_cur[c]
+};
+__device__ __forceinline__ void wait_exchange_applied(const DevState &st, const Grp &g, int c, int iter) {
+  if (g.tid == 0) {
+    const unsigned long long t0 = gtimer();
+    unsigned spins = 0;
+    while (ld_acquire_gpu(st.applied + c) < (unsigned)(iter - 1)) {
+      if ((++spins & 255u) == 0 && ((ld_relaxed_gpu(&st.bar->gen) & 0x80000000u) || gtimer() - t0 > kSpinTimeoutNs)) {
+        atomicOr(st.err, kErrTimeout);
+        break;
+      }
+    }
+  }
+  gsync(g);
+}
+__device__ __forceinline__ void accept_prefetch(const DevProblem &pb, const DevState &st, int lane, int c, int gc, int iter,
+                                                AcceptPre &pre) {
+  const int R = rec_len(pb.P, pb.M), L = pb.L;
+  const double *la = st.la_cur + (size_t)c * R;
+  const size_t slot = (size_t)(iter - 1) * L + c;
+#pragma unroll
+  for (int q = 0; q < kPreRec; ++q) pre.la[q] = lane + 32 * q < R ? __ldcg(la + lane + 32 * q) : 0.0;
+  if (lane == 0) {
+    pre.old_value = pre.la[0];
+    pre.n_noex0 = __ldcg(st.n_noex + c);
+    pre.n_acc0 = __ldcg(st.n_acc + c);
+    pre.sigma0 = __ldcg(st.sigma + c);
+    const size_t prev_slot = iter > 1 ? slot - L : slot;
+    pre.curr_prev = __ldcg(st.t_curr + prev_slot);
+    pre.best_prev = __ldcg(st.t_best + prev_slot);
+    pre.bestid_prev = __ldcg(st.t_bestid + prev_slot);
+  }
+}
+
 __device__ void group_accept_store(const DevProblem &pb, const DevState &st, const Grp &g, const FinScratch &fs, int c,
-                                   int gc, int iter, bool fused) {
+                                   int gc, int iter, bool fused, bool flow = false, bool wait_applied = false,
+                                   const AcceptPre *pre = nullptr) {
   const int tid = g.tid;
   const int P = pb.P, M = pb.M, R = rec_len(P, M), L = pb.L;
+  if (flow && wait_applied && !pre) wait_exchange_applied(st, g, c, iter);
   double *la = st.la_cur + (size_t)c * R;
   double *pub = st.la_pub + (size_t)c * R;
   const size_t slot = (size_t)(iter - 1) * L + c;
   if (tid == 0) {
-    // everything this thread will need from global memory, requested at once (one L2 round trip)
-    const double old_value = __ldcg(la);
-    const int n_noex0 = __ldcg(st.n_noex + c), n_acc0 = __ldcg(st.n_acc + c);
-    const double sigma0 = __ldcg(st.sigma + c);
+    // everything this thread will need from global memory, requested at once (one L2 round trip) -- or already here
+    const double old_value = pre ? pre->old_value : __ldcg(la);
+    const int n_noex0 = pre ? pre->n_noex0 : __ldcg(st.n_noex + c), n_acc0 = pre ? pre->n_acc0 : __ldcg(st.n_acc + c);
+    const double sigma0 = pre ? pre->sigma0 : __ldcg(st.sigma + c);
     const size_t prev_slot = iter > 1 ? slot - L : slot;
-    const double curr_prev = __ldcg(st.t_curr + prev_slot), best_prev = __ldcg(st.t_best + prev_slot);
-    const int bestid_prev = __ldcg(st.t_bestid + prev_slot);
+    const double curr_prev = pre ? pre->curr_prev : __ldcg(st.t_curr + prev_slot);
+    const double best_prev = pre ? pre->best_prev : __ldcg(st.t_best + prev_slot);
+    const int bestid_prev = pre ? pre->bestid_prev : __ldcg(st.t_bestid + prev_slot);
     const double value = fs.value[0];
     double prob;
     int accepted, status = fs.flags[1];
@@ -566,7 +617,7 @@ __device__ void group_accept_store(const DevProblem &pb, const DevState &st, con
           accepted = 1;
         } else {
           status = 1;
-          accepted = prob > smm_acc_uniform(pb.seed_algo, (uint32_t)gc, (uint32_t)iter);
+          accepted = prob > (pre ? pre->u_acc : smm_acc_uniform(pb.seed_algo, (uint32_t)gc, (uint32_t)iter));
         }
       }
     }
@@ -622,7 +673,7 @@ __device__ void group_accept_store(const DevProblem &pb, const DevState &st, con
       v = k == 0 ? fs.value[0] : k == 1 ? fs.value[1] : k == 2 ? (double)fs.flags[1] : k < 3 + P ? fs.pp[k - 3] : fs.mom[k - 3 - P];
       la[k] = v;
     } else {
-      v = __ldcg(la + k);
+      v = pre ? pre->la[(k - tid) >> 5] : __ldcg(la + k);
     }
     pub[k] = v;
     if (fused) {
@@ -635,6 +686,16 @@ __device__ void group_accept_store(const DevProblem &pb, const DevState &st, con
     }
   }
   gsync(g);
+  if (flow && tid == 0) {
+    // everything this group stored (ordered before this thread by the group sync) becomes visible before the tag
+    if (pb.world > 1) {
+      __threadfence_system();
+      for (int r = 0; r < pb.world; ++r) st_release_sys_u64(done_tags(pb, st.peer_val_all[r]) + gc, (unsigned long long)iter);
+    } else {
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(done_tags(pb, st.val_all) + gc), "l"((unsigned long long)iter)
+                   : "memory");
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -808,7 +869,6 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
   return *(const volatile unsigned long long *)p;
 }
 
-constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;  // 4 s: a stuck peer becomes an error, not a hang
 
 // Grid barrier (CTA 0 is the master).  Arrivals are release-adds (each CTA's writes become visible before its
 // arrival); the master waits for all of them, fences once (acquire for its own reads + release for the store
@@ -917,13 +977,33 @@ __device__ __forceinline__ void prefetch_schedule(const DevState &st, int pit, i
   if (threadIdx.x == 0) *nlev_out = st.sched_nlev[sidx];
 }
 
+// swap_ev_ij! for the chains this CTA owns, one warp per chain, from the replayed outcome in shared memory
+__device__ void persistent_exchange_apply(const DevProblem &pb, const DevState &st, int pit, bool fused,
+                                          const unsigned short *own, const unsigned short *exch, bool flow) {
+  const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
+  const int N = pb.N, L = pb.L, R = rec_len(pb.P, pb.M);
+  const double *la_all = st.la_all + (size_t)(fused ? (pit & 1) : 0) * N * R;
+  const int warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int c = b + warp * G; c < L; c += nwarps * G) {  // one warp per owned chain
+    const int gc = pb.chain0 + c;
+    const int partner = exch[gc];
+    if (partner != 0) {
+      exchange_apply_chain(pb, st, pit, c, partner, la_all + (size_t)own[gc] * R, tid & 31);
+      if (flow) {  // tell the CTA that will finish this chain's next evaluation that its state is up to date
+        __syncwarp();
+        if ((tid & 31) == 0) st_release_gpu(st.applied + c, (unsigned)pit);
+      }
+    }
+  }
+}
+
 // exchange of iteration `pit` for the chains this CTA owns.  The pair loop is replicated in every owner CTA
 // on the prefetched schedule: only the N values come from L2 here; one warp walks the levels (a __syncwarp
 // per level), then one warp per owned chain applies the outcome.
 // dynamic smem (persistent kernel): val[N] f64 | own[N] exch[N] u16 | sij | soff
 __device__ void persistent_exchange(const DevProblem &pb, const DevState &st, int pit, bool fused, double *val,
                                     unsigned short *own, unsigned short *exch, const unsigned *sij, const int *soff,
-                                    int nlev) {
+                                    int nlev, bool flow = false, bool apply = true, const double *min_improve = nullptr) {
   const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
   const int N = pb.N, L = pb.L, R = rec_len(pb.P, pb.M);
   const int par = fused ? (pit & 1) : 0;
@@ -942,7 +1022,8 @@ __device__ void persistent_exchange(const DevProblem &pb, const DevState &st, in
       for (int t = lo + tid; t < hi; t += 32) {
         const int i = (int)(sij[t] & 0xffffu), j = (int)(sij[t] >> 16);
         const double vi = val[i], vj = val[j];
-        if (__dsub_rn(vi, vj) > pb.min_improve[i]) {  // dist_fun(evi.value, evj.value) > min_improve[i]
+        const double thr = min_improve ? min_improve[i] : pb.min_improve[i];  // shared copy: no global load per level
+        if (__dsub_rn(vi, vj) > thr) {  // dist_fun(evi.value, evj.value) > min_improve[i]
           val[i] = vj;
           val[j] = vi;
           const unsigned short oi = own[i];
@@ -958,13 +1039,54 @@ __device__ void persistent_exchange(const DevProblem &pb, const DevState &st, in
     if (b == 0 && pb.chain0 == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
   }
   __syncthreads();
-  const int warp = tid >> 5, nwarps = blockDim.x >> 5;
-  for (int c = b + warp * G; c < L; c += nwarps * G) {  // one warp per owned chain
-    const int gc = pb.chain0 + c;
-    const int partner = exch[gc];
-    if (partner != 0) exchange_apply_chain(pb, st, pit, c, partner, la_all + (size_t)own[gc] * R, tid & 31);
-  }
+  if (!apply) return;
+  persistent_exchange_apply(pb, st, pit, fused, own, exch, flow);
   __syncthreads();
+}
+
+// Barrier-free hand-over between iterations: every CTA waits until all N chains (of every rank) carry the completion
+// tag of iteration `target` -- written by the warp that finished the chain, after its trace row, records and state.
+// The acquire loads plus the CTA barrier make those writes visible to the whole CTA.
+__device__ bool wait_all_done(const DevProblem &pb, const DevState &st, int target) {
+  __shared__ int s_bad[2];
+  const unsigned long long *tags = done_tags(pb, st.val_all);
+  const unsigned long long want = (unsigned long long)target;
+  const unsigned long long t0 = gtimer();
+  unsigned spins = 0;
+  if (threadIdx.x == 0) s_bad[0] = s_bad[1] = 0;
+  __syncthreads();
+  for (;;) {
+    // relaxed polls (no L1 invalidation per poll); one acquire fence once every tag has arrived
+    bool ok = true;
+    for (int i = threadIdx.x; i < pb.N; i += blockDim.x) {
+      unsigned long long v;
+      if (pb.world > 1)
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(tags + i) : "memory");
+      else
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(tags + i) : "memory");
+      ok = ok && v >= want;
+    }
+    ++spins;
+    if (threadIdx.x == 0 && (spins & 15u) == 0) {
+      int bad = 0;
+      if (ld_relaxed_gpu(&st.bar->gen) & 0x80000000u) bad = 1;  // another CTA gave up
+      if (gtimer() - t0 > kSpinTimeoutNs) {
+        atomicOr(st.err, kErrTimeout);
+        atomicOr(&st.bar->gen, 0x80000000u);
+        bad = 1;
+      }
+      s_bad[spins & 1u] = bad;
+    }
+    const int all_ok = __syncthreads_and(ok);
+    if (s_bad[spins & 1u]) return false;
+    if (all_ok) break;
+  }
+  if (pb.world > 1)
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+  else
+    fence_acq_rel_gpu();
+  __syncthreads();
+  return true;
 }
 
 // One warp completes segment s of its CTA: publish the CTA's exact partial sums; if this was the last CTA of
@@ -972,16 +1094,27 @@ __device__ void persistent_exchange(const DevProblem &pb, const DevState &st, in
 // the other 31 warps keep simulating.
 __device__ void warp_publish_segment(const DevProblem &pb, const DevState &st, PersistSmem &sm, int s, int it,
                                      bool fused, int part_len, int max_seg, const unsigned long long *acc,
-                                     double *pp_seg, double *fscratch, int fs_len) {
+                                     double *pp_seg, double *fscratch, int fs_len, bool flow = false,
+                                     const unsigned short *exch = nullptr) {
   const int lane = threadIdx.x & 31, D = pb.P;
   const int c = sm.seg_c[s];
   double *part_base = st.partials + (size_t)c * max_seg * part_len;
   unsigned long long *part = (unsigned long long *)(part_base + (size_t)sm.seg_slot[s] * part_len);
   for (int e = lane; e < 2 * D; e += 32) part[e] = acc[(size_t)s * 2 * D + e];
+  // The chain state the finishing warp will need is requested NOW: the release half of the arrival atomic waits for
+  // these loads together with the partial stores, instead of a second and third L2 round trip after it.  (Whether
+  // this CTA is the chain's last is not known yet; the few wasted loads of the others cost nothing.)
+  const Grp gw{lane, 32, 0};
+  const int gc = pb.chain0 + c;
+  const unsigned long long t_pub = st.phase_ts ? gtimer() : 0ull;  // debug: when this warp started publishing
+  AcceptPre pre;
+  if (flow && exch && exch[gc] != 0) wait_exchange_applied(st, gw, c, it);
+  accept_prefetch(pb, st, lane, c, gc, it, pre);
   __syncwarp();
   int last = 0;
   if (lane == 0) {
     const unsigned prev = atom_acq_rel_gpu(st.arrive + c, 1u);  // releases the warp's partial, acquires the others'
+    pre.u_acc = smm_acc_uniform(pb.seed_algo, (uint32_t)gc, (uint32_t)it);  // pure arithmetic while the atomic travels
     last = (prev == (unsigned)(sm.seg_nseg[s] - 1));
     if (last) st_relaxed_gpu(st.arrive + c, 0u);  // re-arm (ordered before the next iteration by the grid barrier)
   }
@@ -989,14 +1122,22 @@ __device__ void warp_publish_segment(const DevProblem &pb, const DevState &st, P
   if (!last) return;
   double *f = fscratch + (size_t)s * fs_len;
   const FinScratch fs{pp_seg + (size_t)s * D, f, f + 2 * D, f + 2 * D + pb.M, (int *)(f + 2 * D + pb.M + 2)};
-  const Grp gw{lane, 32, 0};
+  if (st.phase_ts && lane == 0) st.phase_ts[(size_t)((blockIdx.x * 2 + (it & 1)) * 2 + 1) * 4 + 2] = t_pub;
   group_finalize(pb, gw, fs, part_base, sm.seg_nseg[s], part_len);
-  group_accept_store(pb, st, gw, fs, c, pb.chain0 + c, it, fused);
+  group_accept_store(pb, st, gw, fs, c, gc, it, fused, flow, false, &pre);
+  if (st.phase_ts && lane == 0) st.phase_ts[(size_t)((blockIdx.x * 2 + (it & 1)) * 2 + 1) * 4 + 3] = gtimer();
 }
 
 // dynamic smem: val[N] (double) own[N] exch[N] (u16) | pp_seg[n][D] | acc[n][2D] (u64) | fscratch[n][2D+M+4] |
-//               cand[kPropCand] (proposal candidates) | zq[32 warps][kZigQWords] (u32: deferred ziggurat draws) |
+//               cand[kPropCand] (proposal candidates) | mi[N] | zq[32 warps][kZigQWords] (u32: deferred ziggurat draws) |
 //               okf[kPropCand] (u8)
+// kFlow = false (exchange_mode 1): two grid barriers per iteration, proposals by the CTA that owns the chain.
+// kFlow = true  (exchange_mode 2): no grid barrier at all.  A CTA waits until every chain carries the completion tag of
+//   the previous iteration, replays the exchange, computes the proposals of the chains IT simulates (from the gathered
+//   records; a chain shared by several CTAs is proposed redundantly, attempts are counter-indexed), simulates, and the
+//   warp finishing a chain publishes the chain's tag.  Owners apply the exchange to their chains' state off the critical
+//   path and raise applied[c], which the finishing warp checks before it reads that state ~50 us later.
+template <bool kFlow>
 __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevProblem pb, DevState st, int iter0,
                                                                             int n_iters, int sched_iter0, int n_s,
                                                                             int part_len, int max_seg, int cta_seg) {
@@ -1006,7 +1147,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
   const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
   const int lane = tid & 31;
   const int N = pb.N, L = pb.L, P = pb.P, D = pb.P, S = pb.S;
-  const bool fused = pb.world > 1;
+  const bool fused = kFlow || pb.world > 1;  // records double-buffered by iteration parity in la_all / val_all
   double *val = smem_d;
   unsigned short *own = (unsigned short *)(val + N), *exch = own + N;
   const int fs_len = 2 * D + pb.M + 4;
@@ -1016,8 +1157,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
   unsigned long long *acc = (unsigned long long *)(pp_seg + (size_t)cta_seg * D);
   double *fscratch = (double *)(acc + (size_t)cta_seg * 2 * D);
   double *cand = fscratch + (size_t)cta_seg * fs_len;                      // [kPropCand] proposal candidates
-  uint32_t *zq = (uint32_t *)(cand + kPropCand) + (size_t)(tid >> 5) * kZigQWords;
-  unsigned char *okf = (unsigned char *)((uint32_t *)(cand + kPropCand) + (kPersistThreads / 32) * kZigQWords);  // [kPropCand]
+  double *mi = cand + kPropCand;                                           // [N] min_improve (read in the pair loop)
+  uint32_t *zq = (uint32_t *)(mi + N) + (size_t)(tid >> 5) * kZigQWords;
+  unsigned char *okf = (unsigned char *)((uint32_t *)(mi + N) + (kPersistThreads / 32) * kZigQWords);  // [kPropCand]
+  for (int i = tid; i < N; i += kPersistThreads) mi[i] = pb.min_improve[i];
   load_logtab(sm.logtab);
   load_zigtab(s_zigtab);
   unsigned gen = ld_volatile_u32(&st.bar->gen) & 0x7fffffffu;
@@ -1058,8 +1201,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
   const int static_units = (int)(((long long)total_units * kStaticNum / kStaticDen) / (kPersistThreads / 32));
   const int n_owned = b < L ? (L - b + G - 1) / G : 0;  // chains b, b + G, ...
   // proposal groups: as many threads per chain as the CTA can spare (more attempts per round)
+  const int n_prop = kFlow ? n_seg : n_owned;  // chains this CTA computes proposals for
   int ngroups = 1;
-  while (ngroups < n_owned && ngroups < kPGroups) ngroups <<= 1;
+  while (ngroups < n_prop && ngroups < kPGroups) ngroups <<= 1;
   const int gsize = kPersistThreads / ngroups;
   const int gi = tid / gsize;
   const Grp gprop{tid - gi * gsize, gsize, 1 + gi};
@@ -1071,9 +1215,32 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
   const bool all_on = rows * D == 32;
 
   for (int it = iter0; it < iter0 + n_iters; ++it) {
+    bool have_ex = false;
+    if (kFlow) {
+      // ---- wait for iteration it-1 of every chain, replay its exchange, propose for the chains simulated here ----
+      if (it > iter0 && !wait_all_done(pb, st, it - 1)) return;
+      PHASE_STAMP((b * 2 + (it & 1)) * 2, 3);
+      have_ex = N > 1 && it - 1 >= 2 && it > iter0;
+      if (have_ex && (n_owned > 0 || n_seg > 0))
+        persistent_exchange(pb, st, it - 1, true, val, own, exch, sij, soff, sm.nlev, true, false, mi);  // replay only
+      PHASE_STAMP((b * 2 + (it & 1)) * 2 + 1, 0);  // exchange done
+      const double *la_prev = st.la_all + (size_t)((it - 1) & 1) * N * rec_len(P, pb.M);
+      for (int r = 0; r * ngroups < n_seg; ++r) {
+        const int sidx = r * ngroups + gi;
+        if (sidx < n_seg) {
+          const int c = sm.seg_c[sidx], gc = pb.chain0 + c;
+          // centre: the record that sits on this chain after the exchange (its own last accepted one if not swapped)
+          const double *centre = have_ex ? la_prev + (size_t)own[gc] * rec_len(P, pb.M) : nullptr;
+          group_proposal(pb, st, gprop, ps, c, gc, it, sm.seg_slot[sidx] == 0, centre);
+          for (int q = gprop.tid; q < P; q += gsize) pp_seg[(size_t)sidx * D + q] = ps.pp[q];
+        }
+      }
+      PHASE_STAMP((b * 2 + (it & 1)) * 2 + 1, 1);  // proposals done (group 0)
+    }
     // ---- exchange of iteration it-1 (AlgoBGP.jl:637), then this iteration's proposals ----
-    if (n_owned > 0) {
-      if (N > 1 && it - 1 >= 2 && it > iter0) persistent_exchange(pb, st, it - 1, fused, val, own, exch, sij, soff, sm.nlev);
+    if (!kFlow && n_owned > 0) {
+      if (N > 1 && it - 1 >= 2 && it > iter0)
+        persistent_exchange(pb, st, it - 1, fused, val, own, exch, sij, soff, sm.nlev, false, true, mi);
       PHASE_STAMP((b * 2 + (it & 1)) * 2 + 1, 0);  // exchange done
       for (int r = 0; r * ngroups < n_owned; ++r) {
         const int o = r * ngroups + gi;  // index among the owned chains
@@ -1084,16 +1251,19 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
         }
       }
     }
-    PHASE_STAMP((b * 2 + (it & 1)) * 2 + 1, 1);  // proposals done (group 0)
-    if (!grid_barrier(pb, st, gen, false, seq)) return;
+    if (!kFlow) {
+      PHASE_STAMP((b * 2 + (it & 1)) * 2 + 1, 1);  // proposals done (group 0)
+      if (!grid_barrier(pb, st, gen, false, seq)) return;
+    }
 
     // ---- phase A: this CTA's share of the flattened (chain, Philox block) space as a warp-level work queue ----
     PHASE_STAMP((b * 2 + (it & 1)) * 2, 0);
-    for (int e = tid; e < n_seg * D; e += kPersistThreads) pp_seg[e] = __ldcg(st.pp + (size_t)sm.seg_c[e / D] * P + e % D);
+    if (!kFlow)
+      for (int e = tid; e < n_seg * D; e += kPersistThreads) pp_seg[e] = __ldcg(st.pp + (size_t)sm.seg_c[e / D] * P + e % D);
     for (int e = tid; e < n_seg * 2 * D; e += kPersistThreads) acc[e] = 0ull;
     if (tid < n_seg) sm.done[tid] = 0;
     if (tid == 0) sm.next_unit = static_units * (kPersistThreads / 32);
-    if (n_owned > 0 && N > 1 && it >= 2) prefetch_schedule(st, it, sched_iter0, n_s, sij, soff, &sm.nlev);
+    if ((n_owned > 0 || (kFlow && n_seg > 0)) && N > 1 && it >= 2) prefetch_schedule(st, it, sched_iter0, n_s, sij, soff, &sm.nlev);
     __syncthreads();
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
     {
@@ -1102,6 +1272,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       uint32_t c2 = 0u, c3 = c3base;
       double p = 0.0;
       Acc a{0ull, 0ull};
+      // barrier-free mode: the owner's part of the exchange (trace slot, state of the swapped chains) is off the
+      // critical path -- its warps do it here, before their first units; finishers wait on applied[c] much later
+      if (kFlow && have_ex && n_owned > 0) persistent_exchange_apply(pb, st, it - 1, true, own, exch, true);
       ZigCtx cx = zig_ctx(s_zigtab, zq, S);
       cx.D = D;
       const uint32_t pp_seg_s = smem_addr(pp_seg), acc_s = smem_addr(acc);
@@ -1156,7 +1329,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
             }
             complete = __shfl_sync(0xffffffffu, complete, 0);
             if (complete)
-              warp_publish_segment(pb, st, sm, cur, it, fused, part_len, max_seg, acc, pp_seg, fscratch, fs_len);
+              warp_publish_segment(pb, st, sm, cur, it, fused, part_len, max_seg, acc, pp_seg, fscratch, fs_len, kFlow,
+                                   have_ex ? exch : nullptr);
           }
           cur = s;
           if (s >= 0) {
@@ -1211,13 +1385,17 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
     PHASE_STAMP((b * 2 + (it & 1)) * 2, 1);  // warp 0 left the work loop
     __syncthreads();
     PHASE_STAMP((b * 2 + (it & 1)) * 2, 2);  // every warp of the CTA done (incl. chain finalisation)
-    if (!grid_barrier(pb, st, gen, fused, seq)) return;
-    PHASE_STAMP((b * 2 + (it & 1)) * 2, 3);
+    if (!kFlow) {
+      if (!grid_barrier(pb, st, gen, fused, seq)) return;
+      PHASE_STAMP((b * 2 + (it & 1)) * 2, 3);
+    }
   }
   // ---- exchange of the last iteration of this launch ----
   const int pit = iter0 + n_iters - 1;
-  if (n_owned > 0 && N > 1 && pit >= 2) persistent_exchange(pb, st, pit, fused, val, own, exch, sij, soff, sm.nlev);
-  if (b == 0 && tid == 0) *st.sync_seq = seq;
+  if (kFlow && n_owned > 0 && !wait_all_done(pb, st, pit)) return;
+  if (n_owned > 0 && N > 1 && pit >= 2)
+    persistent_exchange(pb, st, pit, fused, val, own, exch, sij, soff, sm.nlev, false, true, mi);
+  if (!kFlow && b == 0 && tid == 0) *st.sync_seq = seq;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1522,7 +1700,7 @@ size_t exch_smem_bytes(int N) { return sizeof(double) * (size_t)N + sizeof(unsig
 size_t persist_smem_bytes(int N, int D, int M, int cta_seg) {
   const int n_s = N < 3 ? (N > 1 ? N - 1 : 0) : N;
   return sizeof(double) * ((size_t)N + (N + 1) / 2 + (n_s + 1) + (size_t)cta_seg * (D + 2 * D + 2 * D + M + 4)) +
-         sizeof(double) * kPropCand + sizeof(uint32_t) * (size_t)(kPersistThreads / 32) * kZigQWords + kPropCand;
+         sizeof(double) * ((size_t)kPropCand + N) + sizeof(uint32_t) * (size_t)(kPersistThreads / 32) * kZigQWords + kPropCand;
 }
 
 cudaError_t configure_kernels(int N, int n_s) {
@@ -1534,7 +1712,10 @@ cudaError_t configure_kernels(int N, int n_s) {
   return cudaSuccess;
 }
 cudaError_t configure_persistent(int N, int D, int M, int cta_seg) {
-  return cudaFuncSetAttribute(bgp_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(bgp_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)persist_smem_bytes(N, D, M, cta_seg));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(bgp_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)persist_smem_bytes(N, D, M, cta_seg));
 }
 
@@ -1545,9 +1726,12 @@ int eval_max_blocks_per_sm() {
 }
 int persistent_max_blocks_per_sm(int N, int D, int M, int cta_seg) {
   int n = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bgp_persistent_kernel, kPersistThreads,
+  int m = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, bgp_persistent_kernel<false>, kPersistThreads,
                                                 persist_smem_bytes(N, D, M, cta_seg));
-  return n;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, bgp_persistent_kernel<true>, kPersistThreads,
+                                                persist_smem_bytes(N, D, M, cta_seg));
+  return n < m ? n : m;
 }
 int persistent_unit_blocks(int D) { return (32 / D) * kUnitSteps; }
 int persistent_max_cta_seg() { return kMaxCtaSeg; }
@@ -1563,11 +1747,12 @@ void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sch
   bgp_exchange_kernel<<<1, kExchThreads, exch_smem_bytes(pb.N), s>>>(pb, st, iter, sched_idx, n_s);
 }
 cudaError_t launch_persistent(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int sched_iter0,
-                              int n_s, int part_len, int max_seg, int cta_seg, int grid, cudaStream_t s) {
+                              int n_s, int part_len, int max_seg, int cta_seg, int grid, bool flow, cudaStream_t s) {
   DevProblem pbc = pb;
   DevState stc = st;
   void *args[] = {&pbc, &stc, &iter0, &n_iters, &sched_iter0, &n_s, &part_len, &max_seg, &cta_seg};
-  return cudaLaunchCooperativeKernel((void *)bgp_persistent_kernel, dim3(grid), dim3(kPersistThreads), args,
+  void *fn = flow ? (void *)bgp_persistent_kernel<true> : (void *)bgp_persistent_kernel<false>;
+  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args,
                                      persist_smem_bytes(pb.N, pb.P, pb.M, cta_seg), s);
 }
 void launch_objective(const DevProblem &pb, const double *params, int B, int noseed, uint32_t rep0, int n_split,

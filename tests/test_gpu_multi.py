@@ -54,7 +54,7 @@ def _worker(rank, world, port, n_chains, n_iter, mode, q, kind="mvnormal", data_
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_two_gpus_match_the_oracle(smm, oracle, mode):
     from smm_jl_b200 import configs
     if smm.device_count() < 2:

@@ -38,3 +38,11 @@ with _lib.BGPHandle(cfg) as h:
         print("last: warp0 out of units us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 0, 1])))
         print("last: CTA all warps done us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 0, 2])))
         print("last: B2 exit            us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 0, 3])))
+        fin = prev[:, 1, 3] > 0
+        for nm, arr in (("prev", prev), ("last", cur)):
+            done = arr[:, 0, 2].astype(float)
+            order = np.argsort(-done)[:6]
+            print(nm, "slowest CTAs (all warps done):", [(int(b), round(float(f(done[b])) - (0 if nm == "prev" else float(f(np.median(cur[:, 0, 0])))), 1)) for b in order])
+        print("prev: last finish: publish start us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[fin, 1, 2])))
+        print("prev: last finish: tag published us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[fin, 1, 3])))
+        print("prev: last finish: duration      us: min %.1f med %.1f p90 %.1f max %.1f" % pct((prev[fin, 1, 3] - prev[fin, 1, 2]) / 1e3))
