@@ -183,7 +183,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--n-split", type=int, default=0)
-    ap.add_argument("--exchange-mode", type=int, default=1, help="0 = one launch per iteration (+NCCL), 1 = persistent kernel (+fused peer all-gather)")
+    ap.add_argument("--exchange-mode", type=int, default=-1,
+                    help="0 = one launch per iteration (+NCCL), 1 = persistent kernel with grid barriers (+fused peer "
+                         "all-gather), 2 = barrier-free persistent kernel (per-chain completion tags); default: 2 on "
+                         "one GPU, 1 on several (one system-scope flag exchange per iteration instead of one per chain)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -199,6 +202,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.exchange_mode < 0:
+        args.exchange_mode = 2 if world == 1 else 1
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
@@ -288,7 +293,7 @@ def main():
     achieved = bytes_per_launch / (eval_ms * 1e-3) / 1e9     # GB/s
     traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp) and args.exchange_mode == 1:
+    if os.path.exists(tp) and args.exchange_mode >= 1:
         try:
             with open(tp) as f:
                 traffic = json.load(f)["bgp_persistent_kernel_dram_bytes_per_iteration"] * iters_per_launch
@@ -301,8 +306,9 @@ def main():
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel_share_of_step": kt["eval"][0] / max(sum(kt[k][0] for k in ("eval", "exchange", "pairs", "allgather")), 1e-12),
                 "other_kernels_ms": {k: (kt[k][0] / kt[k][1] if kt[k][1] else None) for k in ("exchange", "pairs", "allgather")},
-                "note": "path is instruction-bound (Philox + fp64 Box-Muller), not HBM-bound: B_alg counts the reference's "
-                        "draw matrix which the fused kernel never materialises (DESIGN.md)"}
+                "note": "path is instruction-bound (Philox4x32-10: 20 IMAD.WIDE at 4.2 cycles per warp each + the ALU pipe), "
+                        "not HBM-bound: B_alg counts the reference's draw matrix which the fused kernel never "
+                        "materialises (DESIGN.md)"}
 
     # ---- end to end through the public API: MAlgoBGP / computeNextIteration! with host buffers ---
     barrier()
@@ -389,7 +395,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(world), "n_chains": n_chains, "chains_per_gpu": L, "n_params": N_PARAMS,
                        "n_moments": N_MOMENTS, "n_sim": N_SIM, "objective": "norm_mv (means + variances)",
-                       "parallelism": f"chains sharded over {world} GPU(s)" + ((", all-gather fused into the persistent kernel (peer stores over NVLink)" if args.exchange_mode else ", ncclAllGather per iteration") if world > 1 else ""),
+                       "parallelism": f"chains sharded over {world} GPU(s)" + (({0: ", ncclAllGather per iteration", 1: ", all-gather fused into the persistent kernel (peer stores over NVLink + one flag exchange inside the grid barrier)", 2: ", all-gather fused into the barrier-free persistent kernel (records, values and completion tags stored to every peer over NVLink)"}[args.exchange_mode]) if world > 1 else ""),
                        "exchange_mode": args.exchange_mode,
                        "l2": "no input is re-read between iterations: every draw is generated in registers; the only "
                              "carried data is the chains' own state (~60 KB), which the algorithm's data dependence requires",

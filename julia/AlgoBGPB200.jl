@@ -107,7 +107,7 @@ mutable struct MAlgoBGPB200 <: MAlgo
                 N, n, pointer(sigma0), pointer(tuners), pointer(minimp),
                 get(opts, "sigma_update_steps", 10), get(opts, "sigma_adjust_by", 0.01), get(opts, "smpl_iters", 1000),
                 get(opts, "batch_size", np), UInt64(get(opts, "seed", 20261017)),
-                get(opts, "device", 0), 1, 0, ntuple(_ -> 0x00, 128), get(opts, "exchange_mode", 1), 0)
+                get(opts, "device", 0), 1, 0, ntuple(_ -> 0x00, 128), get(opts, "exchange_mode", 2), 0)
             smm_check(ccall((:smm_bgp_create, LIBSMM_B200), Cint, (Ref{SmmBgpConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         end
         # the chain objects the rest of the package (summary, history, plotting) reads; probs_acc is the Uacc stream

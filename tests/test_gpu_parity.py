@@ -49,7 +49,7 @@ def test_deferred_ziggurat_matches_sequential_definition(smm, oracle, n_sim):
                 v, m, st = h.eval_batch(p, noseed=noseed, rep0=5)
             vo, mo, so = oracle.eval_batch(cfg, p, noseed=noseed, rep0=5, n_threads=4)
             np.testing.assert_array_equal(st, so)
-            # the fixed-point grids (2^-43 for x, 2^-37 for x^2) bound the absolute error of a moment; a sample variance
+            # the fixed-point grids (2^-42 for x, 2^-36 for x^2 at these shapes) bound the absolute error of a moment; a sample variance
             # of two or three draws can be tiny, so the bound is absolute here (north star: 1e-6 relative)
             np.testing.assert_allclose(m, mo, rtol=1e-9, atol=1e-9)
             np.testing.assert_allclose(v, vo, rtol=1e-7, atol=1e-9)
