@@ -9,7 +9,7 @@
 namespace smm {
 
 constexpr int kEvalThreads = 128;   // CTA size of the evaluation kernel (multi-launch mode)
-constexpr int kPersistThreads = 1024;  // CTA size of the persistent kernel: one CTA per SM
+constexpr int kPersistThreads = 768;   // CTA size of the persistent kernel: one CTA per SM (24 warps, 80 registers)
 constexpr int kExchThreads = 512;   // CTA size of the stand-alone exchange kernel
 constexpr int kPairThreads = 256;   // CTA size of the pair-schedule kernel
 constexpr int kMaxSplit = 64;       // CTAs cooperating on one evaluation (multi-launch mode)

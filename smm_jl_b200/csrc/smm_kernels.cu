@@ -1287,7 +1287,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
           int start = 0, g = 0;
           if (lane == 0) {
             const int rem = total_units - *(volatile int *)&sm.next_unit;
-            g = rem > 64 * kMaxGrab ? kMaxGrab : (rem > 64 ? rem >> 6 : 1);
+            constexpr int kTwice = 2 * (kPersistThreads / 32);  // grab = what is left / two warps-worth per warp
+            g = rem > kTwice * kMaxGrab ? kMaxGrab : (rem > kTwice ? rem / kTwice : 1);
             start = atomicAdd(&sm.next_unit, g);
           }
           start = __shfl_sync(0xffffffffu, start, 0);
@@ -1630,7 +1631,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) barrier_bench_kernel(DevPr
 
 // the simulate inner loop alone (add_pair with the handle's keys and accumulators), static or dynamic unit
 // distribution, any CTA size: the ceiling the evaluation kernels are measured against
-__global__ void __launch_bounds__(1024) sim_throughput_kernel(DevProblem pb, int n_per_thread, int dyn, double *out) {
+// kBound: the launch bound the variant is compiled for (1024 -> 64 registers per thread, 768 -> 80, 512 -> 128), to
+// measure what the register budget of the persistent kernel's CTA shape costs
+template <int kBound>
+__global__ void __launch_bounds__(kBound) sim_throughput_kernel(DevProblem pb, int n_per_thread, int dyn, double *out) {
   __shared__ uint4 ztab[kZigBufEntries];
   extern __shared__ uint32_t zq[];  // [blockDim.x / 32][kZigQWords]
   __shared__ unsigned long long fix[2 * SMM_MAX_PARAMS];
@@ -1778,8 +1782,17 @@ cudaError_t launch_barrier_bench(const DevProblem &pb, const DevState &st, int v
 void launch_sim_throughput(const DevProblem &pb, int n_per_thread, int blocks, int threads, int dyn, double *out,
                            cudaStream_t s) {
   const size_t dyn_smem = sizeof(uint32_t) * (threads / 32) * kZigQWords;
-  cudaFuncSetAttribute(sim_throughput_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
-  sim_throughput_kernel<<<blocks, threads, dyn_smem, s>>>(pb, n_per_thread, dyn, out);
+  // dyn: 0 = static split, 1 = unit queue; +2 = the variant compiled for the smallest launch bound >= threads
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    kern<<<blocks, threads, dyn_smem, s>>>(pb, n_per_thread, dyn & 1, out);
+  };
+  if ((dyn & 2) && threads <= 512)
+    go(sim_throughput_kernel<512>);
+  else if ((dyn & 2) && threads <= 768)
+    go(sim_throughput_kernel<768>);
+  else
+    go(sim_throughput_kernel<1024>);
 }
 
 }  // namespace smm
