@@ -563,7 +563,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   st.phase_ts = nullptr;
   if (getenv("SMM_PHASE_TS")) {
     size_t slots = (size_t)L * h->n_split;
-    if ((size_t)h->grid * 4 > slots) slots = (size_t)h->grid * 4;
+    if ((size_t)h->grid * 4 + L > slots) slots = (size_t)h->grid * 4 + L;
     if (int rc = fill(h->phase_ts, slots * 4, 0ull)) return rc;
     st.phase_ts = h->phase_ts.p;
   }
@@ -1123,7 +1123,8 @@ int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij, int32_t *level_offset
 int smm_debug_phase_ts(smm_bgp *h, uint64_t *out, int64_t n) {
   if (!h || !out) return fail(SMM_E_ARG, "null argument");
   if (!h->st.phase_ts) return fail(SMM_E_STATE, "set SMM_PHASE_TS=1 before smm_bgp_create");
-  const int64_t blocks = h->mode >= 1 ? (int64_t)h->grid * 4 : (int64_t)h->L * h->n_split;
+  // persistent modes: 4 rows per CTA, then one row per local chain {publish start, tag time, finishing CTA, iteration}
+  const int64_t blocks = h->mode >= 1 ? (int64_t)h->grid * 4 + h->L : (int64_t)h->L * h->n_split;
   const int64_t have = blocks * 4;
   CUDA_TRY(cudaMemcpy(out, h->st.phase_ts, sizeof(uint64_t) * (n < have ? n : have), cudaMemcpyDeviceToHost));
   return (int)blocks;

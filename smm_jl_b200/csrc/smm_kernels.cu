@@ -106,7 +106,7 @@ constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;  // 4 s: a stuck pe
 
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");  // "memory": stays on its side of barriers
   return t;
 }
 #define PHASE_STAMP(slot, i)                                                                  \
@@ -1125,7 +1125,14 @@ __device__ void warp_publish_segment(const DevProblem &pb, const DevState &st, P
   if (st.phase_ts && lane == 0) st.phase_ts[(size_t)((blockIdx.x * 2 + (it & 1)) * 2 + 1) * 4 + 2] = t_pub;
   group_finalize(pb, gw, fs, part_base, sm.seg_nseg[s], part_len);
   group_accept_store(pb, st, gw, fs, c, gc, it, fused, flow, false, &pre);
-  if (st.phase_ts && lane == 0) st.phase_ts[(size_t)((blockIdx.x * 2 + (it & 1)) * 2 + 1) * 4 + 3] = gtimer();
+  if (st.phase_ts && lane == 0) {
+    st.phase_ts[(size_t)((blockIdx.x * 2 + (it & 1)) * 2 + 1) * 4 + 3] = gtimer();
+    unsigned long long *row = st.phase_ts + ((size_t)gridDim.x * 4 + c) * 4;  // per-chain row of the debug buffer
+    row[0] = t_pub;
+    row[1] = gtimer();
+    row[2] = blockIdx.x;
+    row[3] = (unsigned long long)it;
+  }
 }
 
 // dynamic smem: val[N] (double) own[N] exch[N] (u16) | pp_seg[n][D] | acc[n][2D] (u64) | fscratch[n][2D+M+4] |

@@ -22,7 +22,10 @@ with _lib.BGPHandle(cfg) as h:
     else:
         ms = h.step(100)
         print("us/iter", ms * 10)
-        ts = h.phase_ts().astype(np.int64).reshape(-1, 2, 2, 4)     # [block][parity][half][stamp]
+        raw = h.phase_ts().astype(np.int64)
+        nchain = chains
+        per_chain = raw[-nchain:]                                    # {publish start, tag time, finishing CTA, iteration}
+        ts = raw[:-nchain].reshape(-1, 2, 2, 4)                      # [block][parity][half][stamp]
         last_par = h.iteration & 1
         cur, prev = ts[:, last_par], ts[:, 1 - last_par]
         t0 = prev[:, 0, 0].min()
@@ -46,3 +49,17 @@ with _lib.BGPHandle(cfg) as h:
         print("prev: last finish: publish start us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[fin, 1, 2])))
         print("prev: last finish: tag published us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(prev[fin, 1, 3])))
         print("prev: last finish: duration      us: min %.1f med %.1f p90 %.1f max %.1f" % pct((prev[fin, 1, 3] - prev[fin, 1, 2]) / 1e3))
+
+        # the last iteration, chain by chain: who finished it, when, relative to that CTA's own timeline
+        tA = np.median(cur[:, 0, 0])
+        fb = per_chain[:, 2]
+        rel = lambda a: (a - tA) / 1e3
+        order = np.argsort(-per_chain[:, 1])[:12]
+        print("last iteration: latest chains (chain, finishing CTA, publish start, tag, that CTA: warp0 out / all warps done):")
+        for c in order:
+            b = int(fb[c])
+            print("  chain %3d cta %3d  pub %.1f tag %.1f | cta warp0-out %.1f all-done %.1f  (iter %d)" % (
+                c, b, rel(per_chain[c, 0]), rel(per_chain[c, 1]), rel(cur[b, 0, 1]), rel(cur[b, 0, 2]), per_chain[c, 3]))
+        print("tags: med %.1f p90 %.1f max %.1f" % tuple(np.percentile(rel(per_chain[:, 1]), [50, 90, 100])))
+        cnt = np.bincount(fb, minlength=cur.shape[0])
+        print("chains finished per CTA: ", np.bincount(cnt))
