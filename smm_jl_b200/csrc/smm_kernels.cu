@@ -1289,8 +1289,53 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       // Guided self-scheduling of what the static shares leave: a warp takes (remaining / 2 warps-worth, at most
       // kMaxGrab, at least 1) consecutive units from the CTA's queue.
       int u = (tid >> 5) * static_units, uend = u + static_units;  // this warp's fixed share comes first
+      // Leaving a segment: add this warp's exact sums to the CTA's, count its units; true if that completed the
+      // CTA's part of the chain.  (A warp may leave and re-enter a segment: the accounting is additive.)
+      auto leave_segment = [&](int seg) -> bool {
+        zig_flush(cx, qn, pb.magic_sum, pb.magic_sq);
+        for (int r = 1; r < rows; ++r) {
+          const unsigned long long os = __shfl_down_sync(0xffffffffu, a.sum, r * D);
+          const unsigned long long oq = __shfl_down_sync(0xffffffffu, a.sq, r * D);
+          if (lane < D) {
+            a.sum += os;
+            a.sq += oq;
+          }
+        }
+        if (lane < D) {
+          atomicAdd(acc + (size_t)seg * 2 * D + lane, a.sum);
+          atomicAdd(acc + (size_t)seg * 2 * D + D + lane, a.sq);
+        }
+        __syncwarp();
+        int complete = 0;
+        if (lane == 0) {
+          __threadfence_block();
+          const int n_units = sm.seg_unit0[seg + 1] - sm.seg_unit0[seg];
+          complete = (atomicAdd(&sm.done[seg], units_cur) + units_cur == n_units);
+          if (complete) __threadfence_block();
+        }
+        return __shfl_sync(0xffffffffu, complete, 0) != 0;
+      };
+      // Publishing a completed segment and, if this CTA is the chain's last, finishing the chain keeps a warp busy for
+      // ~5 us.  Towards the end of the phase a warp must not sit on unaccounted units meanwhile (the segment they belong
+      // to could only complete -- and its chain only be finished -- after that, one finalisation after the other): in
+      // the dynamic part it first walks the units it holds, accounts for them, and only then publishes.
+      unsigned pend = 0;
+      bool dynamic_phase = false;
       for (;;) {
         if (u >= uend) {
+          if (pend) {
+            if (cur >= 0) {
+              if (leave_segment(cur)) pend |= 1u << cur;
+              cur = -1;
+            }
+            while (pend) {
+              const int sp = __ffs((int)pend) - 1;
+              pend &= pend - 1;
+              warp_publish_segment(pb, st, sm, sp, it, fused, part_len, max_seg, acc, pp_seg, fscratch, fs_len, kFlow,
+                                   have_ex ? exch : nullptr);
+            }
+          }
+          dynamic_phase = true;
           int start = 0, g = 0;
           if (lane == 0) {
             const int rem = total_units - *(volatile int *)&sm.next_unit;
@@ -1313,30 +1358,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
           s = -1;
         }
         if (s != cur) {
-          if (cur >= 0) {  // leave segment `cur`: add this warp's exact sums to the CTA's, count its units
-            zig_flush(cx, qn, pb.magic_sum, pb.magic_sq);
-            for (int r = 1; r < rows; ++r) {
-              const unsigned long long os = __shfl_down_sync(0xffffffffu, a.sum, r * D);
-              const unsigned long long oq = __shfl_down_sync(0xffffffffu, a.sq, r * D);
-              if (lane < D) {
-                a.sum += os;
-                a.sq += oq;
-              }
-            }
-            if (lane < D) {
-              atomicAdd(acc + (size_t)cur * 2 * D + lane, a.sum);
-              atomicAdd(acc + (size_t)cur * 2 * D + D + lane, a.sq);
-            }
-            __syncwarp();
-            int complete = 0;
-            if (lane == 0) {
-              __threadfence_block();
-              const int n_units = sm.seg_unit0[cur + 1] - sm.seg_unit0[cur];
-              complete = (atomicAdd(&sm.done[cur], units_cur) + units_cur == n_units);
-              if (complete) __threadfence_block();
-            }
-            complete = __shfl_sync(0xffffffffu, complete, 0);
-            if (complete)
+          if (cur >= 0 && leave_segment(cur)) {
+            if (dynamic_phase && u < uend && u < total_units)
+              pend |= 1u << cur;  // units in hand: see above
+            else
               warp_publish_segment(pb, st, sm, cur, it, fused, part_len, max_seg, acc, pp_seg, fscratch, fs_len, kFlow,
                                    have_ex ? exch : nullptr);
           }
