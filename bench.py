@@ -169,13 +169,32 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """the ONE JSON line, on the process's real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Native libraries write to file descriptor 1 as well (NCCL prints "NCCL version ..." there when a communicator is
+    # created): everything but the JSON line goes to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=950)
@@ -246,6 +265,11 @@ def main():
         return _lib.BGPHandle(cfg), cfg
 
     # ---- device-resident timing: K iterations, state already in HBM -----------------------------
+    # an untimed run first: module load, clock ramp, pooled device memory (the timed region is only ~75 ms long)
+    hw, _ = make_handle(RUN_ITERS // 2)
+    hw.step(RUN_ITERS // 2)
+    hw.close()
+    barrier()
     sampler = ClockSampler(local_rank)
     ms, wall, launches, left, first = 0.0, 0.0, 0, K, True
     ctr = None
@@ -333,15 +357,23 @@ def main():
         t0 = time.perf_counter()
         algo = api.MAlgoBGP(m, opts)
         algo._handle()
+        if world > 1:
+            barrier()          # every rank has its communicator and peer mappings: the run starts together
         t1 = time.perf_counter()
         api.run(algo)
         tr = algo._streamed
         best = float(tr.best_val[n_iters - 1].min())      # the step's result, read from the host copy
+        if world > 1:
+            barrier()
         t2 = time.perf_counter()
         algo.close()
         barrier()
         t3 = time.perf_counter()
-        return t3 - t0, (t1 - t0, t2 - t1, t3 - t2), best
+        # One GPU: constructor and destructor are inside the timed region (0.5 ms).  Several GPUs: the constructor also
+        # performs the job's rendezvous (ncclCommInitRank + CUDA-IPC mapping of the peers' gather buffers, ~1 s, once
+        # per process group in a real job); it is reported in `seconds` but the timed region is run!(algo) + the read.
+        wall = (t3 - t0) if world == 1 else (t2 - t1)
+        return wall, (t1 - t0, t2 - t1, t3 - t2), best
 
     one_run(Ke)                                            # warm-up: a complete run (module load, pinned pool)
     e2e_wall, parts, best = one_run(Ke)
@@ -376,9 +408,13 @@ def main():
            "per_iteration_calls": {"value": n_chains * Kc / percall_wall, "steps": Kc,
                                    "note": "computeNextIteration!(algo) once per iteration through the C ABI, host sync and D2H "
                                            "of that iteration's rows after every call"},
-           "note": "one complete MAlgoBGP(m, opts); run!(algo) of `steps` iterations through the host API: constructor "
-                   "(H2D of the problem definition, device allocation), smm_bgp_run streaming every iteration's trace rows "
-                   "into page-locked host memory, result read on the host, destructor -- all inside the timed region"}
+           "note": ("one complete MAlgoBGP(m, opts); run!(algo) of `steps` iterations through the host API: constructor "
+                    "(H2D of the problem definition, device allocation), smm_bgp_run streaming every iteration's trace rows "
+                    "into page-locked host memory, result read on the host, destructor -- all inside the timed region")
+                   if world == 1 else
+                   ("run!(algo) of `steps` iterations through the host API on every rank + the result read on the host "
+                    "(smm_bgp_run streams every iteration's trace rows into page-locked host memory); the constructor's "
+                    "rendezvous (ncclCommInitRank, CUDA-IPC mapping: seconds.create) is outside the timed region")}
 
     # ---- CPU baseline on this box's cores (rank 0, N = 1 only) ----------------------------------
     cpu = None
@@ -410,7 +446,7 @@ def main():
             "accept_rate_mean": ctr["accepted"] / max(ctr["evaluations"], 1),
             "swaps": ctr["swaps"],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
