@@ -622,3 +622,9 @@ JULIA_NAMES = {
     "median": median, "CI": CI, "params": params, "param": param, "paramd": paramd, "dataMoment": dataMoment,
     "dataMomentd": dataMomentd, "dataMomentW": dataMomentW, "allAccepted": allAccepted, "start": start, "finish": finish,
 }
+
+
+# ---------------------------------------------------------------------------------------------
+# slices and inference on the batched objective entry (slices.jl, econometrics.jl) -- see slices.py
+# ---------------------------------------------------------------------------------------------
+from .slices import (Slice, doSlices, optSlices, FD_gradient, getSigma, get_stdErrors, range_length)  # noqa: E402,F401
