@@ -174,3 +174,34 @@ function run!(algo::MAlgoBGPB200)
     haskey(algo.opts, "filename") && save(algo, algo.opts["filename"])
     return algo
 end
+
+"""
+    evaluateObjectiveBatch(m::MProb, plist; noseed=false, rep0=0, device=0)
+
+Many `evaluateObjective(m, p)` calls (mprob.jl:175-205) as ONE `smm_bgp_eval_batch` launch: what the loops of
+`doSlices` / `optSlices` (slices.jl:114-290) and `FD_gradient` / `getSigma` (econometrics.jl:29-145) need.
+`plist` is a vector of parameter dicts; returns a vector of `Eval`s (status -2 and no moments where the objective
+failed, exactly like the CPU path).  With `noseed=true` entry `b` draws its own shocks, indexed by `(b, rep0 + b)`.
+"""
+function evaluateObjectiveBatch(m::MProb, plist::Vector; noseed::Bool = false, rep0::Integer = 0, device::Integer = 0)
+    haskey(SMM_OBJ, m.objfunc) || error("$(m.objfunc) has no device simulator (no CPU fallback in the B200 path)")
+    pnames = collect(keys(m.params_to_sample)); mnames = collect(keys(m.moments))
+    np = length(pnames); nm = length(mnames); B = length(plist)
+    # a one-chain, one-iteration handle carries the problem definition (bounds, data moments, weights, simulator)
+    algo = MAlgoBGPB200(m, Dict("N" => 1, "maxiter" => 1, "maxtemp" => 1, "device" => device, "exchange_mode" => 0))
+    P = Float64[plist[b][pnames[k]] for k in 1:np, b in 1:B]            # column b = entry b  (C row-major [B][P])
+    value = zeros(B); moms = zeros(nm, B); status = zeros(Int32, B)
+    smm_check(ccall((:smm_bgp_eval_batch, LIBSMM_B200), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Int32, Int32, UInt32, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}),
+                    algo.handle, P, B, noseed ? 1 : 0, rep0, value, moms, status))
+    finalize(algo)
+    evs = Eval[]
+    for b in 1:B
+        ev = Eval(m, OrderedDict(zip(pnames, P[:, b])))
+        ev.value = value[b]; ev.status = status[b]
+        status[b] >= 0 && setMoments!(ev, mnames, moms[:, b])
+        noseed && (ev.options[:noseed] = true)
+        push!(evs, ev)
+    end
+    return evs
+end
