@@ -56,6 +56,8 @@ def lib():
     L.smm_oracle_zig_from_words.restype = C.c_double
     L.smm_oracle_exp_neg.argtypes = [C.c_double]
     L.smm_oracle_exp_neg.restype = C.c_double
+    L.smm_oracle_proxy_rate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.smm_oracle_proxy_rate.restype = C.c_double
     L.smm_oracle_neglog01.argtypes = [C.c_double]
     L.smm_oracle_neglog01.restype = C.c_double
     L.smm_oracle_acc_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
@@ -146,6 +148,12 @@ def zig_from_words(a: int, b: int):
 
 def exp_neg(t: float) -> float:
     return lib().smm_oracle_exp_neg(t)
+
+
+def proxy_rate(n_dims: int, n_sim: int, n_evals_per_thread: int, n_threads: int) -> float:
+    """evaluations/s of the "reference-speed proxy": the reference's data flow (draw matrix materialised, then reduced)
+    with a xoshiro256++ / ziggurat generator of the kind Julia's randn is; not stream compatible, timing only"""
+    return lib().smm_oracle_proxy_rate(n_dims, n_sim, n_evals_per_thread, n_threads)
 
 
 def neglog01(u: float) -> float:

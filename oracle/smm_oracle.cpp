@@ -702,6 +702,90 @@ double smm_oracle_zig_from_words(uint32_t a, uint32_t b, int *slow) {
   return ok ? z : smm_zig_slow(a, b, smm_zigtab(), smm_logtab());
 }
 double smm_oracle_exp_neg(double t) { return smm_exp_neg(t); }
+
+// "Reference-speed proxy" (BASELINE.md section 3, B-proxy): the objective's data flow exactly as the reference has it
+// (ObjExamples.jl:76-101: materialise the D x S Float64 draw matrix, then reduce it to means and variances) with the
+// kind of generator Julia's randn is -- xoshiro256++ state in registers + a 256-layer ziggurat, libm exp/log in the
+// rare branch.  NOT stream compatible with anything: it only answers "how fast would the CPU path be if its normals
+// were as cheap as Julia's", so that the reported CPU baseline is not handicapped by the counter-based streams.
+// Returns evaluations per second summed over n_threads threads (each thread evaluates n_evals_per_thread times).
+double smm_oracle_proxy_rate(int D, int S, int n_evals_per_thread, int n_threads) {
+  if (D < 1 || S < 2 || n_evals_per_thread < 1 || n_threads < 1) return 0.0;
+  auto worker = [&](int tid, double *sink) {
+    // xoshiro256++ with its state in locals (registers); the ziggurat's rare branch is kept out of line
+    uint64_t s0 = 0x9E3779B97F4A7C15ull * (uint64_t)(tid + 1), s1 = 0xBF58476D1CE4E5B9ull, s2 = 0x94D049BB133111EBull,
+             s3 = 0x2545F4914F6CDD1Dull + (uint64_t)tid;
+#define SMM_XOSHIRO_NEXT(r)                                         \
+  do {                                                              \
+    const uint64_t sum_ = s0 + s3, t_ = s1 << 17;                   \
+    (r) = ((sum_ << 23) | (sum_ >> 41)) + s0;                       \
+    s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t_;               \
+    s3 = (s3 << 45) | (s3 >> 19);                                   \
+  } while (0)
+    const smm_zigent *tab = smm_zigtab();
+    std::vector<double> X((size_t)D * S), sim(2 * D), p(D);
+    double acc = 0.0;
+    const size_t n_draws = (size_t)D * S;
+    for (int e = 0; e < n_evals_per_thread; ++e) {
+      for (int k = 0; k < D; ++k) p[k] = 0.01 * (k + e % 7);
+      // rand(MvNormal(mu, I), S): the D x S matrix filled in memory order, X[k, s] = mu[k] + z
+      int k = 0;
+      for (size_t q = 0; q < n_draws; ++q) {
+        double z;
+        for (;;) {
+          uint64_t r;
+          SMM_XOSHIRO_NEXT(r);
+          const uint32_t i = (uint32_t)(r >> 55) & 0xFFu;
+          const double u = (double)(r & 0xFFFFFFFFFFFFFull) * 0x1.0p-52, x = u * tab[i].w;
+          z = (r >> 63) ? -x : x;
+          if (__builtin_expect((uint32_t)((r >> 32) & 0xFFFFFu) < (tab[i].kh & 0xFFFFFu), 1)) break;
+          if (i == 0) {
+            for (;;) {
+              uint64_t a, b;
+              SMM_XOSHIRO_NEXT(a);
+              SMM_XOSHIRO_NEXT(b);
+              const double xt = -std::log(((double)(a >> 11) + 0.5) * 0x1.0p-53) / SMM_ZIG_R;
+              const double yt = -std::log(((double)(b >> 11) + 0.5) * 0x1.0p-53);
+              if (yt + yt > xt * xt) {
+                z = (r >> 63) ? -(SMM_ZIG_R + xt) : SMM_ZIG_R + xt;
+                break;
+              }
+            }
+            break;
+          }
+          uint64_t c;
+          SMM_XOSHIRO_NEXT(c);
+          const double f_lo = SMM_ZIGF_HOST[i], f_hi = SMM_ZIGF_HOST[i + 1];
+          if (f_lo + ((double)(c >> 11) * 0x1.0p-53) * (f_hi - f_lo) < std::exp(-0.5 * x * x)) break;
+        }
+        X[q] = p[k] + z;
+        if (++k == D) k = 0;
+      }
+#undef SMM_XOSHIRO_NEXT
+      std::fill(sim.begin(), sim.end(), 0.0);
+      for (int s = 0; s < S; ++s)
+        for (int kk = 0; kk < D; ++kk) sim[kk] += X[(size_t)kk + (size_t)D * s];
+      for (int kk = 0; kk < D; ++kk) sim[kk] /= (double)S;
+      for (int s = 0; s < S; ++s)
+        for (int kk = 0; kk < D; ++kk) {
+          const double d = X[(size_t)kk + (size_t)D * s] - sim[kk];
+          sim[D + kk] += d * d;
+        }
+      for (int kk = 0; kk < D; ++kk) acc += sim[kk] + sim[D + kk] / (double)(S - 1);
+    }
+    *sink = acc;
+  };
+  std::vector<double> sinks(n_threads, 0.0);
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> pool;
+  for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker, t, &sinks[t]);
+  for (auto &th : pool) th.join();
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  double chk = 0.0;
+  for (double v : sinks) chk += v;
+  if (!(chk == chk)) return 0.0;  // keeps the work observable
+  return (double)n_threads * n_evals_per_thread / dt;
+}
 double smm_oracle_neglog01(double u) { return smm_neglog01(u, smm_logtab()); }
 double smm_oracle_acc_uniform(uint64_t seed, uint32_t chain, uint32_t iter) { return smm_acc_uniform(seed, chain, iter); }
 void smm_oracle_pair_unrank(uint32_t q, uint32_t *i, uint32_t *j) { smm_pair_unrank(q, i, j); }
