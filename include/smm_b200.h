@@ -192,7 +192,7 @@ int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij /* [n_pairs][2] in exe
 /* debug: per-CTA globaltimer stamps {start, after proposal, after simulate, end} of the last iteration;
  * needs SMM_PHASE_TS=1 in the environment at create time.  Returns n_split (>0) or an error. */
 int smm_debug_phase_ts(smm_bgp *h, uint64_t *out, int64_t n);
-/* n grid barriers back to back on one 1024-thread CTA per SM (variant 0 = the one the persistent kernel uses) */
+/* n grid barriers back to back on one persistent-kernel-sized CTA per SM (variant 0 = the one exchange_mode 1 uses) */
 int smm_debug_barrier_bench(smm_bgp *h, int32_t variant, int32_t n, float *elapsed_ms);
 /* the simulate inner loop alone with this handle's keys/accumulators: blocks x threads CTAs, each thread
  * n_pairs_per_thread Philox blocks; dynamic != 0 uses the shared-counter unit distribution of the persistent kernel */

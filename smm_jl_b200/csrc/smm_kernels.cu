@@ -1,6 +1,6 @@
 // smm_kernels.cu -- sm_100a kernels of the BGP hot path.
 //
-// Two ways to run an iteration, same device functions, bit-identical results:
+// Three ways to run an iteration, same device functions, bit-identical results:
 //
 //  (A) multi-launch (exchange_mode 0):
 //      bgp_eval_kernel      grid (n_split, L) x 128 threads: proposal -> simulate -> [last CTA of the chain]
@@ -8,25 +8,30 @@
 //      [ncclAllGather of the last-accepted records when world > 1]
 //      bgp_exchange_kernel  exchangeMoves! on the gathered records.
 //
-//  (B) persistent (exchange_mode 1): bgp_persistent_kernel, ONE cooperative launch for up to kPairChunk
-//      iterations, one 1024-thread CTA per SM, two grid barriers per iteration:
+//  (B) persistent with grid barriers (exchange_mode 1): bgp_persistent_kernel<false>, ONE cooperative launch for up
+//      to kPairChunk iterations, one kPersistThreads-thread CTA per SM, two grid barriers per iteration:
 //        [exchange of iteration i-1 (replicated per CTA), proposals of iteration i for the chains the
 //         CTA owns, several chains at a time in warp groups]                               -- barrier --
-//        [every CTA takes an equal share of the flattened (chain, draw) space; inside the CTA warps pull
-//         small units of draws from a shared-memory counter, so all 32 warps finish together whatever the
-//         warp scheduler favours; the CTA that completes a chain finishes it (moments, distance,
-//         accept/reject, trace) in one warp group while the other warps already simulate the next chain;
+//        [every CTA takes an equal share of the flattened (chain, draw) space; inside the CTA every warp walks a
+//         fixed share and then pulls shrinking grabs of draws from a shared-memory counter, so all warps finish
+//         together whatever the warp scheduler favours; the CTA that completes a chain finishes it (moments,
+//         distance, accept/reject, trace) in one warp while the other warps already simulate the next chain;
 //         with world > 1 the finished record is stored straight into every peer GPU's gather buffer
 //         over NVLink]                                                                      -- barrier,
 //         folded with a cross-GPU flag exchange: the all-gather costs no launch and no extra barrier --
+//
+//  (C) persistent, barrier-free (exchange_mode 2): bgp_persistent_kernel<true>.  The warp that finishes a chain
+//      publishes a per-chain completion tag; every CTA waits for the tags of iteration i-1, replays the exchange,
+//      computes the proposals of the chains IT simulates, simulates, finishes -- no grid barrier anywhere.
 //
 // Reference lines: proposal AlgoBGP.jl:424-471 (mysample :400-410, mapto_01/ab mprob.jl:246-272);
 // objfunc_norm ObjExamples.jl:59-116; doAcceptReject! AlgoBGP.jl:324-392; set_eval! :220-245;
 // set_acceptRate! :253-257; exchangeMoves! :647-691; swap_ev_ij! :734-749; pair sample :653-656.
 //
 // Draws never touch memory: a thread owns one simulated dimension k, generates its normals in registers
-// (Philox4x32-10 + the fp64 Box-Muller of include/smm_stream.h) and adds them to ORDER-INVARIANT
-// accumulators (see simulate_*), so the result does not depend on how the draw space is cut up.
+// (Philox4x32-10 + the 256-layer ziggurat of include/smm_stream.h, rare branch deferred to warp-sized batches) and
+// adds them to ORDER-INVARIANT accumulators (see simulate_*), so the result does not depend on how the draw space is
+// cut up.  Proposals and the panel simulator use the Box-Muller transform of the same header.
 #include "smm_device.cuh"
 
 namespace smm {
