@@ -289,9 +289,20 @@ def _base_config(m: MProb, n_chains: int, max_iter: int, opts: dict) -> BGPConfi
         batch_size=int(opts.get("batch_size", len(names))),
         seed_algo=int(opts.get("seed", 20261017)),
         device=int(opts.get("device", 0)), world_size=int(opts.get("world_size", 1)), rank=int(opts.get("rank", 0)),
-        nccl_id=opts.get("nccl_id", b""), exchange_mode=int(opts.get("exchange_mode", 0)),
+        nccl_id=opts.get("nccl_id", b""), exchange_mode=_exchange_mode(m, opts, len(names)),
         n_split=int(opts.get("n_split", 0)),
     )
+
+
+def _exchange_mode(m: MProb, opts: dict, n_params: int) -> int:
+    """opts["exchange_mode"], or the fastest mode the shape allows: the barrier-free persistent kernel on one GPU
+    (2), the persistent kernel with one flag exchange per iteration on several (1); the multi-launch path (0) for the
+    panel objective and for more than 32 parameters (include/smm_b200.h)."""
+    if "exchange_mode" in opts:
+        return int(opts["exchange_mode"])
+    if _objective_id(m) == SMM_OBJ_PANEL or n_params > 32:
+        return 0
+    return 2 if int(opts.get("world_size", 1)) == 1 else 1
 
 
 def evaluateObjective(m: MProb, p, noseed: bool = False, rep: int = 0) -> Eval:
@@ -309,7 +320,7 @@ def evaluateObjective(m: MProb, p, noseed: bool = False, rep: int = 0) -> Eval:
 def evaluateObjectiveBatch(m: MProb, plist, noseed: bool = False, rep0: int = 0) -> "list[Eval]":
     """Many `evaluateObjective` calls in one launch (what doSlices / getSigma / FD_gradient loop over)."""
     names = list(m.params_to_sample.keys())
-    cfg = _base_config(m, 1, 1, {})
+    cfg = _base_config(m, 1, 1, {"exchange_mode": 0})      # a one-chain handle that only carries the problem definition
     P = np.array([[float(p[k]) for k in names] for p in plist], dtype=float)
     t0 = _time.time()
     with _lib.BGPHandle(cfg) as h:
@@ -496,7 +507,15 @@ class MAlgoBGP:
 
     def _handle(self) -> _lib.BGPHandle:
         if self._h is None:
-            self._h = _lib.BGPHandle(self._cfg)
+            try:
+                self._h = _lib.BGPHandle(self._cfg)
+            except _lib.SMMError as e:
+                # an automatically chosen persistent mode may not fit the shape (too many chains per SM): the
+                # multi-launch kernels take any shape.  An explicitly requested mode is never overridden.
+                if "exchange_mode" in self.opts or self._cfg.exchange_mode == 0 or "UNSUPPORTED_SHAPE" not in str(e):
+                    raise
+                self._cfg.exchange_mode = 0
+                self._h = _lib.BGPHandle(self._cfg)
         return self._h
 
     def close(self):
