@@ -39,3 +39,17 @@ def test_stream_tables_are_reproducible():
     assert r.returncode == 0, r.stderr[-2000:]
     with open(os.path.join(ROOT, "include", "smm_stream_tables.h")) as f:
         assert r.stdout == f.read()
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """N > 1: the driver launches the reference arm like the GPU arm; rank 0 alone works and prints, the others exit 0"""
+    env = dict(os.environ, SMM_BENCH_REF_BUDGET="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
