@@ -16,7 +16,7 @@ from typing import Callable, Dict, List, Optional
 
 import numpy as np
 
-from . import api
+# (api.py re-exports this module's functions, so `api` is imported where it is used, not here)
 
 
 class Slice:
@@ -46,8 +46,10 @@ Evaluator = Callable[["api.MProb", List[Dict[str, float]], bool, int], List["api
 
 
 def _evaluate(m, plist, noseed=False, rep0=0, evaluator: Optional[Evaluator] = None):
-    f = evaluator or api.evaluateObjectiveBatch
-    return f(m, plist, noseed, rep0)
+    if evaluator is None:
+        from . import api
+        evaluator = api.evaluateObjectiveBatch
+    return evaluator(m, plist, noseed, rep0)
 
 
 def doSlices(m: "api.MProb", npoints: int, parallel: bool = False, evaluator: Optional[Evaluator] = None) -> Slice:
