@@ -647,6 +647,7 @@ JULIA_NAMES = {
 # slices and inference on the batched objective entry (slices.jl, econometrics.jl) -- see slices.py
 # ---------------------------------------------------------------------------------------------
 from .slices import (Slice, doSlices, optSlices, FD_gradient, getSigma, get_stdErrors, range_length)  # noqa: E402,F401
+from .slices import save as saveSlice, load as loadSlice  # noqa: E402,F401  (save(s::Slice, f) / load(f), slices.jl:283-289)
 
 JULIA_NAMES.update({"doSlices": doSlices, "optSlices": optSlices, "FD_gradient": FD_gradient, "getSigma": getSigma,
                     "get_stdErrors": get_stdErrors, "evaluateObjectiveBatch": evaluateObjectiveBatch})

@@ -42,6 +42,20 @@ class Slice:
         return {"x": xs[ix], "y": ys[ix]}
 
 
+def save(s: Slice, fname: str) -> None:
+    """save(s::Slice, fname) (slices.jl:283-285); a pickle instead of JLD2"""
+    import pickle
+    with open(fname, "wb") as f:
+        pickle.dump({"s": s}, f)
+
+
+def load(fname: str) -> dict:
+    """load(fname) (slices.jl:287-289): {"s": Slice}"""
+    import pickle
+    with open(fname, "rb") as f:
+        return pickle.load(f)
+
+
 Evaluator = Callable[["api.MProb", List[Dict[str, float]], bool, int], List["api.Eval"]]
 
 

@@ -56,3 +56,47 @@ def test_sigma_and_standard_errors(oracle):
     assert not np.allclose(S, S2)
     se = slices.get_stdErrors(m, p, reps=40, evaluator=ev)
     assert list(se) == ["p1", "p2"] and all(0.005 < v < 0.02 for v in se.values())
+
+
+# ---- the reference's own test/test_slices.jl, with the oracle as the evaluator -------------------------------------
+def _problem_2x2():
+    from smm_jl_b200 import api
+    m = api.MProb()
+    api.addSampledParam(m, {"p1": [0.0, -2, 2], "p2": [0.0, -2, 2]})
+    api.addMoment(m, {"name": ["mu1", "mu2"], "value": [0.0, 0.0], "weight": [0.7, 0.3]})
+    api.addEvalFunc(m, api.objfunc_norm)
+    return m
+
+
+def test_slices_read_and_write(oracle, tmp_path):
+    """test_slices.jl:15-37: doSlices(mprob, 3), save, load, get(:p1, :mu1) / get(:p2, :value) survive the round trip"""
+    sl = slices.doSlices(_problem_2x2(), 3, evaluator=oracle_evaluator(oracle))
+    fn = str(tmp_path / "slices.pkl")
+    slices.save(sl, fn)
+    disk = slices.load(fn)["s"]
+    for p, what in (("p1", "mu1"), ("p2", "value")):
+        a, b = sl.get(p, what), disk.get(p, what)
+        assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"])
+
+
+def test_slices_survive_a_failing_objective(oracle):
+    """test_slices.jl:39-60: doSlices(mprob_fail, 30) with Testobj_fails completes; failed evaluations are not stored"""
+    from smm_jl_b200 import api
+    m = _problem_2x2()
+    m.objfunc = api.Testobj_fails
+    sl = slices.doSlices(m, 30, evaluator=oracle_evaluator(oracle))
+    assert all(len(v) == 0 for v in sl.res.values())
+
+
+def test_naive_coordinate_descent_works(oracle):
+    """test_slices.jl:62-65 / Examples.jl:210-230 (snorm_6_taxi): optSlices(mprob, 3, tol, update = 0.4) ends within 0.5
+    (Euclidean norm) of the data moments"""
+    from smm_jl_b200 import api
+    m = api.MProb()
+    api.addSampledParam(m, {"p1": [0.2, -3, 3], "p2": [-0.2, -2, 2], "p3": [-0.3, -2, 2], "p4": [-0.4, -2, 2],
+                            "p5": [0.3, -2, 2], "p6": [0.4, -2, 2]})
+    vals = [-1.0, 1.0, 0.5, -0.5, 0.7, -0.7]
+    api.addMoment(m, {"name": [f"mu{i + 1}" for i in range(6)], "value": vals, "weight": [1.0] * 6})
+    api.addEvalFunc(m, api.objfunc_norm)
+    s = slices.optSlices(m, 3, tol=0.1, update=0.4, evaluator=oracle_evaluator(oracle))
+    assert np.linalg.norm(np.array(vals) - np.array(list(s["best"]["p"].values()))) < 0.5
