@@ -189,6 +189,57 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 _REAL_STDOUT = None
 
+PARITY_CHAINS_PER_GPU, PARITY_ITERS = 32, 40
+
+
+def parity_leg(args, world, rank, local_rank, fresh_id, dist):
+    """Untimed: PARITY_CHAINS_PER_GPU chains per GPU x PARITY_ITERS iterations of the bench workload (same objective,
+    10 000 draws per evaluation, same exchange mode and world size as the timed region), every rank's trace gathered on
+    rank 0 and compared entry by entry with the CPU oracle's single-process run: integer / boolean bookkeeping and the
+    parameter traces bit-exact, objective values and moments within 1e-6 relative (tests/parity.py)."""
+    from smm_jl_b200 import _lib, configs
+    from smm_jl_b200 import dist as sd
+    n_chains, n = PARITY_CHAINS_PER_GPU * world, PARITY_ITERS
+    cfg = configs.mvnormal(n_chains, n, N_PARAMS)
+    cfg.device, cfg.world_size, cfg.rank, cfg.nccl_id = local_rank, world, rank, fresh_id()
+    cfg.n_split, cfg.exchange_mode = args.n_split, args.exchange_mode
+    with _lib.BGPHandle(cfg) as h:
+        h.step(n // 2)
+        h.step(n - n // 2)
+        tr = h.read_trace(1, n)
+        sigma, _ = h.chain_state()
+        ctr = h.counters()
+    if world > 1:
+        import torch
+        tr = sd.gather_trace(tr, device="cuda")
+        sig = [torch.empty(len(sigma), dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(sig, torch.from_numpy(sigma).cuda())
+        sigma = np.concatenate([t.cpu().numpy() for t in sig])
+    if rank != 0:
+        return None
+    from oracle import oracle_lib                     # checker only
+    from tests.parity import RTOL, first_divergence, max_rel_err
+    from smm_jl_b200._abi import Trace
+    ref = oracle_lib.run(configs.mvnormal(n_chains, n, N_PARAMS), n, n_threads=os.cpu_count() or 1)
+    int_mismatches = int(sum(int(np.count_nonzero(getattr(tr, f) != getattr(ref.trace, f))) for f in Trace.INT_FIELDS))
+    params_bits = bool(np.array_equal(tr.params.view(np.uint64), ref.trace.params.view(np.uint64)))
+    sigma_bits = bool(np.array_equal(sigma, ref.sigma))
+    nan_same = all(bool(np.array_equal(np.isnan(getattr(tr, f)), np.isnan(getattr(ref.trace, f)))) for f in Trace.FLOAT_FIELDS)
+    err = max_rel_err(tr, ref.trace)
+    out = {"world": world, "mode": args.exchange_mode, "n_chains": n_chains, "iterations": n, "n_sim": N_SIM,
+           "int_mismatches": int_mismatches, "params_bit_exact": params_bits, "sigma_bit_exact": sigma_bits,
+           "max_rel_err": err, "rtol": RTOL, "swaps": [int(ctr["swaps"]), int(ref.swaps)],
+           "checker": "oracle/libsmm_oracle.so: CPU restatement of the reference algorithm, single process, untimed"}
+    ok = int_mismatches == 0 and params_bits and sigma_bits and nan_same and err <= RTOL and ctr["swaps"] == ref.swaps
+    out["ok"] = bool(ok)
+    if not ok:
+        out["first_divergence"] = repr(first_divergence(tr, ref.trace))
+        emit({"metric": METRIC, "value": None, "n_gpus": world, "parity": out,
+              "error": "the CUDA path does not reproduce the oracle: nothing was timed"})
+        sys.stdout.flush()
+        os._exit(3)
+    return out
+
 
 def emit(line: dict) -> None:
     """the ONE JSON line, on the process's real stdout"""
@@ -275,6 +326,10 @@ def main():
         cfg.device, cfg.world_size, cfg.rank, cfg.nccl_id = local_rank, world, rank, fresh_id()
         cfg.n_split, cfg.exchange_mode = args.n_split, args.exchange_mode
         return _lib.BGPHandle(cfg), cfg
+
+    # ---- untimed parity leg: the path that is about to be timed (same exchange mode, same world) against the CPU
+    # oracle on rank 0 -- the checker, never the thing measured.  A mismatch ends the bench with a non-zero exit.
+    parity = parity_leg(args, world, rank, local_rank, fresh_id, dist if world > 1 else None)
 
     # ---- device-resident timing: K iterations, state already in HBM -----------------------------
     # an untimed run first: module load, clock ramp, pooled device memory (the timed region is only ~75 ms long)
@@ -455,6 +510,7 @@ def main():
                              "carried data is the chains' own state (~60 KB), which the algorithm's data dependence requires",
                        "run_iters": RUN_ITERS, "normals_per_eval": N_PARAMS * N_SIM},
             "clocks": clocks,
+            "parity": parity,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": roofline,

@@ -41,18 +41,21 @@ def broadcast_id(make_id, pg=None, device: Optional[str] = None) -> bytes:
     return bytes(t.cpu().tolist())
 
 
-def gather_trace(local: Trace, pg=None) -> Trace:
-    """All ranks receive the full [n][N] trace: per-rank [n][L] blocks joined in rank (= chain) order."""
+def gather_trace(local: Trace, pg=None, device: Optional[str] = None) -> Trace:
+    """All ranks receive the full [n][N] trace: per-rank [n][L] blocks joined in rank (= chain) order.
+    `device`: where the collective's tensors live ("cuda" for an NCCL process group; default: host, gloo)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(pg)
     parts = [Trace(local.n, local.L, local.P, local.M) for _ in range(world)]
     for f in Trace.FLOAT_FIELDS + Trace.INT_FIELDS:
         mine = torch.from_numpy(np.ascontiguousarray(getattr(local, f)))
+        if device:
+            mine = mine.to(device)
         bufs = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(bufs, mine, group=pg)
         for r in range(world):
-            setattr(parts[r], f, bufs[r].numpy())
+            setattr(parts[r], f, bufs[r].cpu().numpy())
     return Trace.concat_chains(parts)
 
 

@@ -12,6 +12,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_devices() -> int:
+    try:
+        from smm_jl_b200 import _lib
+        return int(_lib.device_count())
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device: without one they are skipped (the product has no CPU fallback to test)."""
+    if not any("gpu" in item.keywords for item in items):
+        return
+    if _cuda_devices() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device: the CUDA path cannot run here (and there is no CPU fallback)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """The CPU oracle (test infrastructure); built on demand with g++."""

@@ -55,11 +55,14 @@ def _worker(rank, world, port, n_chains, n_iter, mode, q, kind="mvnormal", data_
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
-def test_two_gpus_match_the_oracle(smm, oracle, mode):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_n_gpus_match_the_oracle(smm, oracle, world, mode):
+    """world ranks x 16 chains: NCCL all-gather (mode 0), fused peer stores + flag exchange (mode 1), per-chain
+    completion tags to every peer (mode 2) -- the gathered trace equals the oracle's single-process run"""
     from smm_jl_b200 import configs
-    if smm.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    world, n_chains, n_iter = 2, 32, 30
+    if smm.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n_chains, n_iter = 16 * world, 30
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

@@ -220,6 +220,76 @@ def test_large_config_properties(smm):
     assert (sigma > 0).all() and ((acc >= 0) & (acc <= 1)).all()
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_c2_full_size_against_the_oracle(smm, oracle, mode):
+    """BASELINE C2 at FULL size (256 chains x 10 000 draws, the benchmarked configuration) in every exchange mode the
+    bench can run, compared entry by entry with the oracle: bookkeeping exact, floats to 1e-6 relative"""
+    import os
+    n = 60
+    cfg = configs.mvnormal(256, n, exchange_mode=mode)
+    tr, sigma, acc, ctr = run_gpu(smm, cfg, n)
+    ref = oracle.run(configs.mvnormal(256, n), n, n_threads=os.cpu_count() or 1)
+    assert_trace_parity(tr, ref.trace)
+    assert np.array_equal(tr.params.view(np.uint64), ref.trace.params.view(np.uint64))
+    np.testing.assert_array_equal(sigma, ref.sigma)
+    np.testing.assert_array_equal(acc, ref.accept_rate)
+    assert ctr["swaps"] == ref.swaps and ctr["proposal_attempts"] == ref.attempts
+    assert max_rel_err(tr, ref.trace) < 1e-9
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_zero_and_negative_weights_on_device(smm, oracle, mode):
+    """The reference's own fixture carries zero and negative moment weights (test/include/test-include.jl:78): a zero
+    weight divides by zero (ObjExamples.jl:97) -> value = +Inf for every evaluation, a negative one is squared away.
+    From iteration 2 on, exp(acc_tuner * (Inf - Inf)) = NaN -> rejected with status -1 (AlgoBGP.jl:350-353), and the
+    exchange compares Inf - Inf = NaN > min_improve -> never swaps (:688)."""
+    n = 30
+    cfg = configs.c1_serial_normal(n, data_w=[0.0, -1.0], exchange_mode=mode)
+    tr, sigma, acc, ctr = run_gpu(smm, cfg, n)
+    ref = oracle.run(cfg, n)
+    assert_trace_parity(tr, ref.trace)
+    np.testing.assert_array_equal(sigma, ref.sigma)
+    np.testing.assert_array_equal(acc, ref.accept_rate)
+    assert np.isinf(tr.value).all() and (tr.status[1:] == -1).all() and (tr.prob[1:] == 0).all()
+    assert (tr.accepted[0] == 1).all() and (tr.accepted[1:] == 0).all() and ctr["swaps"] == 0
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_nonfinite_branches_of_accept_reject_on_device(smm, oracle, mode):
+    """A weight of 1e-155 makes ((sim - data) / w)^2 overflow unless |sim - data| < 0.13, so chains wander between
+    finite (~1e300) and infinite objective values and doAcceptReject! takes every branch (AlgoBGP.jl:336-367) on the
+    device: Inf -> Inf = NaN prob -> status -1; Inf -> finite = forced accept with prob 1 (:355-359); finite -> Inf =
+    prob exp(-Inf) = 0, status 1; finite -> finite = the ordinary Metropolis test."""
+    n = 60
+    kw = dict(n_params=2, data_w=[1e-155, 1.0, 1.0, 1.0], n_sim=2000)
+    tr, sigma, acc, ctr = run_gpu(smm, configs.mvnormal(8, n, exchange_mode=mode, **kw), n)
+    ref = oracle.run(configs.mvnormal(8, n, **kw), n, n_threads=4)
+    assert_trace_parity(tr, ref.trace)
+    np.testing.assert_array_equal(sigma, ref.sigma)
+    np.testing.assert_array_equal(acc, ref.accept_rate)
+    assert ctr["swaps"] == ref.swaps
+    # the branches were really taken
+    assert (tr.status == -1).sum() > 10
+    forced = (~np.isfinite(tr.curr_val[:-1])) & np.isfinite(tr.value[1:]) & (tr.accepted[1:] == 1) & (tr.exchanged[1:] == 0)
+    assert forced.sum() >= 1 and (tr.prob[1:][forced] == 1.0).all()
+    assert ((tr.prob[1:] == 0) & (tr.status[1:] == 1) & np.isinf(tr.value[1:])).sum() > 10
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_nan_objective_is_the_reference_error(smm, oracle, mode):
+    """`eval_new.value >= 0 || error(...)` (AlgoBGP.jl:341) also fires for NaN: a NaN data moment makes every value
+    NaN, iteration 1 is accepted unconditionally (:327-333), iteration 2 aborts the run -- on both sides"""
+    from smm_jl_b200._abi import SMM_E_NEGATIVE_OBJECTIVE
+    cfg = configs.c1_serial_normal(5, data_mom=[float("nan"), 10.0], exchange_mode=mode)
+    with pytest.raises(smm.SMMError) as e:
+        with smm.BGPHandle(cfg) as h:
+            h.step(5)
+    assert e.value.code == SMM_E_NEGATIVE_OBJECTIVE
+    with pytest.raises(oracle.OracleError) as e2:
+        oracle.run(cfg, 5)
+    assert e2.value.code == SMM_E_NEGATIVE_OBJECTIVE
+
+
 def test_sampler_exhaustion_is_an_error(smm, oracle):
     """AlgoBGP.jl:409: `error("no draw in support ...")` with a single batch"""
     from smm_jl_b200._abi import SMM_E_SAMPLER_EXHAUSTED
