@@ -184,9 +184,10 @@ int smm_bgp_kernel_times(smm_bgp *h, double ms_sum[4], int64_t launches[4]);
 /* test/diagnostic entry points (device implementations of the stream definitions) */
 int smm_debug_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_pairs,
                       double *out /* [2*n_pairs] */);
-/* same, through the ziggurat transform (smm_zig_pair): the simulator stream of the MvNormal objectives */
-int smm_debug_zig_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_pairs,
-                          double *out /* [2*n_pairs] */);
+/* same, through the ziggurat transform (smm_zig_triple: three normals per block): the simulator stream of the
+ * MvNormal objectives */
+int smm_debug_zig_normals(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_blocks,
+                          double *out /* [3*n_blocks] */);
 int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij /* [n_pairs][2] in execution order */,
                     int32_t *level_offsets /* [n_pairs+1] */, int32_t *n_levels);
 /* debug: per-CTA globaltimer stamps {start, after proposal, after simulate, end} of the last iteration;

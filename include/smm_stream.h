@@ -138,12 +138,10 @@ static const smm_logent SMM_LOGTAB_HOST[1 << SMM_LOG_BITS] = SMM_LOG_TABLE;
 static const double SMM_SIN_HOST[SMM_SIN_DEG + 1] = SMM_SIN_COEFS;
 static const double SMM_COS_HOST[SMM_COS_DEG + 1] = SMM_COS_COEFS;
 static const double SMM_LOGQ_HOST[SMM_LOGQ_DEG + 1] = SMM_LOGQ_COEFS;
-/* ziggurat tables (see smm_zig_normal): 16-byte layer entries, so the fast path is one 128-bit load */
-typedef struct smm_zigent {
-  double w;    /* W[i]: outer edge of layer i (virtual width of the base strip for i = 0) */
-  uint32_t kh; /* 0x3FF00000 | floor(2^20 W[i+1]/W[i]): fast-accept bound on the high word of the uniform */
-  uint32_t pad;
-} smm_zigent;
+/* ziggurat table (see smm_zig_fast): one 8-byte entry per layer = the bit pattern of the double W'[i] * 2^-32, whose
+ * low 12 mantissa bits ARE the fast-accept bound KH[i] = floor(2^12 W'[i+1] / W'[i]) on the top 12 bits of the
+ * 32-bit uniform.  W'[i] (= 2^32 * entry) is the outer edge of layer i (virtual width of the base strip for i = 0). */
+typedef uint64_t smm_zigent;
 static const smm_zigent SMM_ZIGTAB_HOST[SMM_ZIG_LAYERS] = SMM_ZIG_TABLE;
 static const double SMM_ZIGF_HOST[SMM_ZIG_LAYERS + 1] = SMM_ZIG_F;
 static const double SMM_EXP_HOST[SMM_EXP_DEG + 1] = SMM_EXP_COEFS;
@@ -248,25 +246,28 @@ SMM_HD void smm_normal_pair(smm_u32x4 r, double *z0, double *z1) {
 
 /* ---- ziggurat normals: the simulator stream of the MvNormal objectives ------------------------
  *
- * Julia's randn -- what the reference's rand(MvNormal(..), ns) (ObjExamples.jl:78) bottoms out in -- is a
- * 256-layer ziggurat; so is this, restated on counter-indexed bits so that it is a pure function:
+ * Julia's randn -- what the reference's rand(MvNormal(..), ns) (ObjExamples.jl:78) bottoms out in -- is a ziggurat;
+ * so is this, restated on counter-indexed bits so that it is a pure function.  ONE Philox block (x, y, z, w) yields
+ * THREE normals: draw t = 0, 1, 2 takes the 32-bit uniform word u = (x, y, z)[t] and the 10-bit select field
+ * s = smm_zig_select(w, t) = [sign : 1][layer i : 9]  (w bits 3..12 | 13..22 | {0, 23..31}; bits 1, 2 are unused):
  *
- *   one normal = Zig(a, b), (a, b) = 64 random bits (half a Philox block):
- *     sign = bit 31 of a, layer i = bits 23..30 of a, u = 0.{a bits 0..19}{b} in [0,1)  (52 bits)
- *     x = u W[i];  FAST PATH (98.5 % of draws): accept when the 20 high bits of u are below
- *     floor(2^20 W[i+1]/W[i])  (x strictly inside the layer's core: 4 integer ops, one fp64 fma)
+ *     x = u * (W'[i] 2^-32)                      (u converted exactly; one fp64 multiply; 512 layers)
+ *     FAST PATH (99.2 % of draws): accept when the top 12 bits of u are below KH[i], i.e.  u < KH[i] 2^20
+ *       (x strictly inside the layer's core: two integer ops, one 8-byte table load, two fp64 ops)
  *     otherwise (smm_zig_slow):
- *       i >= 1: wedge test  f(W[i]) + U (f(W[i+1]) - f(W[i])) < exp(-x^2/2); on rejection a NEW candidate
- *       i == 0: x fell beyond R in the base strip -> Marsaglia's tail: repeat xt = -log(U1)/R, yt = -log(U2)
- *               until 2 yt > xt^2, return R + xt
- *     The extra uniforms and candidates come from auxiliary blocks Philox(a, b, n, TAG; ZIG key), n = 1, 2, ...
- *     in the order the state machine consumes them -- a deterministic function of (a, b) alone.
+ *       i >= 1: wedge test  f(W'[i]) + U (f(W'[i+1]) - f(W'[i])) < exp(-x^2/2); on rejection a NEW candidate (u, s)
+ *       i == 0: x < R is still inside the base strip; beyond R -> Marsaglia's tail: repeat xt = -log(U1)/R,
+ *               yt = -log(U2) until 2 yt > xt^2, return R + xt
+ *     The extra uniforms and candidates come from auxiliary blocks Philox(u, s, n, TAG; ZIG key), n = 1, 2, ... of the
+ *     draw's ORIGINAL (u, s), in the order the state machine consumes them -- a deterministic function of (u, s) alone.
  *
  * exp and log are the fma-only kernels of this header, so host and device agree to the bit. */
-#define SMM_ZIG_TAG 0x5A494721u
+#define SMM_ZIG_TAG 0x5A494732u
 #define SMM_ZIG_KEY0 0x736D6D5Au
-#define SMM_ZIG_KEY1 0x69676767u
+#define SMM_ZIG_KEY1 0x69676733u
 #define SMM_ZIG_MAX_AUX 4096u
+#define SMM_ZIG_PER_BLOCK 3
+#define SMM_ZIG_SEL_MASK ((2u << SMM_ZIG_LAYER_BITS) - 1u) /* sign + layer */
 
 /* exp(t), t in [-700, 0]: t = n ln2 + r, |r| <= ln2/2 (+ rounding), Taylor degree 13, scaled by 2^n */
 SMM_HD double smm_exp_neg(double t) {
@@ -283,14 +284,22 @@ SMM_HD double smm_exp_neg(double t) {
   return SMM_MUL(p, smm_bits_to_double((uint64_t)(n + 1023) << 52));
 }
 
+/* select field of draw t (0, 1, 2) in the block's fourth word */
+SMM_HD uint32_t smm_zig_select(uint32_t w, int t) {
+  return (t == 0 ? (w >> 3) : t == 1 ? (w >> 13) : ((w >> 23) | (w << 9))) & SMM_ZIG_SEL_MASK;
+}
+
+/* (double)u, exactly, without an integer conversion: 2^52 + u has u in its low mantissa word */
+SMM_HD double smm_u32_to_double(uint32_t u) {
+  return SMM_SUB(smm_bits_to_double(0x4330000000000000ull | (uint64_t)u), 4503599627370496.0);
+}
+
 /* the fast path: candidate value and whether it is accepted outright */
-SMM_HD double smm_zig_fast(uint32_t a, uint32_t b, const smm_zigent *tab, int *ok) {
-  const smm_zigent t = tab[(a >> 23) & 0xFFu];
-  const uint32_t hi = (a & 0x000FFFFFu) | 0x3FF00000u;
-  const double d = smm_bits_to_double(((uint64_t)hi << 32) | (uint64_t)b); /* 1 + u */
-  const double x = SMM_FMA(d, t.w, -t.w);                                  /* u W[i], correctly rounded */
-  *ok = hi < t.kh;
-  return smm_bits_to_double(smm_double_to_bits(x) ^ ((uint64_t)(a & 0x80000000u) << 32));
+SMM_HD double smm_zig_fast(uint32_t u, uint32_t s, const smm_zigent *tab, int *ok) {
+  const smm_zigent e = tab[s & (SMM_ZIG_LAYERS - 1u)];
+  const double x = SMM_MUL(smm_u32_to_double(u), smm_bits_to_double(e));
+  *ok = u < ((uint32_t)e << 20);
+  return smm_bits_to_double(smm_double_to_bits(x) | ((uint64_t)(s >> SMM_ZIG_LAYER_BITS) << 63));
 }
 
 /* u in [2^-52, 1 - 2^-52] from two words (odd 52-bit integer: never 0 or 1) */
@@ -298,52 +307,53 @@ SMM_HD double smm_u01_open(uint32_t a, uint32_t b) {
   return SMM_SUB(2.0, smm_bits_to_double(0x3FF0000000000000ull | smm_mant52(a, b) | 1ull));
 }
 
-/* everything after a failed fast test of candidate (a, b) */
-SMM_HD double smm_zig_slow(uint32_t a0, uint32_t b0, const smm_zigent *tab, const smm_logent *logtab) {
-  uint32_t a = a0, b = b0, n = 0;
+/* everything after a failed fast test of candidate (u0, s0) */
+SMM_HD double smm_zig_slow(uint32_t u0, uint32_t s0, const smm_zigent *tab, const smm_logent *logtab) {
+  uint32_t u = u0, s = s0, n = 0;
   for (;;) {
-    const uint32_t i = (a >> 23) & 0xFFu;
-    const uint64_t sign = (uint64_t)(a & 0x80000000u) << 32;
-    const smm_zigent t = tab[i];
-    const uint32_t hi = (a & 0x000FFFFFu) | 0x3FF00000u;
-    const double d = smm_bits_to_double(((uint64_t)hi << 32) | (uint64_t)b);
-    const double x = SMM_FMA(d, t.w, -t.w);
-    if (hi < t.kh) return smm_bits_to_double(smm_double_to_bits(x) ^ sign);
-    if (i == 0u) { /* tail beyond R */
-      for (;;) {
+    const uint32_t i = s & (SMM_ZIG_LAYERS - 1u);
+    const uint64_t sign = (uint64_t)(s >> SMM_ZIG_LAYER_BITS) << 63;
+    const smm_zigent e = tab[i];
+    const double x = SMM_MUL(smm_u32_to_double(u), smm_bits_to_double(e));
+    if (u < ((uint32_t)e << 20)) return smm_bits_to_double(smm_double_to_bits(x) | sign);
+    if (i == 0u) {
+      if (x < SMM_ZIG_R) return smm_bits_to_double(smm_double_to_bits(x) | sign); /* base strip */
+      for (;;) {                                                                   /* tail beyond R */
         ++n;
-        const smm_u32x4 r = smm_philox4x32_10(a0, b0, n, SMM_ZIG_TAG, SMM_ZIG_KEY0, SMM_ZIG_KEY1);
+        const smm_u32x4 r = smm_philox4x32_10(u0, s0, n, SMM_ZIG_TAG, SMM_ZIG_KEY0, SMM_ZIG_KEY1);
         const double xt = SMM_MUL(smm_neglog01(smm_u01_open(r.x, r.y), logtab), SMM_ZIG_RINV);
         const double yt = smm_neglog01(smm_u01_open(r.z, r.w), logtab);
         if (SMM_ADD(yt, yt) > SMM_MUL(xt, xt) || n >= SMM_ZIG_MAX_AUX)
-          return smm_bits_to_double(smm_double_to_bits(SMM_ADD(SMM_ZIG_R, xt)) ^ sign);
+          return smm_bits_to_double(smm_double_to_bits(SMM_ADD(SMM_ZIG_R, xt)) | sign);
       }
     }
     ++n;
-    const smm_u32x4 r = smm_philox4x32_10(a0, b0, n, SMM_ZIG_TAG, SMM_ZIG_KEY0, SMM_ZIG_KEY1);
+    const smm_u32x4 r = smm_philox4x32_10(u0, s0, n, SMM_ZIG_TAG, SMM_ZIG_KEY0, SMM_ZIG_KEY1);
     const double f_lo = SMM_ZIGF(i), f_hi = SMM_ZIGF(i + 1u);
     const double y = SMM_FMA(smm_u01(r.z, r.w), SMM_SUB(f_hi, f_lo), f_lo);
     if (y < smm_exp_neg(SMM_MUL(SMM_MUL(x, x), -0.5)) || n >= SMM_ZIG_MAX_AUX)
-      return smm_bits_to_double(smm_double_to_bits(x) ^ sign);
-    a = r.x; /* rejected: start over with a fresh candidate */
-    b = r.y;
+      return smm_bits_to_double(smm_double_to_bits(x) | sign);
+    u = r.x; /* rejected: start over with a fresh candidate */
+    s = r.y & SMM_ZIG_SEL_MASK;
   }
 }
 
-SMM_HD double smm_zig_normal_tab(uint32_t a, uint32_t b, const smm_zigent *tab, const smm_logent *logtab) {
+SMM_HD double smm_zig_normal_tab(uint32_t u, uint32_t s, const smm_zigent *tab, const smm_logent *logtab) {
   int ok;
-  const double z = smm_zig_fast(a, b, tab, &ok);
-  return ok ? z : smm_zig_slow(a, b, tab, logtab);
+  const double z = smm_zig_fast(u, s, tab, &ok);
+  return ok ? z : smm_zig_slow(u, s, tab, logtab);
 }
-/* the two normals of one Philox block: (x, y) -> z0, (z, w) -> z1 */
-SMM_HD void smm_zig_pair(smm_u32x4 r, double *z0, double *z1) {
-  *z0 = smm_zig_normal_tab(r.x, r.y, smm_zigtab(), smm_logtab());
-  *z1 = smm_zig_normal_tab(r.z, r.w, smm_zigtab(), smm_logtab());
+/* the three normals of one Philox block */
+SMM_HD void smm_zig_triple(smm_u32x4 r, double *z) {
+  z[0] = smm_zig_normal_tab(r.x, smm_zig_select(r.w, 0), smm_zigtab(), smm_logtab());
+  z[1] = smm_zig_normal_tab(r.y, smm_zig_select(r.w, 1), smm_zigtab(), smm_logtab());
+  z[2] = smm_zig_normal_tab(r.z, smm_zig_select(r.w, 2), smm_zigtab(), smm_logtab());
 }
 
 /* ---- the four streams ----------------------------------------------------------------------- */
 
-/* Zsim[k, 2j] and Zsim[k, 2j+1].  With common random numbers (noseed == 0, the reference's
+/* The block of Zsim[k, .] number j: ziggurat objectives take Zsim[k, 3j .. 3j+2] from it (smm_zig_triple), the
+ * dynamic panel two Box-Muller normals (smm_normal_pair).  With common random numbers (noseed == 0, the reference's
  * Random.seed!(1234) at ObjExamples.jl:74) every evaluation sees the same block; with noseed the
  * block is additionally indexed by (eval_uid, rep). */
 SMM_HD smm_u32x4 smm_sim_block(uint64_t seed_sim, uint32_t j, uint32_t k, int noseed, uint32_t eval_uid,

@@ -54,6 +54,8 @@ def lib():
     L.smm_oracle_zig_normals.restype = None
     L.smm_oracle_zig_from_words.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
     L.smm_oracle_zig_from_words.restype = C.c_double
+    L.smm_oracle_zig_select.argtypes = [C.c_uint32, C.c_int]
+    L.smm_oracle_zig_select.restype = C.c_uint32
     L.smm_oracle_exp_neg.argtypes = [C.c_double]
     L.smm_oracle_exp_neg.restype = C.c_double
     L.smm_oracle_proxy_rate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
@@ -132,18 +134,22 @@ def normal_from_words(x, y, z, w):
     return out
 
 
-def zig_normals(seed: int, k: int, c2: int, c3: int, n_pairs: int) -> np.ndarray:
-    """ziggurat normals of Philox blocks (j, k, c2, c3), j < n_pairs (the MvNormal simulator stream)"""
-    out = np.zeros(2 * n_pairs)
-    lib().smm_oracle_zig_normals(seed, k, c2, c3, n_pairs, out.ctypes.data_as(C.POINTER(C.c_double)))
+def zig_normals(seed: int, k: int, c2: int, c3: int, n_blocks: int) -> np.ndarray:
+    """the 3 * n_blocks ziggurat normals of Philox blocks (j, k, c2, c3), j < n_blocks (the MvNormal simulator stream)"""
+    out = np.zeros(3 * n_blocks)
+    lib().smm_oracle_zig_normals(seed, k, c2, c3, n_blocks, out.ctypes.data_as(C.POINTER(C.c_double)))
     return out
 
 
-def zig_from_words(a: int, b: int):
-    """one ziggurat normal from its 64 bits -> (z, slow_path_taken)"""
+def zig_from_words(u: int, sel: int):
+    """one ziggurat normal from its 32-bit uniform and 10-bit select field -> (z, slow_path_taken)"""
     slow = C.c_int(0)
-    z = lib().smm_oracle_zig_from_words(a, b, C.byref(slow))
+    z = lib().smm_oracle_zig_from_words(u, sel, C.byref(slow))
     return z, bool(slow.value)
+
+
+def zig_select(w: int, t: int) -> int:
+    return int(lib().smm_oracle_zig_select(w, t))
 
 
 def exp_neg(t: float) -> float:

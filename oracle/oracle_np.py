@@ -52,28 +52,35 @@ def normal_pairs(x, y, z, w):
 
 
 _ZIG = None
+ZIG_LAYERS = 512
 
 
 def zig_tables():
-    """The 256-layer Marsaglia-Tsang ziggurat re-derived here with mpmath from its defining equations (equal-area
-    layers under exp(-x^2/2), closing condition solved for R by bisection) -- not read from the C header."""
+    """The 512-layer Marsaglia-Tsang ziggurat re-derived here with mpmath from its defining equations (equal-area
+    layers under exp(-x^2/2), closing condition solved for R by bisection) -- not read from the C header -- followed by
+    the documented table rule of include/smm_stream.h: going from the top layer down, W'[i] = double(W[i]) with its
+    low 12 mantissa bits replaced by KH[i], the largest k <= 4096 W'[i+1] / W[i] with k / 4096 <= W'[i+1] / W'[i];
+    F[i] = exp(-W'[i]^2 / 2).  Returns (W', KH, F, R' = W'[1])."""
     global _ZIG
     if _ZIG is None:
+        import struct
+        from fractions import Fraction
         import mpmath as mp
+        NZ = ZIG_LAYERS
         with mp.workprec(160):
             f = lambda x: mp.exp(-x * x / 2)
 
             def build(R):
                 V = R * f(R) + mp.sqrt(mp.pi / 2) * mp.erfc(R / mp.sqrt(2))
                 xs = [V / f(R), R]
-                for i in range(1, 255):
+                for i in range(1, NZ - 1):
                     y = V / xs[i] + f(xs[i])
                     if y >= 1:
                         return None, xs
                     xs.append(mp.sqrt(-2 * mp.log(y)))
-                return xs[255] * (1 - f(xs[255])) - V, xs
+                return xs[NZ - 1] * (1 - f(xs[NZ - 1])) - V, xs
 
-            lo, hi = mp.mpf("3.5"), mp.mpf("3.8")
+            lo, hi = mp.mpf("3.2"), mp.mpf("4.5")
             for _ in range(300):
                 mid = (lo + hi) / 2
                 res, xs = build(mid)
@@ -81,76 +88,92 @@ def zig_tables():
                     lo = mid
                 else:
                     hi = mid
-            R = (lo + hi) / 2
-            _, xs = build(R)
-            xs.append(mp.mpf(0))
-            W = np.array([float(x) for x in xs])
-            KH = np.array([int(mp.floor(mp.mpf(2) ** 20 * xs[i + 1] / xs[i])) for i in range(256)], dtype=np.uint64)
-            F = np.array([float(f(x)) for x in xs])
-        _ZIG = (W, KH, F, float(R))
+            _, xs = build((lo + hi) / 2)
+            ideal = [float(x) for x in xs] + [0.0]
+            Wp, KH = [0.0] * (NZ + 1), [0] * NZ
+            for i in range(NZ - 1, -1, -1):
+                base = struct.unpack("<Q", struct.pack("<d", ideal[i]))[0] & ~0xFFF
+                k = int(mp.floor(4096 * mp.mpf(Wp[i + 1]) / xs[i]))
+                while True:
+                    cand = struct.unpack("<d", struct.pack("<Q", base | k))[0]
+                    if Fraction(k, 4096) <= Fraction(Wp[i + 1]) / Fraction(cand):
+                        break
+                    k -= 1
+                Wp[i], KH[i] = cand, k
+            F = np.array([float(f(mp.mpf(x))) for x in Wp])
+        _ZIG = (np.array(Wp), np.array(KH, dtype=np.uint64), F, Wp[1])
     return _ZIG
 
 
-ZIG_TAG, ZIG_KEY0, ZIG_KEY1 = 0x5A494721, 0x736D6D5A, 0x69676767
+ZIG_TAG, ZIG_KEY0, ZIG_KEY1 = 0x5A494732, 0x736D6D5A, 0x69676733
 
 
 def _u52(a, b):
     return ((int(a) << 20) | (int(b) >> 12))
 
 
-def zig_slow(a0, b0):
-    """the ziggurat's rare branch for one candidate (wedge test / tail / retry), with libm exp and log"""
+def zig_select(w, t):
+    """the 10-bit select field [sign:1][layer:9] of draw t in the block's fourth word"""
+    w = int(w)
+    return ((w >> 3) if t == 0 else (w >> 13) if t == 1 else ((w >> 23) | (w << 9))) & 0x3FF
+
+
+def zig_slow(u0, s0):
+    """the ziggurat's rare branch for one candidate (wedge test / base strip / tail / retry), with libm exp and log"""
     W, KH, F, R = zig_tables()
-    a, b, n = int(a0), int(b0), 0
+    u, s, n = int(u0), int(s0), 0
     while True:
-        i = (a >> 23) & 0xFF
-        sgn = -1.0 if (a >> 31) else 1.0
-        hi20 = a & 0xFFFFF
-        u = ((hi20 << 32) | b) / 2.0 ** 52
-        x = u * W[i]
-        if hi20 < int(KH[i]):
+        i = s & 0x1FF
+        sgn = -1.0 if (s >> 9) else 1.0
+        x = u * (W[i] / 2.0 ** 32)
+        if (u >> 20) < int(KH[i]):
             return sgn * x
         if i == 0:
+            if x < R:
+                return sgn * x
             while True:
                 n += 1
-                r = [int(v) for v in philox(a0, b0, n, ZIG_TAG, ZIG_KEY0, ZIG_KEY1)]
+                r = [int(v) for v in philox(u0, s0, n, ZIG_TAG, ZIG_KEY0, ZIG_KEY1)]
                 u1 = (2 ** 52 - (_u52(r[0], r[1]) | 1)) / 2.0 ** 52
                 u2 = (2 ** 52 - (_u52(r[2], r[3]) | 1)) / 2.0 ** 52
                 xt, yt = -math.log(u1) / R, -math.log(u2)
                 if yt + yt > xt * xt:
                     return sgn * (R + xt)
         n += 1
-        r = [int(v) for v in philox(a0, b0, n, ZIG_TAG, ZIG_KEY0, ZIG_KEY1)]
+        r = [int(v) for v in philox(u0, s0, n, ZIG_TAG, ZIG_KEY0, ZIG_KEY1)]
         uw = _u52(r[2], r[3]) / 2.0 ** 52
         if F[i] + uw * (F[i + 1] - F[i]) < math.exp(-0.5 * x * x):
             return sgn * x
-        a, b = r[0], r[1]
+        u, s = r[0], r[1] & 0x3FF
 
 
-def zig_normals(a, b):
-    """ziggurat normals from arrays of 32-bit word pairs: numpy fast path, Python loop for the ~1.5 % rest"""
+def zig_normals(u, s):
+    """ziggurat normals from arrays of 32-bit uniform words and 10-bit select fields: numpy fast path, Python loop for
+    the ~0.8 % rest"""
     W, KH, _, _ = zig_tables()
-    a, b = np.asarray(a, dtype=np.uint64), np.asarray(b, dtype=np.uint64)
-    i = ((a >> np.uint64(23)) & np.uint64(0xFF)).astype(np.int64)
-    hi20 = a & np.uint64(0xFFFFF)
-    u = ((hi20 << np.uint64(32)) | b).astype(np.float64) / np.float64(2 ** 52)
-    z = np.where((a >> np.uint64(31)).astype(bool), -1.0, 1.0) * (u * W[i])
-    slow = np.nonzero(hi20 >= KH[i])[0]
+    u, s = np.asarray(u, dtype=np.uint64), np.asarray(s, dtype=np.uint64)
+    i = (s & np.uint64(0x1FF)).astype(np.int64)
+    z = np.where((s >> np.uint64(9)).astype(bool), -1.0, 1.0) * (u.astype(np.float64) * (W[i] / 2.0 ** 32))
+    slow = np.nonzero((u >> np.uint64(20)) >= KH[i])[0]
     for t in slow:
-        z[t] = zig_slow(a[t], b[t])
+        z[t] = zig_slow(u[t], s[t])
     return z
 
 
 def sim_normals(seed_sim, k, S, noseed=0, uid=0, rep=0, transform="zig"):
-    nb = (S + 1) // 2
+    per = 3 if transform == "zig" else 2
+    nb = (S + per - 1) // per
     j = np.arange(nb, dtype=np.uint64)
     c2 = uid if noseed else 0
     c3 = (STREAM_SIM << 28) | ((rep & 0x0FFFFFFF) if noseed else 0)
     r = philox(j, k, c2, c3, seed_sim & MASK, seed_sim >> 32)
-    if transform == "zig":      # MvNormal objectives
-        z0, z1 = zig_normals(r[0], r[1]), zig_normals(r[2], r[3])
-    else:                       # dynamic panel
-        z0, z1 = normal_pairs(*r)
+    if transform == "zig":      # MvNormal objectives: three draws per block
+        w = r[3]
+        sel = [(w >> np.uint64(3)) & np.uint64(0x3FF), (w >> np.uint64(13)) & np.uint64(0x3FF),
+               ((w >> np.uint64(23)) | (w << np.uint64(9))) & np.uint64(0x3FF)]
+        zs = [zig_normals(r[t], sel[t]) for t in range(3)]
+        return np.stack(zs, axis=1).reshape(-1)[:S]
+    z0, z1 = normal_pairs(*r)  # dynamic panel
     return np.stack([z0, z1], axis=1).reshape(-1)[:S]
 
 

@@ -67,18 +67,21 @@ struct MProb {
 };
 
 // ---- the simulator streams -----------------------------------------------------------------------
-// Z[k, s] for s in [0, S): normal #(s&1) of block (j = s>>1, row k).  The transform is part of the simulator:
-// ziggurat (smm_zig_pair, the algorithm behind Julia's randn) for the MvNormal objectives, Box-Muller
-// (smm_normal_pair) for the dynamic panel.
+// Z[k, s] for s in [0, S).  The transform is part of the simulator: ziggurat for the MvNormal objectives (the
+// algorithm behind Julia's randn; three normals per Philox block: Z[k, 3j + t] = draw t of block (j, row k),
+// smm_zig_triple), Box-Muller for the dynamic panel (two per block: Z[k, 2j + t], smm_normal_pair).
 void fill_normals_row(const MProb &m, uint32_t k, int S, uint32_t uid, uint32_t rep, double *out) {
-  const bool zig = m.objective != SMM_OBJ_PANEL;
+  if (m.objective != SMM_OBJ_PANEL) {
+    for (int j = 0; 3 * j < S; ++j) {
+      double z[3];
+      smm_zig_triple(smm_sim_block(m.seed_sim, (uint32_t)j, k, m.noseed, uid, rep), z);
+      for (int t = 0; t < 3 && 3 * j + t < S; ++t) out[3 * j + t] = z[t];
+    }
+    return;
+  }
   for (int j = 0; 2 * j < S; ++j) {
     double z0, z1;
-    const smm_u32x4 r = smm_sim_block(m.seed_sim, (uint32_t)j, k, m.noseed, uid, rep);
-    if (zig)
-      smm_zig_pair(r, &z0, &z1);
-    else
-      smm_normal_pair(r, &z0, &z1);
+    smm_normal_pair(smm_sim_block(m.seed_sim, (uint32_t)j, k, m.noseed, uid, rep), &z0, &z1);
     out[2 * j] = z0;
     if (2 * j + 1 < S) out[2 * j + 1] = z1;
   }
@@ -689,23 +692,24 @@ void smm_oracle_normal_from_words(uint32_t x, uint32_t y, uint32_t z, uint32_t w
   smm_u32x4 r = {x, y, z, w};
   smm_normal_pair(r, &out[0], &out[1]);
 }
-void smm_oracle_zig_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, double *out) {
-  for (int j = 0; j < n_pairs; ++j)
-    smm_zig_pair(smm_philox4x32_10((uint32_t)j, k, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32)), &out[2 * j],
-                 &out[2 * j + 1]);
+// out[3 * n_blocks]: the three ziggurat normals of Philox blocks (j, k, c2, c3), j < n_blocks
+void smm_oracle_zig_normals(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_blocks, double *out) {
+  for (int j = 0; j < n_blocks; ++j)
+    smm_zig_triple(smm_philox4x32_10((uint32_t)j, k, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32)), &out[3 * j]);
 }
-// one ziggurat normal from its 64 bits; *slow = 1 when the fast path rejected the candidate
-double smm_oracle_zig_from_words(uint32_t a, uint32_t b, int *slow) {
+// one ziggurat normal from its 32-bit uniform and 10-bit select field; *slow = 1 when the fast path rejected the candidate
+double smm_oracle_zig_from_words(uint32_t u, uint32_t sel, int *slow) {
   int ok;
-  const double z = smm_zig_fast(a, b, smm_zigtab(), &ok);
+  const double z = smm_zig_fast(u, sel, smm_zigtab(), &ok);
   if (slow) *slow = !ok;
-  return ok ? z : smm_zig_slow(a, b, smm_zigtab(), smm_logtab());
+  return ok ? z : smm_zig_slow(u, sel, smm_zigtab(), smm_logtab());
 }
+uint32_t smm_oracle_zig_select(uint32_t w, int t) { return smm_zig_select(w, t); }
 double smm_oracle_exp_neg(double t) { return smm_exp_neg(t); }
 
 // "Reference-speed proxy" (BASELINE.md section 3, B-proxy): the objective's data flow exactly as the reference has it
 // (ObjExamples.jl:76-101: materialise the D x S Float64 draw matrix, then reduce it to means and variances) with the
-// kind of generator Julia's randn is -- xoshiro256++ state in registers + a 256-layer ziggurat, libm exp/log in the
+// kind of generator Julia's randn is -- xoshiro256++ state in registers + a ziggurat (one 64-bit word per normal), libm exp/log in the
 // rare branch.  NOT stream compatible with anything: it only answers "how fast would the CPU path be if its normals
 // were as cheap as Julia's", so that the reported CPU baseline is not handicapped by the counter-based streams.
 // Returns evaluations per second summed over n_threads threads (each thread evaluates n_evals_per_thread times).
@@ -735,11 +739,12 @@ double smm_oracle_proxy_rate(int D, int S, int n_evals_per_thread, int n_threads
         for (;;) {
           uint64_t r;
           SMM_XOSHIRO_NEXT(r);
-          const uint32_t i = (uint32_t)(r >> 55) & 0xFFu;
-          const double u = (double)(r & 0xFFFFFFFFFFFFFull) * 0x1.0p-52, x = u * tab[i].w;
+          const uint32_t i = (uint32_t)(r >> 32) & (SMM_ZIG_LAYERS - 1u);
+          const double x = (double)(uint32_t)r * smm_bits_to_double(tab[i]);
           z = (r >> 63) ? -x : x;
-          if (__builtin_expect((uint32_t)((r >> 32) & 0xFFFFFu) < (tab[i].kh & 0xFFFFFu), 1)) break;
+          if (__builtin_expect((uint32_t)r < ((uint32_t)tab[i] << 20), 1)) break;
           if (i == 0) {
+            if (x < SMM_ZIG_R) break;
             for (;;) {
               uint64_t a, b;
               SMM_XOSHIRO_NEXT(a);

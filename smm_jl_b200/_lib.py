@@ -260,11 +260,11 @@ class BGPHandle:
         check(lib().smm_debug_barrier_bench(self._h, variant, n, C.byref(ms)))
         return ms.value * 1e3 / n
 
-    def sim_throughput(self, n_pairs_per_thread: int, blocks: int, threads: int, dynamic: bool):
-        """the simulate inner loop alone: returns (ms, normals/s)"""
+    def sim_throughput(self, n_blocks_per_thread: int, blocks: int, threads: int, dynamic: bool):
+        """the simulate inner loop alone (three normals per Philox block): returns (ms, normals/s)"""
         ms = C.c_float(0.0)
-        check(lib().smm_debug_sim_throughput(self._h, n_pairs_per_thread, blocks, threads, int(dynamic), C.byref(ms)))
-        return ms.value, 2.0 * n_pairs_per_thread * blocks * threads / (ms.value * 1e-3)
+        check(lib().smm_debug_sim_throughput(self._h, n_blocks_per_thread, blocks, threads, int(dynamic), C.byref(ms)))
+        return ms.value, 3.0 * n_blocks_per_thread * blocks * threads / (ms.value * 1e-3)
 
     def export_state(self) -> bytes:
         n = lib().smm_bgp_state_bytes(self._h)
@@ -298,10 +298,10 @@ def debug_normals(seed: int, k: int, c2: int, c3: int, n_pairs: int, device: int
     return out
 
 
-def debug_zig_normals(seed: int, k: int, c2: int, c3: int, n_pairs: int, device: int = 0) -> np.ndarray:
-    """device evaluation of smm_zig_pair on Philox blocks (j, k, c2, c3), j < n_pairs"""
-    out = np.zeros(2 * n_pairs)
-    check(lib().smm_debug_zig_normals(device, seed, k, c2, c3, n_pairs, out.ctypes.data_as(C.POINTER(C.c_double))))
+def debug_zig_normals(seed: int, k: int, c2: int, c3: int, n_blocks: int, device: int = 0) -> np.ndarray:
+    """device evaluation of smm_zig_triple on Philox blocks (j, k, c2, c3), j < n_blocks: 3 * n_blocks normals"""
+    out = np.zeros(3 * n_blocks)
+    check(lib().smm_debug_zig_normals(device, seed, k, c2, c3, n_blocks, out.ctypes.data_as(C.POINTER(C.c_double))))
     return out
 
 

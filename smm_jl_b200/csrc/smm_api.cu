@@ -424,7 +424,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   } prop;  // (cudaGetDeviceProperties costs milliseconds; one attribute is all that is needed)
   CUDA_TRY(cudaDeviceGetAttribute(&prop.multiProcessorCount, cudaDevAttrMultiProcessorCount, cfg->device));
   h->part_len = 2 * P;
-  const int n_blocks_philox = (cfg->n_sim + 1) / 2;
+  const int n_blocks_philox = zig_blocks(cfg->n_sim);  // Philox blocks per simulated row (three draws each)
   h->n_split = choose_split(L, prop.multiProcessorCount, eval_max_blocks_per_sm(), n_blocks_philox, cfg->n_split);
   if (cfg->objective_id == SMM_OBJ_FAILS) h->n_split = 1;
   h->panel = cfg->objective_id == SMM_OBJ_PANEL;
@@ -490,8 +490,9 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   pb.seed_sim = cfg->seed_sim; pb.seed_algo = cfg->seed_algo;
   {
     // fixed-point grids of the order-invariant accumulators (smm_kernels.cu): |x| <= xmax = box + 14 sigma-units
-    // (a ziggurat draw is at most R + 52 ln2 / R < 13.6 in magnitude),
-    // totals S*xmax and S*xmax^2 must stay below 2^62, single terms below 2^(51-F) (4x headroom for eval_batch)
+    // (a ziggurat draw is at most R + 52 ln2 / R < 13.3 in magnitude),
+    // totals S*xmax and S*xmax^2 must stay below 2^62, single terms -- the sums of a block's three values -- below
+    // 2^(51-F) (4x headroom for eval_batch)
     double box = 0.0;
     for (int k = 0; k < P; ++k) {
       box = std::fmax(box, std::fabs(cfg->lb[k]));
@@ -500,7 +501,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     const double xmax = 4.0 * (box + 14.0);
     auto pick = [&](double term_max) {
       int f_total = 62 - (int)std::ceil(std::log2((double)cfg->n_sim * term_max));
-      int f_term = 51 - (int)std::ceil(std::log2(term_max));
+      int f_term = 51 - (int)std::ceil(std::log2(SMM_ZIG_PER_BLOCK * term_max));
       int f = f_total < f_term ? f_total : f_term;
       return f > 60 ? 60 : f;
     };
@@ -1085,12 +1086,13 @@ int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes) {
 static int debug_normals_impl(int32_t device, uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int32_t n_pairs,
                               int zig, double *out) {
   if (!out || n_pairs < 1) return fail(SMM_E_ARG, "bad argument");
+  const size_t per = zig ? SMM_ZIG_PER_BLOCK : 2;  // normals per Philox block
   if (smm_device_count() <= device) return fail(SMM_E_CUDA, "no such CUDA device");
   CUDA_TRY(cudaSetDevice(device));
   DevBuf<double> d;
-  CUDA_TRY(d.alloc((size_t)2 * n_pairs, true));
+  CUDA_TRY(d.alloc(per * n_pairs, true));
   launch_debug_normals(seed, k, c2, c3, n_pairs, zig, d.p, 0);
-  cudaError_t e = cudaMemcpy(out, d.p, sizeof(double) * 2 * n_pairs, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(out, d.p, sizeof(double) * per * n_pairs, cudaMemcpyDeviceToHost);
   d.free();
   CUDA_TRY(e);
   return 0;

@@ -21,6 +21,9 @@ constexpr int kPanelMaxK = 16;      // regressors of the dynamic-panel objective
 // pooled raw sums of the dynamic-panel objective (see smm_panel.cuh): 14 for y, 6 per regressor
 __host__ __device__ inline int panel_na(int K) { return 14 + 6 * K; }
 
+// Philox blocks per simulated row of a ziggurat objective: three draws per block (include/smm_stream.h)
+__host__ __device__ inline int zig_blocks(int S) { return (S + SMM_ZIG_PER_BLOCK - 1) / SMM_ZIG_PER_BLOCK; }
+
 // Last-accepted record of a chain, one row of R = 3 + P + M doubles:
 //   [0] value  [1] prob  [2] status (as double)  [3..3+P) params  [3+P..3+P+M) simMoments
 __host__ __device__ inline int rec_len(int P, int M) { return 3 + P + M; }

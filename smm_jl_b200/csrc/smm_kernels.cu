@@ -246,175 +246,294 @@ struct Acc {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Zsim of the MvNormal objectives is a ziggurat (include/smm_stream.h): 98.5 % of the draws take the FAST path
-// (one 16-byte table entry from shared memory, 4 integer ops, one DFMA).  The rest -- wedge test with exp, tail
-// with two logs, retries -- would cost every warp a divergent detour on more than half of its steps, so it is
-// DEFERRED: the fast path always accumulates its candidate; a lane whose candidate was not accepted pushes the
-// 64 random bits and the row onto its warp's queue (ballot + popc), and when 32 entries have gathered the whole
-// warp runs smm_zig_slow on them, one entry per lane, and adds [pattern(true x) - pattern(candidate x)] to the
-// accumulators with 64-bit integer atomics.  Integer accumulation is exact and order-free, so the totals are
-// bit-identical to the sequential definition (oracle: smm_zig_pair draw by draw).
+// Zsim of the MvNormal objectives is a ziggurat (include/smm_stream.h): ONE Philox block gives THREE normals, and
+// 99.2 % of the draws take the FAST path (one 8-byte table entry from shared memory, a shift, a compare, two fp64
+// operations).  The rest -- wedge test with exp, tail with two logs, retries -- would cost every warp a divergent detour
+// on half of its steps, so it is DEFERRED: the fast path always accumulates its candidates; a lane whose block holds a
+// rejected candidate pushes the block's index onto its warp's queue (ballot + popc, two stores), and when 32 entries
+// have gathered the whole warp re-derives those blocks, one per lane, resolves them with smm_zig_normal_tab and adds
+// [pattern(true block sums) - pattern(candidate block sums)] to the accumulators with 64-bit integer atomics.
+// Integer accumulation is exact and order-free, so the totals are those of the sequential definition.
+//
+// BLOCK-WISE ACCUMULATION.  The three values X = p + Z of a block are summed in double, in stream order,
+//   s = fl(fl(X0 + X1) + X2),  q = fl(fma(X2, X2, fl(fma(X1, X1, fl(X0 X0)))))      (missing draws of the last block: +0)
+// and s, q are what is rounded to the fixed-point grid -- a block always lives in one lane, so this is as independent of
+// the work split as a per-draw rounding, at a third of the integer adds.
 // ------------------------------------------------------------------------------------------------
-constexpr int kZigQCap = 96;                  // entries per warp: < 32 before a step, <= 95 after its two pushes
-constexpr int kZigQWords = 3 * kZigQCap;      // a[], b[], row[]
-constexpr int kZigSigned = 2 * SMM_ZIG_LAYERS;  // shared-memory table: one entry per (sign, layer)
+constexpr int kZigQCap = 64;                    // entries per warp: < 32 before a step, <= 63 after its push
+constexpr int kZigQWords = 2 * kZigQCap;        // j[], kpack[]
+constexpr int kZigSigned = 2 * SMM_ZIG_LAYERS;  // shared-memory table: one 8-byte entry per (sign, layer)
 
 // Everything the hot loop needs lives in 32-bit registers (shared-window addresses, not generic pointers).
 struct ZigCtx {
-  uint32_t ztab;  // shared address of the signed layer table: entry (a >> 23) = {+-W[i], kh[i]}, on an 8 KB boundary
-  uint32_t c3ff;  // 0x3FF00000 held in a register (so that (a & 0xFFFFF) | 0x3FF00000 is ONE LOP3)
+  uint32_t ztab;  // shared address of the signed layer table: entry s = {+-W'[i] 2^-32 | KH[i]}, on an 8 KB boundary
   uint32_t q;     // shared address of this warp's queue
   uint32_t lt;    // %lanemask_lt
   uint32_t pvec;  // shared address: [D] parameters of the evaluation being simulated (f64)
   uint32_t fix;   // shared address: [2D] u64 where corrections are added
+  uint32_t c2, c3;  // counter words 2, 3 of the blocks being simulated (what the drain needs to re-derive a block)
   int D;
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// The signed copy of the layer table (index = sign << 8 | layer; -W for negative draws, so the sign costs nothing)
-// must start on an 8 KB boundary of the shared window, because zig_fast_dev forms entry addresses with OR.  A
-// declared __align__(8192) is not enough: static shared memory starts 1 KB into the window on sm_100, and the
-// compiler aligns relative to that.  So the kernels reserve 16 KB and use the aligned half.
+// The signed copy of the layer table (index = sign << 9 | layer; the sign bit is set in the entries of the upper half, so
+// the sign costs nothing) must start on an 8 KB boundary of the shared window, because zig_fast_dev forms entry
+// addresses with OR.  A declared __align__(8192) is not enough: static shared memory starts 1 KB into the window on
+// sm_100, and the compiler aligns relative to that.  So the kernels reserve 16 KB and use the aligned half.
 constexpr int kZigBufEntries = 2 * kZigSigned;
-__device__ __forceinline__ uint32_t zig_table_addr(const uint4 *buf) { return (smem_addr(buf) + 8191u) & ~8191u; }
-__device__ __forceinline__ void load_zigtab(uint4 *buf) {
-  uint4 *dst = buf + (zig_table_addr(buf) - smem_addr(buf)) / 16u;
-  const uint4 *src = reinterpret_cast<const uint4 *>(smm_zigtab());
-  for (int i = threadIdx.x; i < kZigSigned; i += blockDim.x) {
-    uint4 e = src[i & (SMM_ZIG_LAYERS - 1)];
-    if (i >= SMM_ZIG_LAYERS) e.y ^= 0x80000000u;
-    dst[i] = e;
-  }
+static_assert(kZigSigned * 8 == 8192, "address masks below assume an 8 KB table");
+__device__ __forceinline__ uint32_t zig_table_addr(const unsigned long long *buf) { return (smem_addr(buf) + 8191u) & ~8191u; }
+__device__ __forceinline__ void load_zigtab(unsigned long long *buf) {
+  unsigned long long *dst = buf + (zig_table_addr(buf) - smem_addr(buf)) / 8u;
+  const smm_zigent *src = smm_zigtab();
+  for (int i = threadIdx.x; i < kZigSigned; i += blockDim.x)
+    dst[i] = src[i & (SMM_ZIG_LAYERS - 1)] | (i >= SMM_ZIG_LAYERS ? 0x8000000000000000ull : 0ull);
 }
-// `opaque` is any kernel argument known to be non-negative: OR-ing its sign bit into the constants keeps ptxas from
-// folding them back into immediates (a LOP3 takes one immediate; with both operands in registers the mask-and-merge
-// of the fast path is a single instruction)
-__device__ __forceinline__ ZigCtx zig_ctx(const uint4 *zbuf, uint32_t *q_warp, int opaque) {
+// `opaque` is any kernel argument known to be non-negative: OR-ing its sign bit into the table address keeps ptxas from
+// folding it back into an immediate (a LOP3 takes one immediate; with the base in a register the mask-and-merge of the
+// entry address is a single instruction)
+__device__ __forceinline__ ZigCtx zig_ctx(const unsigned long long *zbuf, uint32_t *q_warp, int opaque) {
   ZigCtx cx;
   const uint32_t zero = (uint32_t)opaque >> 31;
   cx.ztab = zig_table_addr(zbuf) | zero;
-  cx.c3ff = 0x3FF00000u | zero;
   cx.q = smem_addr(q_warp);
   asm volatile("" : "+r"(cx.q));  // opaque: keep the address in a register instead of recomputing it from %tid per push
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(cx.lt));
   cx.pvec = 0;
   cx.fix = 0;
+  cx.c2 = 0;
+  cx.c3 = 0;
   cx.D = 0;
   return cx;
 }
 
-// candidate of the fast path (same value as smm_zig_fast) and whether it is final:
-// SHF, LOP3, LDS.128, LOP3, DFMA, ISETP
-__device__ __forceinline__ double zig_fast_dev(uint32_t a, uint32_t b, const ZigCtx &cx, bool &ok) {
-  uint32_t addr, hi, e0, e1, e2, e3;  // e3: padding word of the entry
-  asm("lop3.b32 %0, %1, 0x1FF0, %2, 0xEA;" : "=r"(addr) : "r"(a >> 19), "r"(cx.ztab));
-  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3) : "r"(addr));
-  asm("lop3.b32 %0, %1, 0xFFFFF, %2, 0xEA;" : "=r"(hi) : "r"(a), "r"(cx.c3ff));
-  const double w = __hiloint2double((int)e1, (int)e0);
-  ok = hi < e2;
-  return __fma_rn(__hiloint2double((int)hi, (int)b), w, -w);
+// candidate of the fast path (same value as smm_zig_fast) and whether it is final.  `sel8` carries the draw's select
+// field (sign, layer) in bits 3..12, anything elsewhere:  LOP3, LDS.64, SHF, ISETP, DADD, DMUL
+__device__ __forceinline__ double zig_fast_dev(uint32_t u, uint32_t sel8, const ZigCtx &cx, bool &ok) {
+  uint32_t addr, e0, e1;
+  asm("lop3.b32 %0, %1, 0x1FF8, %2, 0xEA;" : "=r"(addr) : "r"(sel8), "r"(cx.ztab));
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0), "=r"(e1) : "r"(addr));
+  ok = u < (e0 << 20);
+  const double t = __dsub_rn(__hiloint2double(0x43300000, (int)u), 4503599627370496.0);  // (double)u, exactly
+  return __dmul_rn(t, __hiloint2double((int)e1, (int)e0));
 }
 
-// the warp resolves `cnt` (<= 32) queued draws starting at entry `first`
-__device__ __noinline__ void zig_drain(const ZigCtx cx, double magic_sum, double magic_sq, int first, int cnt) {
+// block sums of three values (see BLOCK-WISE ACCUMULATION above)
+__device__ __forceinline__ void block_sums(double x0, double x1, double x2, double &s, double &q) {
+  s = __dadd_rn(__dadd_rn(x0, x1), x2);
+  q = __fma_rn(x2, x2, __fma_rn(x1, x1, __dmul_rn(x0, x0)));
+}
+
+// the warp resolves `cnt` (<= 32) queued blocks starting at entry `first`
+__device__ __noinline__ void zig_drain(const DevProblem &pb, const ZigCtx cx, int first, int cnt) {
   const int lane = threadIdx.x & 31;
   if (lane < cnt) {
-    uint32_t a, b, kk;
+    uint32_t j, kp;
     const uint32_t qa = cx.q + 4u * (uint32_t)(first + lane);
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(qa) : "memory");
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(b) : "r"(qa), "n"(4 * kZigQCap) : "memory");
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(kk) : "r"(qa), "n"(8 * kZigQCap) : "memory");
-    bool ok;
-    const double zf = zig_fast_dev(a, b, cx, ok);
-    const double zs = smm_zig_slow(a, b, smm_zigtab(), smm_logtab());  // global tables: this path is rare
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(j) : "r"(qa) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(kp) : "r"(qa), "n"(4 * kZigQCap) : "memory");
+    const uint32_t kk = kp & 0xFFu, nact = kp >> 8;
+    const smm_u32x4 r = smm_philox4x32_10(j, kk, cx.c2, cx.c3, (uint32_t)pb.seed_sim, (uint32_t)(pb.seed_sim >> 32));
     double p;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(p) : "r"(cx.pvec + 8u * kk) : "memory");
-    const double xf = __dadd_rn(p, zf), xs = __dadd_rn(p, zs);
-    const unsigned long long dsum = (unsigned long long)__double_as_longlong(__dadd_rn(xs, magic_sum)) -
-                                    (unsigned long long)__double_as_longlong(__dadd_rn(xf, magic_sum));
-    const unsigned long long dsq = (unsigned long long)__double_as_longlong(__fma_rn(xs, xs, magic_sq)) -
-                                   (unsigned long long)__double_as_longlong(__fma_rn(xf, xf, magic_sq));
+    const uint32_t uu[3] = {r.x, r.y, r.z};
+    double xf[3], xs[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      int ok;
+      const uint32_t sel = smm_zig_select(r.w, t);
+      const double zf = smm_zig_fast(uu[t], sel, smm_zigtab(), &ok);  // global tables: this path is rare
+      const double zs = ok ? zf : smm_zig_slow(uu[t], sel, smm_zigtab(), smm_logtab());
+      const bool act = (uint32_t)t < nact;
+      xf[t] = act ? __dadd_rn(p, zf) : 0.0;
+      xs[t] = act ? __dadd_rn(p, zs) : 0.0;
+    }
+    double sf, qf, ss, qs;
+    block_sums(xf[0], xf[1], xf[2], sf, qf);
+    block_sums(xs[0], xs[1], xs[2], ss, qs);
+    const unsigned long long dsum = (unsigned long long)__double_as_longlong(__dadd_rn(ss, pb.magic_sum)) -
+                                    (unsigned long long)__double_as_longlong(__dadd_rn(sf, pb.magic_sum));
+    const unsigned long long dsq = (unsigned long long)__double_as_longlong(__dadd_rn(qs, pb.magic_sq)) -
+                                   (unsigned long long)__double_as_longlong(__dadd_rn(qf, pb.magic_sq));
     asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(cx.fix + 8u * kk), "l"(dsum) : "memory");
     asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(cx.fix + 8u * ((uint32_t)cx.D + kk)), "l"(dsq) : "memory");
   }
   __syncwarp();
 }
 
-__device__ __forceinline__ void zig_store(uint32_t qa, uint32_t a, uint32_t b, uint32_t k) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(a) : "memory");
-  asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(qa), "r"(b), "n"(4 * kZigQCap) : "memory");
-  asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(qa), "r"(k), "n"(8 * kZigQCap) : "memory");
-}
 // between steps: bring the queue back below 32 entries (full warps of work only)
-__device__ __forceinline__ void zig_relieve(const ZigCtx &cx, int &qn, double magic_sum, double magic_sq) {
+__device__ __forceinline__ void zig_relieve(const DevProblem &pb, const ZigCtx &cx, int &qn) {
   while (qn >= 32) {
     __syncwarp();
-    zig_drain(cx, magic_sum, magic_sq, qn - 32, 32);
+    zig_drain(pb, cx, qn - 32, 32);
     qn -= 32;
   }
 }
-__device__ __forceinline__ void zig_flush(const ZigCtx &cx, int &qn, double magic_sum, double magic_sq) {
-  zig_relieve(cx, qn, magic_sum, magic_sq);
+__device__ __forceinline__ void zig_flush(const DevProblem &pb, const ZigCtx &cx, int &qn) {
+  zig_relieve(pb, cx, qn);
   if (qn > 0) {
     __syncwarp();
-    zig_drain(cx, magic_sum, magic_sq, 0, qn);
+    zig_drain(pb, cx, 0, qn);
     qn = 0;
   }
 }
 
-// One Philox block of row k: X = p + Z for its two draws, added to the accumulators.  Called by all 32 lanes of
-// a warp; act0/act1 say whether this lane's two draws count (kMasked = false: both always do).  Needs qn < 32 on
-// entry; the caller runs zig_relieve between steps (kept out of here so that hot loops contain no call).
+// Philox4x32-10 of the simulator stream with the 20 round keys of seed_sim held in registers
+struct SimKeys {
+  uint32_t a[10], b[10];
+};
+__device__ __forceinline__ smm_u32x4 philox_keys(const SimKeys &ks, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)SMM_PHILOX_M0 * c0;
+    const uint64_t p1 = (uint64_t)SMM_PHILOX_M1 * c2;
+    c0 = (uint32_t)(p1 >> 32) ^ c1 ^ ks.a[r];
+    c1 = (uint32_t)p1;
+    c2 = (uint32_t)(p0 >> 32) ^ c3 ^ ks.b[r];
+    c3 = (uint32_t)p0;
+  }
+  smm_u32x4 out;
+  out.x = c0;
+  out.y = c1;
+  out.z = c2;
+  out.w = c3;
+  return out;
+}
+__device__ __forceinline__ SimKeys sim_keys(const DevProblem &pb) {
+  SimKeys ks;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    ks.a[r] = pb.rk_sim0[r];
+    ks.b[r] = pb.rk_sim1[r];
+  }
+  return ks;
+}
+// the same keys parked in shared memory ([20] u32, 16-byte aligned) for the out-of-line hot loop
+__device__ __forceinline__ void store_keys(const DevProblem &pb, uint32_t *dst) {
+  if (threadIdx.x < 10) dst[threadIdx.x] = pb.rk_sim0[threadIdx.x];
+  else if (threadIdx.x < 20) dst[threadIdx.x] = pb.rk_sim1[threadIdx.x - 10];
+}
+__device__ __forceinline__ SimKeys load_keys(uint32_t keys_s) {
+  uint32_t w[20];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[4 * i]), "=r"(w[4 * i + 1]), "=r"(w[4 * i + 2]), "=r"(w[4 * i + 3])
+                 : "r"(keys_s + 16u * i));
+  SimKeys ks;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    ks.a[r] = w[r];
+    ks.b[r] = w[10 + r];
+  }
+  return ks;
+}
+
+// One Philox block of row k: X = p + Z for its three draws, block-summed and added to the accumulators.  Called by all
+// 32 lanes of a warp; nact = how many of this lane's draws count (kMasked = false: all three always do; 0 = the lane
+// sits this step out).  Needs qn < 32 on entry; the caller resolves the queue between steps (kept out of here so that
+// hot loops contain no call).  kpack = k | nact << 8 is what the queue stores next to j.
 template <bool kMasked>
-__device__ __forceinline__ void add_pair(const DevProblem &pb, const ZigCtx &cx, int &qn, Acc &a, double p, uint32_t j,
-                                         uint32_t k, uint32_t c2, uint32_t c3, bool act0, bool act1) {
-  const smm_u32x4 r = philox_sim(pb, j, k, c2, c3);
-  bool ok0, ok1;
-  const double x0 = __dadd_rn(p, zig_fast_dev(r.x, r.y, cx, ok0));
-  const double x1 = __dadd_rn(p, zig_fast_dev(r.z, r.w, cx, ok1));
-  const unsigned long long s0 = (unsigned long long)__double_as_longlong(__dadd_rn(x0, pb.magic_sum));
-  const unsigned long long q0 = (unsigned long long)__double_as_longlong(__fma_rn(x0, x0, pb.magic_sq));
-  const unsigned long long s1 = (unsigned long long)__double_as_longlong(__dadd_rn(x1, pb.magic_sum));
-  const unsigned long long q1 = (unsigned long long)__double_as_longlong(__fma_rn(x1, x1, pb.magic_sq));
-  bool slow0 = !ok0, slow1 = !ok1;
+__device__ __forceinline__ void add_block(const SimKeys &ks, double magic_sum, double magic_sq, const ZigCtx &cx, int &qn,
+                                          Acc &a, double p, uint32_t j, uint32_t k, uint32_t kpack, int nact) {
+  const smm_u32x4 r = philox_keys(ks, j, k, cx.c2, cx.c3);
+  bool ok0, ok1, ok2;
+  double x0 = __dadd_rn(p, zig_fast_dev(r.x, r.w, cx, ok0));
+  double x1 = __dadd_rn(p, zig_fast_dev(r.y, r.w >> 10, cx, ok1));
+  double x2 = __dadd_rn(p, zig_fast_dev(r.z, __funnelshift_l(r.w, r.w, 12), cx, ok2));
+  bool slow = !(ok0 && ok1 && ok2);
   if (kMasked) {
-    if (act0) {
-      a.sum += s0;
-      a.sq += q0;
+    if (nact < 3) {
+      x2 = 0.0;
+      ok2 = true;
     }
-    if (act1) {
-      a.sum += s1;
-      a.sq += q1;
+    if (nact < 2) {
+      x1 = 0.0;
+      ok1 = true;
     }
-    slow0 = slow0 && act0;
-    slow1 = slow1 && act1;
-  } else {
-    a.sum += s0 + s1;
-    a.sq += q0 + q1;
+    slow = nact > 0 && !(ok0 && ok1 && ok2);
   }
-  if (__any_sync(0xffffffffu, slow0 || slow1)) {  // 62 % of the steps: some lane of the 64 draws left the fast path
-    const unsigned m0 = __ballot_sync(0xffffffffu, slow0), m1 = __ballot_sync(0xffffffffu, slow1);
-    const int n0 = __popc(m0);
-    const uint32_t base = cx.q + 4u * (uint32_t)qn;
-    if (slow0) zig_store(base + 4u * (uint32_t)__popc(m0 & cx.lt), r.x, r.y, k);
-    if (slow1) zig_store(base + 4u * (uint32_t)(n0 + __popc(m1 & cx.lt)), r.z, r.w, k);
-    qn += n0 + __popc(m1);
+  double s, q;
+  block_sums(x0, x1, x2, s, q);
+  const unsigned long long sb = (unsigned long long)__double_as_longlong(__dadd_rn(s, magic_sum));
+  const unsigned long long qb = (unsigned long long)__double_as_longlong(__dadd_rn(q, magic_sq));
+  if (!kMasked || nact > 0) {
+    a.sum += sb;
+    a.sq += qb;
   }
+  if (__any_sync(0xffffffffu, slow)) {  // half of the steps: some lane's block holds a candidate that left the fast path
+    const unsigned m = __ballot_sync(0xffffffffu, slow);
+    if (slow) {
+      const uint32_t qa = cx.q + 4u * (uint32_t)(qn + __popc(m & cx.lt));
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(j) : "memory");
+      asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(qa), "r"(kpack), "n"(4 * kZigQCap) : "memory");
+    }
+    qn += __popc(m);
+  }
+}
+
+// THE HOT LOOP, out of line so that it is register-allocated on its own (the persistent kernel around it carries far
+// too much state): up to n_steps warp steps of row k, blocks j, j + dj, ...; it stops early when 32 deferred blocks have
+// gathered (the caller drains them and comes back).  The round keys travel through shared memory into 20 registers.
+struct SimRet {
+  unsigned long long sum, sq;
+  int done, qn;
+};
+__device__ __noinline__ SimRet sim_steps_full(uint32_t keys_s, uint32_t ztab, uint32_t q_s, uint32_t c2, uint32_t c3, double p,
+                                              double magic_sum, double magic_sq, uint32_t j, uint32_t dj, int n_steps,
+                                              uint32_t kpack3, int qn, unsigned long long sum, unsigned long long sq) {
+  const SimKeys ks = load_keys(keys_s);
+  ZigCtx cx;
+  cx.ztab = ztab;
+  cx.q = q_s;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(cx.lt));
+  cx.c2 = c2;
+  cx.c3 = c3;
+  cx.pvec = cx.fix = 0;
+  cx.D = 0;
+  Acc a{sum, sq};
+  const uint32_t k = kpack3 & 0xFFu;
+  int q = 0;
+#pragma unroll 1
+  for (; q < n_steps && qn < 32; ++q, j += dj) add_block<false>(ks, magic_sum, magic_sq, cx, qn, a, p, j, k, kpack3, 3);
+  return SimRet{a.sum, a.sq, q, qn};
+}
+// the same for steps in which lanes or draws are masked out: lane active iff lane_on and j < jlimit, with nact_on draws
+__device__ __noinline__ SimRet sim_steps_masked(uint32_t keys_s, uint32_t ztab, uint32_t q_s, uint32_t c2, uint32_t c3, double p,
+                                                double magic_sum, double magic_sq, uint32_t j, uint32_t dj, int n_steps,
+                                                uint32_t k, int qn, unsigned long long sum, unsigned long long sq,
+                                                bool lane_on, uint32_t jlimit, int nact_on) {
+  const SimKeys ks = load_keys(keys_s);
+  ZigCtx cx;
+  cx.ztab = ztab;
+  cx.q = q_s;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(cx.lt));
+  cx.c2 = c2;
+  cx.c3 = c3;
+  cx.pvec = cx.fix = 0;
+  cx.D = 0;
+  Acc a{sum, sq};
+  int q = 0;
+#pragma unroll 1
+  for (; q < n_steps && qn < 32; ++q, j += dj) {
+    const int nact = (lane_on && j < jlimit) ? nact_on : 0;
+    add_block<true>(ks, magic_sum, magic_sq, cx, qn, a, p, j, k, k | ((uint32_t)nact << 8), nact);
+  }
+  return SimRet{a.sum, a.sq, q, qn};
 }
 
 // Static mapping, any D <= g.n: thread t owns row k = t % D and blocks j0 + t/D, +lanes, ...
 // zt: the 16 KB buffer holding the signed layer table (shared); red: shared [2 * g.n] u64; zfix: shared [2 * D] u64 (zeroed
 // here); zq: shared [g.n / 32][kZigQWords]; pp: shared.
 // Writes the group's partial sums [2][D] (u64 patterns) to `part`.
-__device__ void simulate_static(const DevProblem &pb, const Grp &g, const uint4 *zt, const double *pp, int j0, int j1,
-                                uint32_t uid, uint32_t rep, unsigned long long *red, unsigned long long *zfix,
+__device__ void simulate_static(const DevProblem &pb, const Grp &g, const unsigned long long *zt, const double *pp, int j0,
+                                int j1, uint32_t uid, uint32_t rep, unsigned long long *red, unsigned long long *zfix,
                                 uint32_t *zq, double *part) {
   const int D = pb.P, S = pb.S, tid = g.tid;
   const int lanes = g.n / D;
-  const int n_full = S >> 1;  // blocks whose two normals are both used
-  const uint32_t c2 = pb.noseed ? uid : 0u;
-  const uint32_t c3 = (SMM_STREAM_SIM << 28) | (pb.noseed ? (rep & SMM_ITER_MASK) : 0u);
+  const int n_full = S / 3;      // blocks whose three normals are all used
+  const int n_tail = S - 3 * n_full;  // draws of the last, partial block (0 = there is none)
   for (int e = tid; e < 2 * D; e += g.n) zfix[e] = 0ull;
   gsync(g);
   Acc a{0ull, 0ull};
@@ -422,22 +541,27 @@ __device__ void simulate_static(const DevProblem &pb, const Grp &g, const uint4 
   cx.pvec = smem_addr(pp);
   cx.fix = smem_addr(zfix);
   cx.D = D;
+  cx.c2 = pb.noseed ? uid : 0u;
+  cx.c3 = (SMM_STREAM_SIM << 28) | (pb.noseed ? (rep & SMM_ITER_MASK) : 0u);
   int qn = 0;
+  const SimKeys ks = sim_keys(pb);
   const bool on = tid < lanes * D;
   const int k = tid % D, ln = tid / D;
   const double p = pp[k];
   const int jend = j1 < n_full ? j1 : n_full;
-  // every warp runs the same number of steps (the ballots inside add_pair need all 32 lanes)
+  // every warp runs the same number of steps (the ballots inside add_block need all 32 lanes)
   const int n_steps = jend > j0 ? (jend - j0 + lanes - 1) / lanes : 0;
   for (int t = 0; t < n_steps; ++t) {
     const int j = j0 + ln + t * lanes;
-    const bool act = on && j < jend;
-    add_pair<true>(pb, cx, qn, a, p, (uint32_t)j, (uint32_t)k, c2, c3, act, act);
-    if (qn >= 32) zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
+    const int nact = (on && j < jend) ? 3 : 0;
+    add_block<true>(ks, pb.magic_sum, pb.magic_sq, cx, qn, a, p, (uint32_t)j, (uint32_t)k, (uint32_t)k | ((uint32_t)nact << 8), nact);
+    if (qn >= 32) zig_relieve(pb, cx, qn);
   }
-  if ((S & 1) && j0 <= n_full && n_full < j1)  // odd S: the last block contributes one draw
-    add_pair<true>(pb, cx, qn, a, p, (uint32_t)n_full, (uint32_t)k, c2, c3, on && ln == 0, false);
-  zig_flush(cx, qn, pb.magic_sum, pb.magic_sq);
+  if (n_tail && j0 <= n_full && n_full < j1) {  // S not a multiple of 3: the last block contributes one or two draws
+    const int nact = (on && ln == 0) ? n_tail : 0;
+    add_block<true>(ks, pb.magic_sum, pb.magic_sq, cx, qn, a, p, (uint32_t)n_full, (uint32_t)k, (uint32_t)k | ((uint32_t)nact << 8), nact);
+  }
+  zig_flush(pb, cx, qn);
   red[2 * tid] = a.sum;
   red[2 * tid + 1] = a.sq;
   gsync(g);
@@ -476,10 +600,10 @@ __device__ void group_finalize(const DevProblem &pb, const Grp &g, const FinScra
     unsigned long long acc = 0ull;
     const unsigned long long *pu = (const unsigned long long *)part_base;
     for (int s = 0; s < n_seg; ++s) acc += __ldcg(pu + (size_t)s * part_len + e);
-    // remove S copies of bits(M) (mod 2^64: exact), then fixed point -> double
+    // remove one copy of bits(M) per block (mod 2^64: exact), then fixed point -> double
     const bool is_sq = e >= D;
     const unsigned long long mb = (unsigned long long)__double_as_longlong(is_sq ? pb.magic_sq : pb.magic_sum);
-    const long long fixed = (long long)(acc - (unsigned long long)pb.S * mb);
+    const long long fixed = (long long)(acc - (unsigned long long)zig_blocks(pb.S) * mb);
     fs.tot[e] = __dmul_rn((double)fixed, is_sq ? pb.scale_sq : pb.scale_sum);
   }
   gsync(g);
@@ -803,7 +927,7 @@ __device__ __forceinline__ FinScratch fin_scratch(EvalSmem &sm) {
 __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, DevState st, int iter, int n_split,
                                                                 int part_len) {
   __shared__ EvalSmem sm;
-  __shared__ uint4 s_zigtab[kZigBufEntries];  // 16 KB: the 8 KB-aligned half holds the table (see load_zigtab)
+  __shared__ unsigned long long s_zigtab[kZigBufEntries];  // 16 KB: the 8 KB-aligned half holds the table (see load_zigtab)
   const int c = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
   const int gc = pb.chain0 + c;
   const Grp g{tid, (int)blockDim.x, 0};
@@ -819,7 +943,7 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, D
     if (split != 0) return;
   } else {
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
-    const int nb = (pb.S + 1) >> 1;
+    const int nb = zig_blocks(pb.S);
     const int j0 = (int)(((long long)nb * split) / n_split), j1 = (int)(((long long)nb * (split + 1)) / n_split);
     simulate_static(pb, g, s_zigtab, sm.pp, j0, j1, (uint32_t)gc, (uint32_t)iter, sm.red, sm.zfix, sm.zq,
                     part_base + (size_t)split * part_len);
@@ -955,6 +1079,7 @@ constexpr int kMaxCtaSeg = 32;                   // chains (segments) one CTA ma
 
 struct PersistSmem {
   smm_logent logtab[1 << SMM_LOG_BITS];
+  __align__(16) uint32_t keys[20];  // Philox round keys of seed_sim for the out-of-line hot loop
   // segment geometry of this CTA's share (iteration invariant)
   int n_seg, total_units;
   int seg_c[kMaxCtaSeg], seg_j0[kMaxCtaSeg], seg_j1[kMaxCtaSeg], seg_unit0[kMaxCtaSeg + 1];
@@ -1154,7 +1279,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
                                                                             int n_iters, int sched_iter0, int n_s,
                                                                             int part_len, int max_seg, int cta_seg) {
   __shared__ PersistSmem sm;
-  __shared__ uint4 s_zigtab[kZigBufEntries];  // 16 KB: the 8 KB-aligned half holds the table (see load_zigtab)
+  __shared__ unsigned long long s_zigtab[kZigBufEntries];  // 16 KB: the 8 KB-aligned half holds the table (see load_zigtab)
   extern __shared__ double smem_d[];
   const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
   const int lane = tid & 31;
@@ -1175,10 +1300,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
   for (int i = tid; i < N; i += kPersistThreads) mi[i] = pb.min_improve[i];
   load_logtab(sm.logtab);
   load_zigtab(s_zigtab);
+  store_keys(pb, sm.keys);
+  const uint32_t keys_s = smem_addr(sm.keys);
   unsigned gen = ld_volatile_u32(&st.bar->gen) & 0x7fffffffu;
   unsigned long long seq = ld_volatile_u64(st.sync_seq);
-  const int nb = (S + 1) >> 1;
-  const int n_full = S >> 1;
+  const int nb = zig_blocks(S);          // Philox blocks per row of an evaluation (three draws each)
+  const int n_full = S / 3;              // ... of which this many are complete
+  const int n_tail = S - 3 * n_full;     // draws of the last, partial block (0 = none)
   const long long T = (long long)L * nb;
   const long long Gw = T < G ? T : G;  // CTAs that take a share of the draw space (all of them unless T is tiny)
   const long long lo = b < Gw ? (T * b) / Gw : 0, hi = b < Gw ? (T * (b + 1)) / Gw : 0;
@@ -1281,7 +1409,6 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
     {
       const uint32_t c3base = SMM_STREAM_SIM << 28;
       int cur = -1, units_cur = 0, j0 = 0, jfull = 0, j1 = 0;
-      uint32_t c2 = 0u, c3 = c3base;
       double p = 0.0;
       Acc a{0ull, 0ull};
       // barrier-free mode: the owner's part of the exchange (trace slot, state of the swapped chains) is off the
@@ -1289,15 +1416,17 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       if (kFlow && have_ex && n_owned > 0) persistent_exchange_apply(pb, st, it - 1, true, own, exch, true);
       ZigCtx cx = zig_ctx(s_zigtab, zq, S);
       cx.D = D;
+      cx.c3 = c3base;
       const uint32_t pp_seg_s = smem_addr(pp_seg), acc_s = smem_addr(acc);
-      int qn = 0;  // deferred ziggurat draws of this warp (all of the current segment)
+      const uint32_t kpack3 = (uint32_t)k | 0x300u;  // queue tag of a complete block of this lane's row
+      int qn = 0;  // deferred ziggurat blocks of this warp (all of the current segment)
       // Guided self-scheduling of what the static shares leave: a warp takes (remaining / 2 warps-worth, at most
       // kMaxGrab, at least 1) consecutive units from the CTA's queue.
       int u = (tid >> 5) * static_units, uend = u + static_units;  // this warp's fixed share comes first
       // Leaving a segment: add this warp's exact sums to the CTA's, count its units; true if that completed the
       // CTA's part of the chain.  (A warp may leave and re-enter a segment: the accounting is additive.)
       auto leave_segment = [&](int seg) -> bool {
-        zig_flush(cx, qn, pb.magic_sum, pb.magic_sq);
+        zig_flush(pb, cx, qn);
         for (int r = 1; r < rows; ++r) {
           const unsigned long long os = __shfl_down_sync(0xffffffffu, a.sum, r * D);
           const unsigned long long oq = __shfl_down_sync(0xffffffffu, a.sq, r * D);
@@ -1381,40 +1510,49 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
             p = lane_on ? pp_seg[(size_t)s * D + k] : 0.0;
             cx.pvec = pp_seg_s + 8u * (uint32_t)(s * D);
             cx.fix = acc_s + 8u * (uint32_t)(s * 2 * D);
-            c2 = pb.noseed ? (uint32_t)(pb.chain0 + sm.seg_c[s]) : 0u;
-            c3 = c3base | (pb.noseed ? ((uint32_t)it & SMM_ITER_MASK) : 0u);
+            cx.c2 = pb.noseed ? (uint32_t)(pb.chain0 + sm.seg_c[s]) : 0u;
+            cx.c3 = c3base | (pb.noseed ? ((uint32_t)it & SMM_ITER_MASK) : 0u);
           }
         }
         if (s < 0) break;
         // the part of the grabbed range that lies in this segment: units [u, ue)
         const int ue = uend < sm.seg_unit0[s + 1] ? uend : sm.seg_unit0[s + 1];
         units_cur += ue - u;
-        if (pb.obj != SMM_OBJ_FAILS) {  // every lane of the warp walks the steps (ballots inside add_pair)
+        if (pb.obj != SMM_OBJ_FAILS) {  // every lane of the warp walks the steps (ballots inside add_block)
           const int ju = j0 + (u - sm.seg_unit0[s]) * unit_j;   // first block of the range
           const int jue = j0 + (ue - sm.seg_unit0[s]) * unit_j;  // one past its last block
           const int n_steps = (ue - u) * kUnitSteps;
           const int jb = ju + jo;
           if (all_on && jue <= jfull) {
-            int q = 0;
-            while (q < n_steps) {  // the inner loop is call-free: it leaves when 32 deferred draws have gathered
-#pragma unroll 1
-              for (; q < n_steps && qn < 32; ++q)
-                add_pair<false>(pb, cx, qn, a, p, (uint32_t)(jb + q * rows), (uint32_t)k, c2, c3, true, true);
-              zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
+            for (int q = 0; q < n_steps;) {  // the hot loop lives out of line; it comes back when 32 deferred blocks have gathered
+              const SimRet r = sim_steps_full(keys_s, cx.ztab, cx.q, cx.c2, cx.c3, p, pb.magic_sum, pb.magic_sq,
+                                              (uint32_t)(jb + q * rows), (uint32_t)rows, n_steps - q, kpack3, qn, a.sum, a.sq);
+              a.sum = r.sum;
+              a.sq = r.sq;
+              qn = r.qn;
+              q += r.done;
+              zig_relieve(pb, cx, qn);
             }
           } else {
-#pragma unroll 1
-            for (int q = 0; q < n_steps; ++q) {
-              const int j = jb + q * rows;
-              const bool act = lane_on && j < jfull;
-              add_pair<true>(pb, cx, qn, a, p, (uint32_t)j, (uint32_t)k, c2, c3, act, act);
-              zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
+            for (int q = 0; q < n_steps;) {
+              const SimRet r = sim_steps_masked(keys_s, cx.ztab, cx.q, cx.c2, cx.c3, p, pb.magic_sum, pb.magic_sq,
+                                                (uint32_t)(jb + q * rows), (uint32_t)rows, n_steps - q, (uint32_t)k, qn, a.sum,
+                                                a.sq, lane_on, (uint32_t)jfull, 3);
+              a.sum = r.sum;
+              a.sq = r.sq;
+              qn = r.qn;
+              q += r.done;
+              zig_relieve(pb, cx, qn);
             }
           }
-          if ((S & 1) && n_full < j1 && ju <= n_full && n_full < jue) {  // odd S: the single last draw
-            const bool act = lane_on && jb <= n_full && (n_full - jb) % rows == 0;
-            add_pair<true>(pb, cx, qn, a, p, (uint32_t)n_full, (uint32_t)k, c2, c3, act, false);
-            zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
+          if (n_tail && n_full < j1 && ju <= n_full && n_full < jue) {  // S not a multiple of 3: the last, partial block
+            const bool on = lane_on && jb <= n_full && (n_full - jb) % rows == 0;
+            const SimRet r = sim_steps_masked(keys_s, cx.ztab, cx.q, cx.c2, cx.c3, p, pb.magic_sum, pb.magic_sq, (uint32_t)n_full,
+                                              0u, 1, (uint32_t)k, qn, a.sum, a.sq, on, (uint32_t)n_full + 1u, n_tail);
+            a.sum = r.sum;
+            a.sq = r.sq;
+            qn = r.qn;
+            zig_relieve(pb, cx, qn);
           }
         }
         u = ue;
@@ -1444,7 +1582,7 @@ __global__ void __launch_bounds__(kEvalThreads) objective_kernel(DevProblem pb, 
                                                                  double *partials, unsigned *arrive, double *value,
                                                                  double *moments, int *status) {
   __shared__ EvalSmem sm;
-  __shared__ uint4 s_zigtab[kZigBufEntries];
+  __shared__ unsigned long long s_zigtab[kZigBufEntries];
   const int bi = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
   const Grp g{tid, (int)blockDim.x, 0};
   load_logtab(sm.logtab);
@@ -1457,7 +1595,7 @@ __global__ void __launch_bounds__(kEvalThreads) objective_kernel(DevProblem pb, 
     if (split != 0) return;
   } else {
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
-    const int nb = (pb.S + 1) >> 1;
+    const int nb = zig_blocks(pb.S);
     const int j0 = (int)(((long long)nb * split) / n_split), j1 = (int)(((long long)nb * (split + 1)) / n_split);
     simulate_static(pb, g, s_zigtab, sm.pp, j0, j1, (uint32_t)bi, rep0 + (uint32_t)bi, sm.red, sm.zfix, sm.zq,
                     part_base + (size_t)split * part_len);
@@ -1574,18 +1712,24 @@ __global__ void __launch_bounds__(kPairThreads) bgp_pairs_kernel(DevProblem pb, 
 // ------------------------------------------------------------------------------------------------
 // diagnostics
 // ------------------------------------------------------------------------------------------------
-__global__ void debug_normals_kernel(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_pairs, int zig,
+// zig == 0: out[2 n] Box-Muller pairs; zig != 0: out[3 n] ziggurat triples of blocks (j, k, c2, c3), j < n
+__global__ void debug_normals_kernel(uint64_t seed, uint32_t k, uint32_t c2, uint32_t c3, int n_blocks, int zig,
                                      double *out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_pairs) return;
-  double z0, z1;
+  if (j >= n_blocks) return;
   const smm_u32x4 r = smm_philox4x32_10((uint32_t)j, k, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-  if (zig)
-    smm_zig_pair(r, &z0, &z1);
-  else
+  if (zig) {
+    double z[3];
+    smm_zig_triple(r, z);
+    out[3 * j] = z[0];
+    out[3 * j + 1] = z[1];
+    out[3 * j + 2] = z[2];
+  } else {
+    double z0, z1;
     smm_normal_pair(r, &z0, &z1);
-  out[2 * j] = z0;
-  out[2 * j + 1] = z1;
+    out[2 * j] = z0;
+    out[2 * j + 1] = z1;
+  }
 }
 
 // RNG-only roofline: Philox + Box-Muller + the two accumulations, nothing else
@@ -1666,18 +1810,20 @@ __global__ void __launch_bounds__(kPersistThreads, 1) barrier_bench_kernel(DevPr
   }
 }
 
-// the simulate inner loop alone (add_pair with the handle's keys and accumulators), static or dynamic unit
+// the simulate inner loop alone (add_block with the handle's keys and accumulators), static or dynamic unit
 // distribution, any CTA size: the ceiling the evaluation kernels are measured against
 // kBound: the launch bound the variant is compiled for (1024 -> 64 registers per thread, 768 -> 80, 512 -> 128), to
 // measure what the register budget of the persistent kernel's CTA shape costs
 template <int kBound>
 __global__ void __launch_bounds__(kBound) sim_throughput_kernel(DevProblem pb, int n_per_thread, int dyn, double *out) {
-  __shared__ uint4 ztab[kZigBufEntries];
+  __shared__ unsigned long long ztab[kZigBufEntries];
   extern __shared__ uint32_t zq[];  // [blockDim.x / 32][kZigQWords]
   __shared__ unsigned long long fix[2 * SMM_MAX_PARAMS];
   __shared__ double pvec[SMM_MAX_PARAMS];
+  __shared__ __align__(16) uint32_t keys[20];
   __shared__ int ctr;
   load_zigtab(ztab);
+  store_keys(pb, keys);
   if (threadIdx.x == 0) ctr = 0;
   const int lane = threadIdx.x & 31, D = pb.P;
   for (int e = threadIdx.x; e < D; e += blockDim.x) pvec[e] = 0.25 * (double)e;
@@ -1690,16 +1836,23 @@ __global__ void __launch_bounds__(kBound) sim_throughput_kernel(DevProblem pb, i
   cx.pvec = smem_addr(pvec);
   cx.fix = smem_addr(fix);
   cx.D = D;
+  cx.c3 = SMM_STREAM_SIM << 28;
+  const uint32_t kpack3 = k | 0x300u, keys_s = smem_addr(keys);
   int qn = 0;
+  auto steps = [&](uint32_t j, uint32_t dj, int n) {
+    for (int q = 0; q < n;) {
+      const SimRet r = sim_steps_full(keys_s, cx.ztab, cx.q, cx.c2, cx.c3, p, pb.magic_sum, pb.magic_sq, j + (uint32_t)q * dj, dj,
+                                      n - q, kpack3, qn, a.sum, a.sq);
+      a.sum = r.sum;
+      a.sq = r.sq;
+      qn = r.qn;
+      q += r.done;
+      zig_relieve(pb, cx, qn);
+    }
+  };
   if (!dyn) {
     const uint32_t j0 = (blockIdx.x * blockDim.x + threadIdx.x) / D * (uint32_t)n_per_thread;
-    int j = 0;
-    while (j < n_per_thread) {
-#pragma unroll 1
-      for (; j < n_per_thread && qn < 32; ++j)
-        add_pair<false>(pb, cx, qn, a, p, j0 + (uint32_t)j, k, 0u, SMM_STREAM_SIM << 28, true, true);
-      zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
-    }
+    steps(j0, 1u, n_per_thread);
   } else {
     const int rows = 32 / D, unit = rows * kTputSteps, jo = lane / D;
     const int jmax = n_per_thread * (blockDim.x / D) / unit * unit;
@@ -1709,18 +1862,11 @@ __global__ void __launch_bounds__(kBound) sim_throughput_kernel(DevProblem pb, i
     while (next < jmax) {
       const int base = next + jo;
       if (lane == 0) next = atomicAdd(&ctr, unit);
-      int u = 0;
-      while (u < kTputSteps) {
-#pragma unroll 1
-        for (; u < kTputSteps && qn < 32; ++u)
-          add_pair<false>(pb, cx, qn, a, p, (uint32_t)(base + u * rows) + blockIdx.x * 1000003u, k, 0u,
-                          SMM_STREAM_SIM << 28, true, true);
-        zig_relieve(cx, qn, pb.magic_sum, pb.magic_sq);
-      }
+      steps((uint32_t)base + blockIdx.x * 1000003u, (uint32_t)rows, kTputSteps);
       next = __shfl_sync(0xffffffffu, next, 0);
     }
   }
-  zig_flush(cx, qn, pb.magic_sum, pb.magic_sq);
+  zig_flush(pb, cx, qn);
   __syncthreads();
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   out[2 * gid] = __longlong_as_double((long long)(a.sum + fix[k]));

@@ -27,16 +27,16 @@ def test_normals_bit_exact(smm, oracle):
 
 
 def test_ziggurat_normals_bit_exact(smm, oracle):
-    """the simulator stream of the MvNormal objectives (fast path, wedges, tails, retries: 1.5 % of 400 000 draws leave
-    the fast path) is bit-identical on host and device"""
+    """the simulator stream of the MvNormal objectives (fast path, wedges, base strip, tails, retries: 0.8 % of 600 000
+    draws leave the fast path) is bit-identical on host and device"""
     for (seed, k, c2, c3) in [(1234, 0, 0, 1 << 28), (1234, 7, 0, 1 << 28), (99, 3, 17, (1 << 28) | 5)]:
         g = smm.debug_zig_normals(seed, k, c2, c3, 200000)
         o = oracle.zig_normals(seed, k, c2, c3, 200000)
         assert np.array_equal(g.view(np.uint64), o.view(np.uint64))
-        assert np.abs(g).max() > 3.6541528853610088      # the tail branch was exercised
+        assert np.abs(g).max() > 3.8520461503683912      # the tail branch was exercised
 
 
-@pytest.mark.parametrize("n_sim", [1, 2, 63, 64, 65, 1001, 4096])
+@pytest.mark.parametrize("n_sim", [1, 2, 3, 4, 95, 96, 97, 1001, 4096])
 def test_deferred_ziggurat_matches_sequential_definition(smm, oracle, n_sim):
     """the kernels resolve rejected fast-path candidates later, in warp-sized batches, and patch the exact integer
     accumulators; the totals must equal the oracle's draw-by-draw evaluation for ragged draw counts, in both modes"""
@@ -49,7 +49,7 @@ def test_deferred_ziggurat_matches_sequential_definition(smm, oracle, n_sim):
                 v, m, st = h.eval_batch(p, noseed=noseed, rep0=5)
             vo, mo, so = oracle.eval_batch(cfg, p, noseed=noseed, rep0=5, n_threads=4)
             np.testing.assert_array_equal(st, so)
-            # the fixed-point grids (2^-42 for x, 2^-36 for x^2 at these shapes) bound the absolute error of a moment; a sample variance
+            # the fixed-point grids (2^-40 for a block's sum of x, 2^-34 for its sum of x^2 at these shapes) bound the absolute error of a moment; a sample variance
             # of two or three draws can be tiny, so the bound is absolute here (north star: 1e-6 relative)
             np.testing.assert_allclose(m, mo, rtol=1e-9, atol=1e-9)
             np.testing.assert_allclose(v, vo, rtol=1e-7, atol=1e-9)
