@@ -261,12 +261,13 @@ struct Acc {
 // the work split as a per-draw rounding, at a third of the integer adds.
 // ------------------------------------------------------------------------------------------------
 constexpr int kZigQCap = 64;                    // entries per warp: < 32 before a step, <= 63 after its push
-constexpr int kZigQWords = 2 * kZigQCap;        // j[], kpack[]
+constexpr int kZigQWords = 2 * kZigQCap;        // {j, kpack} pairs (8-byte aligned)
 constexpr int kZigSigned = 2 * SMM_ZIG_LAYERS;  // shared-memory table: one 8-byte entry per (sign, layer)
 
 // Everything the hot loop needs lives in 32-bit registers (shared-window addresses, not generic pointers).
 struct ZigCtx {
   uint32_t ztab;  // shared address of the signed layer table: entry s = {+-W'[i] 2^-32 | KH[i]}, on an 8 KB boundary
+  uint32_t hi52;  // 0x43300000 (high word of 2^52) held in a register, so that building 2^52 + u costs no MOV per draw
   uint32_t q;     // shared address of this warp's queue
   uint32_t lt;    // %lanemask_lt
   uint32_t pvec;  // shared address: [D] parameters of the evaluation being simulated (f64)
@@ -297,6 +298,7 @@ __device__ __forceinline__ ZigCtx zig_ctx(const unsigned long long *zbuf, uint32
   ZigCtx cx;
   const uint32_t zero = (uint32_t)opaque >> 31;
   cx.ztab = zig_table_addr(zbuf) | zero;
+  cx.hi52 = 0x43300000u | zero;
   cx.q = smem_addr(q_warp);
   asm volatile("" : "+r"(cx.q));  // opaque: keep the address in a register instead of recomputing it from %tid per push
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(cx.lt));
@@ -315,7 +317,7 @@ __device__ __forceinline__ double zig_fast_dev(uint32_t u, uint32_t sel8, const 
   asm("lop3.b32 %0, %1, 0x1FF8, %2, 0xEA;" : "=r"(addr) : "r"(sel8), "r"(cx.ztab));
   asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0), "=r"(e1) : "r"(addr));
   ok = u < (e0 << 20);
-  const double t = __dsub_rn(__hiloint2double(0x43300000, (int)u), 4503599627370496.0);  // (double)u, exactly
+  const double t = __dsub_rn(__hiloint2double((int)cx.hi52, (int)u), 4503599627370496.0);  // (double)u, exactly
   return __dmul_rn(t, __hiloint2double((int)e1, (int)e0));
 }
 
@@ -325,33 +327,38 @@ __device__ __forceinline__ void block_sums(double x0, double x1, double x2, doub
   q = __fma_rn(x2, x2, __fma_rn(x1, x1, __dmul_rn(x0, x0)));
 }
 
-// the warp resolves `cnt` (<= 32) queued blocks starting at entry `first`
+// the warp resolves `cnt` (<= 32) queued blocks starting at entry `first`, one block per lane: the block is re-derived,
+// its FIRST rejected candidate goes through smm_zig_slow in a single convergent call (one in 5000 blocks holds a second
+// one: a divergent tail), and the difference of the block's fixed-point patterns is added to the shared accumulators
 __device__ __noinline__ void zig_drain(const DevProblem &pb, const ZigCtx cx, int first, int cnt) {
   const int lane = threadIdx.x & 31;
   if (lane < cnt) {
     uint32_t j, kp;
-    const uint32_t qa = cx.q + 4u * (uint32_t)(first + lane);
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(j) : "r"(qa) : "memory");
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(kp) : "r"(qa), "n"(4 * kZigQCap) : "memory");
+    const uint32_t qa = cx.q + 8u * (uint32_t)(first + lane);
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(j), "=r"(kp) : "r"(qa) : "memory");
     const uint32_t kk = kp & 0xFFu, nact = kp >> 8;
     const smm_u32x4 r = smm_philox4x32_10(j, kk, cx.c2, cx.c3, (uint32_t)pb.seed_sim, (uint32_t)(pb.seed_sim >> 32));
     double p;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(p) : "r"(cx.pvec + 8u * kk) : "memory");
-    const uint32_t uu[3] = {r.x, r.y, r.z};
-    double xf[3], xs[3];
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      int ok;
-      const uint32_t sel = smm_zig_select(r.w, t);
-      const double zf = smm_zig_fast(uu[t], sel, smm_zigtab(), &ok);  // global tables: this path is rare
-      const double zs = ok ? zf : smm_zig_slow(uu[t], sel, smm_zigtab(), smm_logtab());
-      const bool act = (uint32_t)t < nact;
-      xf[t] = act ? __dadd_rn(p, zf) : 0.0;
-      xs[t] = act ? __dadd_rn(p, zs) : 0.0;
-    }
+    bool ok0, ok1, ok2;
+    const double zf0 = zig_fast_dev(r.x, r.w, cx, ok0);
+    const double zf1 = zig_fast_dev(r.y, r.w >> 10, cx, ok1);
+    const double zf2 = zig_fast_dev(r.z, __funnelshift_l(r.w, r.w, 12), cx, ok2);
+    ok1 = ok1 || nact < 2;
+    ok2 = ok2 || nact < 3;
+    // the unsigned half of the shared table is the stream's table: the rare branch reads it through a generic pointer
+    const smm_zigent *tab = (const smm_zigent *)__cvta_shared_to_generic((size_t)(cx.ztab & ~7u));
+    const int t1 = !ok0 ? 0 : (!ok1 ? 1 : 2);
+    const double z1 = smm_zig_slow(t1 == 0 ? r.x : (t1 == 1 ? r.y : r.z), smm_zig_select(r.w, t1), tab, smm_logtab());
+    double zs0 = t1 == 0 ? z1 : zf0, zs1 = t1 == 1 ? z1 : zf1, zs2 = t1 == 2 ? z1 : zf2;
+    if (t1 == 0 && !ok1) zs1 = smm_zig_slow(r.y, smm_zig_select(r.w, 1), tab, smm_logtab());
+    if (t1 < 2 && !ok2) zs2 = smm_zig_slow(r.z, smm_zig_select(r.w, 2), tab, smm_logtab());
+    const double xf0 = __dadd_rn(p, zf0), xs0 = __dadd_rn(p, zs0);
+    const double xf1 = nact < 2 ? 0.0 : __dadd_rn(p, zf1), xs1 = nact < 2 ? 0.0 : __dadd_rn(p, zs1);
+    const double xf2 = nact < 3 ? 0.0 : __dadd_rn(p, zf2), xs2 = nact < 3 ? 0.0 : __dadd_rn(p, zs2);
     double sf, qf, ss, qs;
-    block_sums(xf[0], xf[1], xf[2], sf, qf);
-    block_sums(xs[0], xs[1], xs[2], ss, qs);
+    block_sums(xf0, xf1, xf2, sf, qf);
+    block_sums(xs0, xs1, xs2, ss, qs);
     const unsigned long long dsum = (unsigned long long)__double_as_longlong(__dadd_rn(ss, pb.magic_sum)) -
                                     (unsigned long long)__double_as_longlong(__dadd_rn(sf, pb.magic_sum));
     const unsigned long long dsq = (unsigned long long)__double_as_longlong(__dadd_rn(qs, pb.magic_sq)) -
@@ -434,10 +441,28 @@ __device__ __forceinline__ SimKeys load_keys(uint32_t keys_s) {
 // 32 lanes of a warp; nact = how many of this lane's draws count (kMasked = false: all three always do; 0 = the lane
 // sits this step out).  Needs qn < 32 on entry; the caller resolves the queue between steps (kept out of here so that
 // hot loops contain no call).  kpack = k | nact << 8 is what the queue stores next to j.
-template <bool kMasked>
+// kVariant != 0: ablations for the throughput micro-benchmark only (1 = deferred queue off, 2 = also no table lookup,
+// 3 = Philox alone)
+template <bool kMasked, int kVariant = 0>
 __device__ __forceinline__ void add_block(const SimKeys &ks, double magic_sum, double magic_sq, const ZigCtx &cx, int &qn,
                                           Acc &a, double p, uint32_t j, uint32_t k, uint32_t kpack, int nact) {
   const smm_u32x4 r = philox_keys(ks, j, k, cx.c2, cx.c3);
+  if (kVariant == 3) {
+    a.sum += r.x ^ r.y;
+    a.sq += r.z ^ r.w;
+    return;
+  }
+  if (kVariant == 2) {
+    const double w = __hiloint2double(0x3DF00000 | (int)(cx.ztab >> 28), 0);
+    const double x0 = __dadd_rn(p, __dmul_rn(__dsub_rn(__hiloint2double(0x43300000, (int)r.x), 4503599627370496.0), w));
+    const double x1 = __dadd_rn(p, __dmul_rn(__dsub_rn(__hiloint2double(0x43300000, (int)r.y), 4503599627370496.0), w));
+    const double x2 = __dadd_rn(p, __dmul_rn(__dsub_rn(__hiloint2double(0x43300000, (int)r.z), 4503599627370496.0), w));
+    double s, q;
+    block_sums(x0, x1, x2, s, q);
+    a.sum += (unsigned long long)__double_as_longlong(__dadd_rn(s, magic_sum)) + r.w;
+    a.sq += (unsigned long long)__double_as_longlong(__dadd_rn(q, magic_sq));
+    return;
+  }
   bool ok0, ok1, ok2;
   double x0 = __dadd_rn(p, zig_fast_dev(r.x, r.w, cx, ok0));
   double x1 = __dadd_rn(p, zig_fast_dev(r.y, r.w >> 10, cx, ok1));
@@ -462,12 +487,15 @@ __device__ __forceinline__ void add_block(const SimKeys &ks, double magic_sum, d
     a.sum += sb;
     a.sq += qb;
   }
+  if (kVariant == 1) {
+    a.sum += slow;
+    return;
+  }
   if (__any_sync(0xffffffffu, slow)) {  // half of the steps: some lane's block holds a candidate that left the fast path
     const unsigned m = __ballot_sync(0xffffffffu, slow);
     if (slow) {
-      const uint32_t qa = cx.q + 4u * (uint32_t)(qn + __popc(m & cx.lt));
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(qa), "r"(j) : "memory");
-      asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(qa), "r"(kpack), "n"(4 * kZigQCap) : "memory");
+      const uint32_t qa = cx.q + 8u * (uint32_t)(qn + __popc(m & cx.lt));
+      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(qa), "r"(j), "r"(kpack) : "memory");
     }
     qn += __popc(m);
   }
@@ -480,12 +508,14 @@ struct SimRet {
   unsigned long long sum, sq;
   int done, qn;
 };
+template <int kVariant = 0>
 __device__ __noinline__ SimRet sim_steps_full(uint32_t keys_s, uint32_t ztab, uint32_t q_s, uint32_t c2, uint32_t c3, double p,
                                               double magic_sum, double magic_sq, uint32_t j, uint32_t dj, int n_steps,
                                               uint32_t kpack3, int qn, unsigned long long sum, unsigned long long sq) {
   const SimKeys ks = load_keys(keys_s);
   ZigCtx cx;
   cx.ztab = ztab;
+  cx.hi52 = 0x43300000u | (ztab >> 31);  // opaque (shared addresses are small): stays in a register
   cx.q = q_s;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(cx.lt));
   cx.c2 = c2;
@@ -496,7 +526,7 @@ __device__ __noinline__ SimRet sim_steps_full(uint32_t keys_s, uint32_t ztab, ui
   const uint32_t k = kpack3 & 0xFFu;
   int q = 0;
 #pragma unroll 1
-  for (; q < n_steps && qn < 32; ++q, j += dj) add_block<false>(ks, magic_sum, magic_sq, cx, qn, a, p, j, k, kpack3, 3);
+  for (; q < n_steps && qn < 32; ++q, j += dj) add_block<false, kVariant>(ks, magic_sum, magic_sq, cx, qn, a, p, j, k, kpack3, 3);
   return SimRet{a.sum, a.sq, q, qn};
 }
 // the same for steps in which lanes or draws are masked out: lane active iff lane_on and j < jlimit, with nact_on draws
@@ -507,6 +537,7 @@ __device__ __noinline__ SimRet sim_steps_masked(uint32_t keys_s, uint32_t ztab, 
   const SimKeys ks = load_keys(keys_s);
   ZigCtx cx;
   cx.ztab = ztab;
+  cx.hi52 = 0x43300000u | (ztab >> 31);
   cx.q = q_s;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(cx.lt));
   cx.c2 = c2;
@@ -1817,7 +1848,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) barrier_bench_kernel(DevPr
 template <int kBound>
 __global__ void __launch_bounds__(kBound) sim_throughput_kernel(DevProblem pb, int n_per_thread, int dyn, double *out) {
   __shared__ unsigned long long ztab[kZigBufEntries];
-  extern __shared__ uint32_t zq[];  // [blockDim.x / 32][kZigQWords]
+  extern __shared__ __align__(16) uint32_t zq[];  // [blockDim.x / 32][kZigQWords]
   __shared__ unsigned long long fix[2 * SMM_MAX_PARAMS];
   __shared__ double pvec[SMM_MAX_PARAMS];
   __shared__ __align__(16) uint32_t keys[20];
@@ -1839,10 +1870,14 @@ __global__ void __launch_bounds__(kBound) sim_throughput_kernel(DevProblem pb, i
   cx.c3 = SMM_STREAM_SIM << 28;
   const uint32_t kpack3 = k | 0x300u, keys_s = smem_addr(keys);
   int qn = 0;
+  const int variant = dyn >> 2;
+  dyn &= 1;
   auto steps = [&](uint32_t j, uint32_t dj, int n) {
     for (int q = 0; q < n;) {
-      const SimRet r = sim_steps_full(keys_s, cx.ztab, cx.q, cx.c2, cx.c3, p, pb.magic_sum, pb.magic_sq, j + (uint32_t)q * dj, dj,
-                                      n - q, kpack3, qn, a.sum, a.sq);
+      const uint32_t jq = j + (uint32_t)q * dj;
+#define SMM_TPUT_CALL(V) sim_steps_full<V>(keys_s, cx.ztab, cx.q, cx.c2, cx.c3, p, pb.magic_sum, pb.magic_sq, jq, dj, n - q, kpack3, qn, a.sum, a.sq)
+      const SimRet r = variant == 0 ? SMM_TPUT_CALL(0) : variant == 1 ? SMM_TPUT_CALL(1) : variant == 2 ? SMM_TPUT_CALL(2) : SMM_TPUT_CALL(3);
+#undef SMM_TPUT_CALL
       a.sum = r.sum;
       a.sq = r.sq;
       qn = r.qn;
@@ -1968,7 +2003,7 @@ void launch_sim_throughput(const DevProblem &pb, int n_per_thread, int blocks, i
   // dyn: 0 = static split, 1 = unit queue; +2 = the variant compiled for the smallest launch bound >= threads
   auto go = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
-    kern<<<blocks, threads, dyn_smem, s>>>(pb, n_per_thread, dyn & 1, out);
+    kern<<<blocks, threads, dyn_smem, s>>>(pb, n_per_thread, (dyn & 1) | (dyn >> 2 << 2), out);
   };
   if ((dyn & 2) && threads <= 512)
     go(sim_throughput_kernel<512>);
