@@ -273,6 +273,7 @@ struct ZigCtx {
   uint32_t pvec;  // shared address: [D] parameters of the evaluation being simulated (f64)
   uint32_t fix;   // shared address: [2D] u64 where corrections are added
   uint32_t c2, c3;  // counter words 2, 3 of the blocks being simulated (what the drain needs to re-derive a block)
+  uint32_t segc2;   // persistent kernel: shared address of c2 per segment (queue entries carry their segment); 0 = use c2
   int D;
 };
 
@@ -306,6 +307,7 @@ __device__ __forceinline__ ZigCtx zig_ctx(const unsigned long long *zbuf, uint32
   cx.fix = 0;
   cx.c2 = 0;
   cx.c3 = 0;
+  cx.segc2 = 0;
   cx.D = 0;
   return cx;
 }
@@ -336,10 +338,14 @@ __device__ __noinline__ void zig_drain(const DevProblem &pb, const ZigCtx cx, in
     uint32_t j, kp;
     const uint32_t qa = cx.q + 8u * (uint32_t)(first + lane);
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(j), "=r"(kp) : "r"(qa) : "memory");
-    const uint32_t kk = kp & 0xFFu, nact = kp >> 8;
-    const smm_u32x4 r = smm_philox4x32_10(j, kk, cx.c2, cx.c3, (uint32_t)pb.seed_sim, (uint32_t)(pb.seed_sim >> 32));
+    // entry tag: row k (8 bits) | active draws (2 bits) | segment of the CTA's share (persistent kernel; 0 elsewhere)
+    const uint32_t kk = kp & 0xFFu, nact = (kp >> 8) & 3u, seg = kp >> 10;
+    uint32_t c2 = cx.c2;
+    if (cx.segc2) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c2) : "r"(cx.segc2 + 4u * seg) : "memory");
+    const smm_u32x4 r = smm_philox4x32_10(j, kk, c2, cx.c3, (uint32_t)pb.seed_sim, (uint32_t)(pb.seed_sim >> 32));
+    const uint32_t D = (uint32_t)cx.D;
     double p;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(p) : "r"(cx.pvec + 8u * kk) : "memory");
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(p) : "r"(cx.pvec + 8u * (seg * D + kk)) : "memory");
     bool ok0, ok1, ok2;
     const double zf0 = zig_fast_dev(r.x, r.w, cx, ok0);
     const double zf1 = zig_fast_dev(r.y, r.w >> 10, cx, ok1);
@@ -363,8 +369,8 @@ __device__ __noinline__ void zig_drain(const DevProblem &pb, const ZigCtx cx, in
                                     (unsigned long long)__double_as_longlong(__dadd_rn(sf, pb.magic_sum));
     const unsigned long long dsq = (unsigned long long)__double_as_longlong(__dadd_rn(qs, pb.magic_sq)) -
                                    (unsigned long long)__double_as_longlong(__dadd_rn(qf, pb.magic_sq));
-    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(cx.fix + 8u * kk), "l"(dsum) : "memory");
-    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(cx.fix + 8u * ((uint32_t)cx.D + kk)), "l"(dsq) : "memory");
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(cx.fix + 8u * (seg * 2u * D + kk)), "l"(dsum) : "memory");
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(cx.fix + 8u * (seg * 2u * D + D + kk)), "l"(dsq) : "memory");
   }
   __syncwarp();
 }
@@ -549,7 +555,7 @@ __device__ __noinline__ SimRet sim_steps_masked(uint32_t keys_s, uint32_t ztab, 
 #pragma unroll 1
   for (; q < n_steps && qn < 32; ++q, j += dj) {
     const int nact = (lane_on && j < jlimit) ? nact_on : 0;
-    add_block<true>(ks, magic_sum, magic_sq, cx, qn, a, p, j, k, k | ((uint32_t)nact << 8), nact);
+    add_block<true>(ks, magic_sum, magic_sq, cx, qn, a, p, j, k & 0xFFu, k | ((uint32_t)nact << 8), nact);  // k: row | segment << 10
   }
   return SimRet{a.sum, a.sq, q, qn};
 }
@@ -607,7 +613,8 @@ __device__ void simulate_static(const DevProblem &pb, const Grp &g, const unsign
 
 constexpr int kUnitSteps = 1;   // warp steps per work unit of the persistent kernel
 constexpr int kMaxGrab = 8;     // units a warp takes from its CTA's queue at once (guided: fewer towards the end)
-constexpr int kStaticNum = 3, kStaticDen = 4;  // share of a CTA's units that is split statically over its warps
+constexpr int kMinGrab = 2;     // ... and at least (a call of the out-of-line hot loop costs about half a step)
+constexpr int kStaticNum = 7, kStaticDen = 8;  // share of a CTA's units that is split statically over its warps
 constexpr int kTputSteps = 8;   // sim_throughput_kernel: steps per queue access
 
 __device__ void group_distance(const DevProblem &pb, const Grp &g, const FinScratch &fs);
@@ -1115,9 +1122,9 @@ struct PersistSmem {
   int n_seg, total_units;
   int seg_c[kMaxCtaSeg], seg_j0[kMaxCtaSeg], seg_j1[kMaxCtaSeg], seg_unit0[kMaxCtaSeg + 1];
   int seg_slot[kMaxCtaSeg], seg_nseg[kMaxCtaSeg];   // partial slot of this CTA / CTAs sharing the chain
+  uint32_t seg_c2[kMaxCtaSeg];                       // counter word 2 of the segment's blocks (chain id with noseed, else 0)
   // per-iteration work queue
   int next_unit;
-  int done[kMaxCtaSeg];
   int nlev;  // levels of the prefetched exchange schedule
   // proposals
   double g_pp[kPGroups][SMM_MAX_PARAMS];
@@ -1356,6 +1363,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       sm.seg_unit0[n] = u0;
       sm.seg_slot[n] = b - b_first;
       sm.seg_nseg[n] = b_last - b_first + 1;
+      sm.seg_c2[n] = pb.noseed ? (uint32_t)(pb.chain0 + c) : 0u;
       u0 += (sm.seg_j1[n] - sm.seg_j0[n] + unit_j - 1) / unit_j;
       ++n;
       x = xe;
@@ -1432,14 +1440,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
     if (!kFlow)
       for (int e = tid; e < n_seg * D; e += kPersistThreads) pp_seg[e] = __ldcg(st.pp + (size_t)sm.seg_c[e / D] * P + e % D);
     for (int e = tid; e < n_seg * 2 * D; e += kPersistThreads) acc[e] = 0ull;
-    if (tid < n_seg) sm.done[tid] = 0;
     if (tid == 0) sm.next_unit = static_units * (kPersistThreads / 32);
     if ((n_owned > 0 || (kFlow && n_seg > 0)) && N > 1 && it >= 2) prefetch_schedule(st, it, sched_iter0, n_s, sij, soff, &sm.nlev);
     __syncthreads();
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
     {
       const uint32_t c3base = SMM_STREAM_SIM << 28;
-      int cur = -1, units_cur = 0, j0 = 0, jfull = 0, j1 = 0;
+      int cur = -1, j0 = 0, jfull = 0, j1 = 0;
       double p = 0.0;
       Acc a{0ull, 0ull};
       // barrier-free mode: the owner's part of the exchange (trace slot, state of the swapped chains) is off the
@@ -1447,17 +1454,15 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       if (kFlow && have_ex && n_owned > 0) persistent_exchange_apply(pb, st, it - 1, true, own, exch, true);
       ZigCtx cx = zig_ctx(s_zigtab, zq, S);
       cx.D = D;
-      cx.c3 = c3base;
-      const uint32_t pp_seg_s = smem_addr(pp_seg), acc_s = smem_addr(acc);
-      const uint32_t kpack3 = (uint32_t)k | 0x300u;  // queue tag of a complete block of this lane's row
-      int qn = 0;  // deferred ziggurat blocks of this warp (all of the current segment)
-      // Guided self-scheduling of what the static shares leave: a warp takes (remaining / 2 warps-worth, at most
-      // kMaxGrab, at least 1) consecutive units from the CTA's queue.
-      int u = (tid >> 5) * static_units, uend = u + static_units;  // this warp's fixed share comes first
-      // Leaving a segment: add this warp's exact sums to the CTA's, count its units; true if that completed the
-      // CTA's part of the chain.  (A warp may leave and re-enter a segment: the accounting is additive.)
-      auto leave_segment = [&](int seg) -> bool {
-        zig_flush(pb, cx, qn);
+      cx.c3 = c3base | (pb.noseed ? ((uint32_t)it & SMM_ITER_MASK) : 0u);
+      cx.pvec = smem_addr(pp_seg);
+      cx.fix = smem_addr(acc);
+      cx.segc2 = smem_addr(sm.seg_c2);
+      uint32_t ktag = (uint32_t)k;  // queue tag of this lane's blocks: row | segment << 10 (| active draws << 8)
+      int qn = 0;                   // deferred ziggurat blocks of this warp; entries carry their segment, so the queue
+                                    // lives across segment changes and is emptied once, when the warp is out of units
+      // Leaving a segment: add this warp's exact sums to the CTA's.  (A warp may leave and re-enter a segment.)
+      auto fold = [&](int seg) {
         for (int r = 1; r < rows; ++r) {
           const unsigned long long os = __shfl_down_sync(0xffffffffu, a.sum, r * D);
           const unsigned long long oq = __shfl_down_sync(0xffffffffu, a.sq, r * D);
@@ -1470,42 +1475,19 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
           atomicAdd(acc + (size_t)seg * 2 * D + lane, a.sum);
           atomicAdd(acc + (size_t)seg * 2 * D + D + lane, a.sq);
         }
-        __syncwarp();
-        int complete = 0;
-        if (lane == 0) {
-          __threadfence_block();
-          const int n_units = sm.seg_unit0[seg + 1] - sm.seg_unit0[seg];
-          complete = (atomicAdd(&sm.done[seg], units_cur) + units_cur == n_units);
-          if (complete) __threadfence_block();
-        }
-        return __shfl_sync(0xffffffffu, complete, 0) != 0;
+        a.sum = 0ull;
+        a.sq = 0ull;
       };
-      // Publishing a completed segment and, if this CTA is the chain's last, finishing the chain keeps a warp busy for
-      // ~5 us.  Towards the end of the phase a warp must not sit on unaccounted units meanwhile (the segment they belong
-      // to could only complete -- and its chain only be finished -- after that, one finalisation after the other): in
-      // the dynamic part it first walks the units it holds, accounts for them, and only then publishes.
-      unsigned pend = 0;
-      bool dynamic_phase = false;
+      // Every warp first walks its fixed share of the CTA's units; what the fixed shares leave is handed out by guided
+      // self-scheduling: a warp takes (remaining / 2 warps-worth, at most kMaxGrab, at least kMinGrab) consecutive units.
+      int u = (tid >> 5) * static_units, uend = u + static_units;
       for (;;) {
         if (u >= uend) {
-          if (pend) {
-            if (cur >= 0) {
-              if (leave_segment(cur)) pend |= 1u << cur;
-              cur = -1;
-            }
-            while (pend) {
-              const int sp = __ffs((int)pend) - 1;
-              pend &= pend - 1;
-              warp_publish_segment(pb, st, sm, sp, it, fused, part_len, max_seg, acc, pp_seg, fscratch, fs_len, kFlow,
-                                   have_ex ? exch : nullptr);
-            }
-          }
-          dynamic_phase = true;
           int start = 0, g = 0;
           if (lane == 0) {
             const int rem = total_units - *(volatile int *)&sm.next_unit;
-            constexpr int kTwice = 2 * (kPersistThreads / 32);  // grab = what is left / two warps-worth per warp
-            g = rem > kTwice * kMaxGrab ? kMaxGrab : (rem > kTwice ? rem / kTwice : 1);
+            constexpr int kTwice = 2 * (kPersistThreads / 32);
+            g = rem > kTwice * kMaxGrab ? kMaxGrab : (rem > kTwice * kMinGrab ? rem / kTwice : kMinGrab);
             start = atomicAdd(&sm.next_unit, g);
           }
           start = __shfl_sync(0xffffffffu, start, 0);
@@ -1523,32 +1505,20 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
           s = -1;
         }
         if (s != cur) {
-          if (cur >= 0 && leave_segment(cur)) {
-            if (dynamic_phase && u < uend && u < total_units)
-              pend |= 1u << cur;  // units in hand: see above
-            else
-              warp_publish_segment(pb, st, sm, cur, it, fused, part_len, max_seg, acc, pp_seg, fscratch, fs_len, kFlow,
-                                   have_ex ? exch : nullptr);
-          }
+          if (cur >= 0) fold(cur);
           cur = s;
           if (s >= 0) {
-            units_cur = 0;
-            a.sum = 0ull;
-            a.sq = 0ull;
             j0 = sm.seg_j0[s];
             j1 = sm.seg_j1[s];
             jfull = j1 < n_full ? j1 : n_full;
             p = lane_on ? pp_seg[(size_t)s * D + k] : 0.0;
-            cx.pvec = pp_seg_s + 8u * (uint32_t)(s * D);
-            cx.fix = acc_s + 8u * (uint32_t)(s * 2 * D);
-            cx.c2 = pb.noseed ? (uint32_t)(pb.chain0 + sm.seg_c[s]) : 0u;
-            cx.c3 = c3base | (pb.noseed ? ((uint32_t)it & SMM_ITER_MASK) : 0u);
+            cx.c2 = sm.seg_c2[s];
+            ktag = (uint32_t)k | ((uint32_t)s << 10);
           }
         }
         if (s < 0) break;
         // the part of the grabbed range that lies in this segment: units [u, ue)
         const int ue = uend < sm.seg_unit0[s + 1] ? uend : sm.seg_unit0[s + 1];
-        units_cur += ue - u;
         if (pb.obj != SMM_OBJ_FAILS) {  // every lane of the warp walks the steps (ballots inside add_block)
           const int ju = j0 + (u - sm.seg_unit0[s]) * unit_j;   // first block of the range
           const int jue = j0 + (ue - sm.seg_unit0[s]) * unit_j;  // one past its last block
@@ -1557,7 +1527,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
           if (all_on && jue <= jfull) {
             for (int q = 0; q < n_steps;) {  // the hot loop lives out of line; it comes back when 32 deferred blocks have gathered
               const SimRet r = sim_steps_full(keys_s, cx.ztab, cx.q, cx.c2, cx.c3, p, pb.magic_sum, pb.magic_sq,
-                                              (uint32_t)(jb + q * rows), (uint32_t)rows, n_steps - q, kpack3, qn, a.sum, a.sq);
+                                              (uint32_t)(jb + q * rows), (uint32_t)rows, n_steps - q, ktag | 0x300u, qn, a.sum,
+                                              a.sq);
               a.sum = r.sum;
               a.sq = r.sq;
               qn = r.qn;
@@ -1567,8 +1538,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
           } else {
             for (int q = 0; q < n_steps;) {
               const SimRet r = sim_steps_masked(keys_s, cx.ztab, cx.q, cx.c2, cx.c3, p, pb.magic_sum, pb.magic_sq,
-                                                (uint32_t)(jb + q * rows), (uint32_t)rows, n_steps - q, (uint32_t)k, qn, a.sum,
-                                                a.sq, lane_on, (uint32_t)jfull, 3);
+                                                (uint32_t)(jb + q * rows), (uint32_t)rows, n_steps - q, ktag, qn, a.sum, a.sq,
+                                                lane_on, (uint32_t)jfull, 3);
               a.sum = r.sum;
               a.sq = r.sq;
               qn = r.qn;
@@ -1579,7 +1550,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
           if (n_tail && n_full < j1 && ju <= n_full && n_full < jue) {  // S not a multiple of 3: the last, partial block
             const bool on = lane_on && jb <= n_full && (n_full - jb) % rows == 0;
             const SimRet r = sim_steps_masked(keys_s, cx.ztab, cx.q, cx.c2, cx.c3, p, pb.magic_sum, pb.magic_sq, (uint32_t)n_full,
-                                              0u, 1, (uint32_t)k, qn, a.sum, a.sq, on, (uint32_t)n_full + 1u, n_tail);
+                                              0u, 1, ktag, qn, a.sum, a.sq, on, (uint32_t)n_full + 1u, n_tail);
             a.sum = r.sum;
             a.sq = r.sq;
             qn = r.qn;
@@ -1588,10 +1559,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
         }
         u = ue;
       }
+      zig_flush(pb, cx, qn);  // the corrections of every segment this warp touched
     }
     PHASE_STAMP((b * 2 + (it & 1)) * 2, 1);  // warp 0 left the work loop
     __syncthreads();
-    PHASE_STAMP((b * 2 + (it & 1)) * 2, 2);  // every warp of the CTA done (incl. chain finalisation)
+    // The CTA's sums of every chain it touched are complete: one warp per segment publishes them; the warp that brings
+    // the last partial of a chain finishes the chain (moments, distance, accept/reject, trace, record, completion tag).
+    for (int sp = tid >> 5; sp < n_seg; sp += kPersistThreads / 32)
+      warp_publish_segment(pb, st, sm, sp, it, fused, part_len, max_seg, acc, pp_seg, fscratch, fs_len, kFlow,
+                           have_ex ? exch : nullptr);
+    PHASE_STAMP((b * 2 + (it & 1)) * 2, 2);  // warp 0 done (incl. chain finalisation)
     if (!kFlow) {
       if (!grid_barrier(pb, st, gen, fused, seq)) return;
       PHASE_STAMP((b * 2 + (it & 1)) * 2, 3);
