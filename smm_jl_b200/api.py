@@ -295,14 +295,15 @@ def _base_config(m: MProb, n_chains: int, max_iter: int, opts: dict) -> BGPConfi
 
 
 def _exchange_mode(m: MProb, opts: dict, n_params: int) -> int:
-    """opts["exchange_mode"], or the fastest mode the shape allows: the barrier-free persistent kernel on one GPU
-    (2), the persistent kernel with one flag exchange per iteration on several (1); the multi-launch path (0) for the
-    panel objective and for more than 32 parameters (include/smm_b200.h)."""
+    """opts["exchange_mode"], or the fastest mode the shape allows: the barrier-free persistent kernel (2) on one GPU
+    and on several (records go to the peers by plain stores, one completion counter per rank); the multi-launch path
+    (0) for the panel objective and for more than 32 parameters (include/smm_b200.h).  A persistent mode that does not
+    fit the shape (SMM_E_UNSUPPORTED_SHAPE at create time) falls back to 0 in MAlgoBGP._handle."""
     if "exchange_mode" in opts:
         return int(opts["exchange_mode"])
     if _objective_id(m) == SMM_OBJ_PANEL or n_params > 32:
         return 0
-    return 2 if int(opts.get("world_size", 1)) == 1 else 1
+    return 2
 
 
 def evaluateObjective(m: MProb, p, noseed: bool = False, rep: int = 0) -> Eval:

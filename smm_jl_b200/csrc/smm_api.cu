@@ -24,7 +24,8 @@ int persistent_max_blocks_per_sm(int N, int D, int M, int cta_seg);
 int persistent_max_cta_seg();
 cudaError_t configure_persistent(int N, int D, int M, int cta_seg);
 cudaError_t launch_persistent(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int sched_iter0,
-                              int n_s, int part_len, int max_seg, int cta_seg, int grid, bool flow, cudaStream_t s);
+                              int n_s, int part_len, int max_seg, int cta_seg, int grid, bool flow,
+                              unsigned long long done_base, cudaStream_t s);
 void launch_eval(const DevProblem &pb, const DevState &st, int iter, int n_split, int part_len, cudaStream_t s);
 void launch_pairs(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int n_s, cudaStream_t s);
 void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sched_idx, int n_s, cudaStream_t s);
@@ -128,6 +129,7 @@ struct smm_bgp {
   int grid = 0, max_seg = 1, cta_seg = 1;  // persistent kernel: CTAs, partial slots per chain, chains per CTA share
   void *peer_ptrs[3 * kMaxWorld] = {nullptr};  // IPC-opened peer buffers (closed in release)
   int iter = 0;      // iterations completed (algo.i)
+  unsigned long long done_base = 0;  // exchange_mode 2: value of the completion counter once everything enqueued has run
   int sched_iter0 = -1, sched_n = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   std::vector<cudaEvent_t> win_ev;  // window boundaries of smm_bgp_run
@@ -458,7 +460,8 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
       return fail(SMM_E_UNSUPPORTED_SHAPE, "exchange_mode 1: too many chains per SM for the persistent kernel; use exchange_mode 0");
     CUDA_TRY(configure_persistent(N, P, M, h->cta_seg));
     if (persistent_max_blocks_per_sm(N, P, M, h->cta_seg) < 1)
-      return fail(SMM_E_CUDA, "persistent kernel does not fit on an SM");
+      return fail(SMM_E_UNSUPPORTED_SHAPE,
+                  "persistent kernel does not fit on an SM (its shared memory grows with the chain count); use exchange_mode 0");
     const int per_chain = (int)((gw + L - 1) / L + 1);
     if (per_chain > h->max_seg) h->max_seg = per_chain;
   }
@@ -676,7 +679,8 @@ int enqueue_iterations(smm_bgp *h, int n_iters) {
       }
       CUDA_TRY(prof_begin(h, 0));
       CUDA_TRY(launch_persistent(h->pb, h->st, it0, n, h->sched_iter0 < 0 ? 2 : h->sched_iter0, h->n_s, h->part_len,
-                                 h->max_seg, h->cta_seg, h->grid, h->mode == 2, s));
+                                 h->max_seg, h->cta_seg, h->grid, h->mode == 2, h->done_base, s));
+      if (h->mode == 2) h->done_base += (unsigned long long)h->N * (unsigned)n;  // every chain of every rank, n times
       CUDA_TRY(prof_end(h));
       h->prof_iters += h->profiling ? n : 0;
       h->ctr.kernel_launches++;
@@ -1073,8 +1077,10 @@ int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes) {
   IN(h->st.t_exch, int, n);
   IN(h->st.t_bestid, int, n);
 #undef IN
-  // completion tags / applied marks of exchange_mode 2 refer to iterations of the run that is being replaced
+  // completion counter / applied marks of exchange_mode 2 refer to the run that is being replaced.  (With several ranks
+  // every rank imports between the same two steps, and a step ends only when all ranks have finished it.)
   CUDA_TRY(cudaMemset(h->val_all.p + 2 * (size_t)h->N, 0, sizeof(double) * h->N));
+  h->done_base = 0;
   CUDA_TRY(cudaMemset(h->applied.p, 0, sizeof(unsigned) * L));
   h->iter = (int)hd.iter;
   h->sched_iter0 = -1;

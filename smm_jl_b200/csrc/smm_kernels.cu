@@ -697,9 +697,11 @@ __device__ __forceinline__ void slow_spin(double seconds) {
 // rank's gather buffer (peer stores over NVLink).
 // ------------------------------------------------------------------------------------------------
 // flow (barrier-free persistent kernel): wait_applied != 0 -> first wait until the owner CTA has applied the exchange
-// of iteration iter-1 to this chain (st.applied[c] >= iter-1); at the end publish the chain's completion tag (= iter)
-// to every rank, which is what the next iteration of every CTA waits for instead of a grid barrier.
-__device__ __forceinline__ unsigned long long *done_tags(const DevProblem &pb, double *val_all) {
+// of iteration iter-1 to this chain (st.applied[c] >= iter-1).  Completion is published per CTA, not per chain: see
+// publish_completions.
+// The completion counter of a rank (exchange_mode 2): ONE monotone 64-bit count of finished chain evaluations, over all
+// ranks, since the handle was created; every CTA adds the chains it finished to the counter of every rank.
+__device__ __forceinline__ unsigned long long *done_counter(const DevProblem &pb, double *val_all) {
   return (unsigned long long *)(val_all + 2 * (size_t)pb.N);
 }
 // The chain state doAcceptReject!/set_eval! read, fetched ahead of time by a 32-lane group (persistent kernel: before
@@ -853,16 +855,6 @@ __device__ void group_accept_store(const DevProblem &pb, const DevState &st, con
     }
   }
   gsync(g);
-  if (flow && tid == 0) {
-    // everything this group stored (ordered before this thread by the group sync) becomes visible before the tag
-    if (pb.world > 1) {
-      __threadfence_system();
-      for (int r = 0; r < pb.world; ++r) st_release_sys_u64(done_tags(pb, st.peer_val_all[r]) + gc, (unsigned long long)iter);
-    } else {
-      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(done_tags(pb, st.val_all) + gc), "l"((unsigned long long)iter)
-                   : "memory");
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1112,6 +1104,8 @@ __device__ __forceinline__ long long block_of(long long x, long long T, long lon
 }
 
 constexpr int kPGroups = 8;                      // proposal groups per CTA (128 threads each at most)
+constexpr int kExchWarps = 8;                    // warps walking the exchange levels when N > 512
+constexpr int kExchBarrier = 10;                 // their named barrier (0 = CTA, 1..kPGroups = proposal groups)
 constexpr int kPropCand = 2 * kPersistThreads;   // candidate slots shared by the groups
 constexpr int kMaxCtaSeg = 32;                   // chains (segments) one CTA may touch per iteration
 
@@ -1125,6 +1119,7 @@ struct PersistSmem {
   uint32_t seg_c2[kMaxCtaSeg];                       // counter word 2 of the segment's blocks (chain id with noseed, else 0)
   // per-iteration work queue
   int next_unit;
+  unsigned n_finished;  // chains this CTA finished in the current iteration
   int nlev;  // levels of the prefetched exchange schedule
   // proposals
   double g_pp[kPGroups][SMM_MAX_PARAMS];
@@ -1183,11 +1178,14 @@ __device__ void persistent_exchange(const DevProblem &pb, const DevState &st, in
     exch[i] = 0;
   }
   __syncthreads();
-  if (tid < 32) {
+  // The levels are walked by one warp (a __syncwarp per level) or, when the levels are wide (many chains over several
+  // GPUs), by kExchWarps warps with a named barrier per level; the pairs of a level share no chain.
+  const int nw = N > 512 ? kExchWarps : 1;
+  if (tid < 32 * nw) {
     unsigned n_swaps = 0;
     for (int l = 0; l < nlev; ++l) {
       const int lo = soff[l], hi = soff[l + 1];
-      for (int t = lo + tid; t < hi; t += 32) {
+      for (int t = lo + tid; t < hi; t += 32 * nw) {
         const int i = (int)(sij[t] & 0xffffu), j = (int)(sij[t] >> 16);
         const double vi = val[i], vj = val[j];
         const double thr = min_improve ? min_improve[i] : pb.min_improve[i];  // shared copy: no global load per level
@@ -1202,7 +1200,10 @@ __device__ void persistent_exchange(const DevProblem &pb, const DevState &st, in
           ++n_swaps;
         }
       }
-      __syncwarp();
+      if (nw == 1)
+        __syncwarp();
+      else
+        asm volatile("bar.sync %0, %1;" ::"n"(kExchBarrier), "r"(32 * nw) : "memory");
     }
     if (b == 0 && pb.chain0 == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
   }
@@ -1212,55 +1213,67 @@ __device__ void persistent_exchange(const DevProblem &pb, const DevState &st, in
   __syncthreads();
 }
 
-// Barrier-free hand-over between iterations: every CTA waits until all N chains (of every rank) carry the completion
-// tag of iteration `target` -- written by the warp that finished the chain, after its trace row, records and state.
-// The acquire loads plus the CTA barrier make those writes visible to the whole CTA.
-__device__ bool wait_all_done(const DevProblem &pb, const DevState &st, int target) {
-  __shared__ int s_bad[2];
-  const unsigned long long *tags = done_tags(pb, st.val_all);
-  const unsigned long long want = (unsigned long long)target;
-  const unsigned long long t0 = gtimer();
-  unsigned spins = 0;
-  if (threadIdx.x == 0) s_bad[0] = s_bad[1] = 0;
-  __syncthreads();
-  for (;;) {
-    // relaxed polls (no L1 invalidation per poll); one acquire fence once every tag has arrived
-    bool ok = true;
-    for (int i = threadIdx.x; i < pb.N; i += blockDim.x) {
+// Barrier-free hand-over between iterations: every CTA waits until the rank's completion counter says that all N chains
+// (of every rank) have finished the iteration -- their trace rows, records and state were stored before the finishing
+// CTA's fence and its add to the counter.  One thread polls one word; the acquire fence plus the CTA barrier make those
+// writes visible to the whole CTA.
+__device__ bool wait_all_done(const DevProblem &pb, const DevState &st, unsigned long long target) {
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) {
+    const unsigned long long *ctr = done_counter(pb, st.val_all);
+    const unsigned long long t0 = gtimer();
+    unsigned spins = 0;
+    int bad = 0;
+    for (;;) {
       unsigned long long v;
       if (pb.world > 1)
-        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(tags + i) : "memory");
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
       else
-        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(tags + i) : "memory");
-      ok = ok && v >= want;
-    }
-    ++spins;
-    if (threadIdx.x == 0 && (spins & 15u) == 0) {
-      int bad = 0;
-      if (ld_relaxed_gpu(&st.bar->gen) & 0x80000000u) bad = 1;  // another CTA gave up
-      if (gtimer() - t0 > kSpinTimeoutNs) {
-        atomicOr(st.err, kErrTimeout);
-        atomicOr(&st.bar->gen, 0x80000000u);
-        bad = 1;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
+      if ((++spins & 63u) == 0) {
+        if (ld_relaxed_gpu(&st.bar->gen) & 0x80000000u) bad = 1;  // another CTA gave up
+        if (gtimer() - t0 > kSpinTimeoutNs) {
+          atomicOr(st.err, kErrTimeout);
+          atomicOr(&st.bar->gen, 0x80000000u);
+          bad = 1;
+        }
+        if (bad) break;
       }
-      s_bad[spins & 1u] = bad;
     }
-    const int all_ok = __syncthreads_and(ok);
-    if (s_bad[spins & 1u]) return false;
-    if (all_ok) break;
+    if (pb.world > 1)
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else
+      fence_acq_rel_gpu();
+    s_bad = bad;
   }
-  if (pb.world > 1)
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
-  else
-    fence_acq_rel_gpu();
   __syncthreads();
-  return true;
+  return s_bad == 0;
+}
+
+// The other half: after the CTA's finishing warps have stored everything (CTA barrier by the caller), one thread fences
+// once -- system scope when the records went to peer GPUs -- and adds the number of chains this CTA finished to the
+// completion counter of every rank (a remote atomic over NVLink for the peers).
+__device__ __forceinline__ void publish_completions(const DevProblem &pb, const DevState &st, unsigned n_finished) {
+  if (n_finished == 0) return;
+  if (pb.world > 1) {
+    __threadfence_system();
+    for (int r = 0; r < pb.world; ++r)
+      asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(done_counter(pb, st.peer_val_all[r])),
+                   "l"((unsigned long long)n_finished)
+                   : "memory");
+  } else {
+    fence_acq_rel_gpu();
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(done_counter(pb, st.val_all)),
+                 "l"((unsigned long long)n_finished)
+                 : "memory");
+  }
 }
 
 // One warp completes segment s of its CTA: publish the CTA's exact partial sums; if this was the last CTA of
 // the chain, finish the chain (moments, distance, accept/reject, trace, record) -- all inside the warp, while
 // the other 31 warps keep simulating.
-__device__ void warp_publish_segment(const DevProblem &pb, const DevState &st, PersistSmem &sm, int s, int it,
+__device__ bool warp_publish_segment(const DevProblem &pb, const DevState &st, PersistSmem &sm, int s, int it,
                                      bool fused, int part_len, int max_seg, const unsigned long long *acc,
                                      double *pp_seg, double *fscratch, int fs_len, bool flow = false,
                                      const unsigned short *exch = nullptr) {
@@ -1287,7 +1300,7 @@ __device__ void warp_publish_segment(const DevProblem &pb, const DevState &st, P
     if (last) st_relaxed_gpu(st.arrive + c, 0u);  // re-arm (ordered before the next iteration by the grid barrier)
   }
   last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) return;
+  if (!last) return false;
   double *f = fscratch + (size_t)s * fs_len;
   const FinScratch fs{pp_seg + (size_t)s * D, f, f + 2 * D, f + 2 * D + pb.M, (int *)(f + 2 * D + pb.M + 2)};
   if (st.phase_ts && lane == 0) st.phase_ts[(size_t)((blockIdx.x * 2 + (it & 1)) * 2 + 1) * 4 + 2] = t_pub;
@@ -1301,6 +1314,7 @@ __device__ void warp_publish_segment(const DevProblem &pb, const DevState &st, P
     row[2] = blockIdx.x;
     row[3] = (unsigned long long)it;
   }
+  return true;
 }
 
 // dynamic smem: val[N] (double) own[N] exch[N] (u16) | pp_seg[n][D] | acc[n][2D] (u64) | fscratch[n][2D+M+4] |
@@ -1315,7 +1329,8 @@ __device__ void warp_publish_segment(const DevProblem &pb, const DevState &st, P
 template <bool kFlow>
 __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevProblem pb, DevState st, int iter0,
                                                                             int n_iters, int sched_iter0, int n_s,
-                                                                            int part_len, int max_seg, int cta_seg) {
+                                                                            int part_len, int max_seg, int cta_seg,
+                                                                            unsigned long long done_base) {
   __shared__ PersistSmem sm;
   __shared__ unsigned long long s_zigtab[kZigBufEntries];  // 16 KB: the 8 KB-aligned half holds the table (see load_zigtab)
   extern __shared__ double smem_d[];
@@ -1397,7 +1412,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
     bool have_ex = false;
     if (kFlow) {
       // ---- wait for iteration it-1 of every chain, replay its exchange, propose for the chains simulated here ----
-      if (it > iter0 && !wait_all_done(pb, st, it - 1)) return;
+      if (it > iter0 && !wait_all_done(pb, st, done_base + (unsigned long long)N * (unsigned)(it - iter0))) return;
       PHASE_STAMP((b * 2 + (it & 1)) * 2, 3);
       have_ex = N > 1 && it - 1 >= 2 && it > iter0;
       if (have_ex && (n_owned > 0 || n_seg > 0))
@@ -1440,7 +1455,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
     if (!kFlow)
       for (int e = tid; e < n_seg * D; e += kPersistThreads) pp_seg[e] = __ldcg(st.pp + (size_t)sm.seg_c[e / D] * P + e % D);
     for (int e = tid; e < n_seg * 2 * D; e += kPersistThreads) acc[e] = 0ull;
-    if (tid == 0) sm.next_unit = static_units * (kPersistThreads / 32);
+    if (tid == 0) {
+      sm.next_unit = static_units * (kPersistThreads / 32);
+      sm.n_finished = 0u;
+    }
     if ((n_owned > 0 || (kFlow && n_seg > 0)) && N > 1 && it >= 2) prefetch_schedule(st, it, sched_iter0, n_s, sij, soff, &sm.nlev);
     __syncthreads();
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
@@ -1566,9 +1584,15 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
     // The CTA's sums of every chain it touched are complete: one warp per segment publishes them; the warp that brings
     // the last partial of a chain finishes the chain (moments, distance, accept/reject, trace, record, completion tag).
     for (int sp = tid >> 5; sp < n_seg; sp += kPersistThreads / 32)
-      warp_publish_segment(pb, st, sm, sp, it, fused, part_len, max_seg, acc, pp_seg, fscratch, fs_len, kFlow,
-                           have_ex ? exch : nullptr);
+      if (warp_publish_segment(pb, st, sm, sp, it, fused, part_len, max_seg, acc, pp_seg, fscratch, fs_len, kFlow,
+                               have_ex ? exch : nullptr) &&
+          lane == 0)
+        atomicAdd(&sm.n_finished, 1u);
     PHASE_STAMP((b * 2 + (it & 1)) * 2, 2);  // warp 0 done (incl. chain finalisation)
+    if (kFlow) {  // one fence and one counter update per CTA tell every rank which chains are complete
+      __syncthreads();
+      if (tid == 0) publish_completions(pb, st, sm.n_finished);
+    }
     if (!kFlow) {
       if (!grid_barrier(pb, st, gen, fused, seq)) return;
       PHASE_STAMP((b * 2 + (it & 1)) * 2, 3);
@@ -1576,7 +1600,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
   }
   // ---- exchange of the last iteration of this launch ----
   const int pit = iter0 + n_iters - 1;
-  if (kFlow && n_owned > 0 && !wait_all_done(pb, st, pit)) return;
+  if (kFlow && n_owned > 0 && !wait_all_done(pb, st, done_base + (unsigned long long)N * (unsigned)n_iters)) return;
   if (n_owned > 0 && N > 1 && pit >= 2)
     persistent_exchange(pb, st, pit, fused, val, own, exch, sij, soff, sm.nlev, false, true, mi);
   if (!kFlow && b == 0 && tid == 0) *st.sync_seq = seq;
@@ -1946,10 +1970,11 @@ void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sch
   bgp_exchange_kernel<<<1, kExchThreads, exch_smem_bytes(pb.N), s>>>(pb, st, iter, sched_idx, n_s);
 }
 cudaError_t launch_persistent(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int sched_iter0,
-                              int n_s, int part_len, int max_seg, int cta_seg, int grid, bool flow, cudaStream_t s) {
+                              int n_s, int part_len, int max_seg, int cta_seg, int grid, bool flow,
+                              unsigned long long done_base, cudaStream_t s) {
   DevProblem pbc = pb;
   DevState stc = st;
-  void *args[] = {&pbc, &stc, &iter0, &n_iters, &sched_iter0, &n_s, &part_len, &max_seg, &cta_seg};
+  void *args[] = {&pbc, &stc, &iter0, &n_iters, &sched_iter0, &n_s, &part_len, &max_seg, &cta_seg, &done_base};
   void *fn = flow ? (void *)bgp_persistent_kernel<true> : (void *)bgp_persistent_kernel<false>;
   return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPersistThreads), args,
                                      persist_smem_bytes(pb.N, pb.P, pb.M, cta_seg), s);

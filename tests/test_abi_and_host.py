@@ -151,3 +151,56 @@ def test_temperature_ladder_and_shards():
     assert owner_of(129, 1024, 8) == 1
     with pytest.raises(ValueError):
         shard_range(10, 4, 0)
+
+
+def _toy_problem(api, n_params=2, objective=None):
+    m = api.MProb()
+    for k in range(n_params):
+        api.addSampledParam(m, f"p{k}", 0.1, -1.0, 1.0)
+    for k in range(n_params):
+        api.addMoment(m, f"m{k}", 0.0, 1.0)
+    api.addEvalFunc(m, objective or api.objfunc_norm)
+    return m
+
+
+def test_exchange_mode_selection_and_fallback(monkeypatch):
+    """the host mirror picks the barrier-free persistent kernel for every world size, the multi-launch kernels for
+    the panel objective / more than 32 parameters, never overrides an explicit request, and falls back to mode 0 when
+    the library says the persistent kernel does not fit the shape (SMM_E_UNSUPPORTED_SHAPE)"""
+    from smm_jl_b200 import api, _lib
+    from smm_jl_b200._abi import SMM_E_UNSUPPORTED_SHAPE, SMM_E_CUDA
+    m = _toy_problem(api)
+    assert api._exchange_mode(m, {}, 2) == 2
+    assert api._exchange_mode(m, {"world_size": 8}, 2) == 2
+    assert api._exchange_mode(m, {"exchange_mode": 1, "world_size": 8}, 2) == 1
+    assert api._exchange_mode(m, {}, 40) == 0
+    assert api._exchange_mode(_toy_problem(api, 2, api.objfunc_panel), {}, 2) == 0
+
+    created = []
+
+    class FakeHandle:
+        def __init__(self, cfg):
+            created.append(cfg.exchange_mode)
+            if cfg.exchange_mode != 0:
+                raise _lib.SMMError(SMM_E_UNSUPPORTED_SHAPE, "persistent kernel does not fit on an SM")
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(_lib, "BGPHandle", FakeHandle)
+    algo = api.MAlgoBGP(m, {"N": 4, "maxiter": 5})
+    algo._handle()
+    assert created == [2, 0] and algo._cfg.exchange_mode == 0
+    created.clear()
+    algo = api.MAlgoBGP(m, {"N": 4, "maxiter": 5, "exchange_mode": 1})      # explicit: the error surfaces
+    with pytest.raises(_lib.SMMError):
+        algo._handle()
+    assert created == [1]
+
+    class Broken(FakeHandle):
+        def __init__(self, cfg):
+            raise _lib.SMMError(SMM_E_CUDA, "no such CUDA device")
+
+    monkeypatch.setattr(_lib, "BGPHandle", Broken)
+    with pytest.raises(_lib.SMMError):                                        # other failures are never retried
+        api.MAlgoBGP(m, {"N": 4, "maxiter": 5})._handle()

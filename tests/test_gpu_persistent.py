@@ -37,7 +37,7 @@ def test_c1_persistent(smm, pmode, oracle, niter):
     assert ctr["swaps"] == ref.swaps and ctr["proposal_attempts"] == ref.attempts
 
 
-@pytest.mark.parametrize("n_chains,n_split", [(16, 0), (64, 0), (64, 40), (300, 0), (1, 0)])
+@pytest.mark.parametrize("n_chains,n_split", [(16, 0), (64, 0), (64, 40), (300, 0), (1, 0), (1024, 0)])
 def test_mvnormal_persistent(smm, pmode, oracle, n_chains, n_split):
     niter = 30
     cfg = configs.mvnormal(n_chains, niter, exchange_mode=pmode, n_split=n_split, n_sim=2000)
