@@ -137,6 +137,13 @@ int smm_nccl_unique_id(uint8_t out[SMM_NCCL_ID_BYTES]);
 
 int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out);
 void smm_bgp_destroy(smm_bgp *h);
+/* Process-wide caches behind create/destroy: CUDA streams and events per device; with world_size > 1 the NCCL
+ * communicator of (device, world_size, rank) and the CUDA-IPC mapped exchange arena the peers store their records
+ * into.  They are made by the first handle (ncclCommInitRank from cfg->nccl_id, ~1 s at 8 ranks) and handed to every
+ * later handle of the same (device, world_size, rank), whose nccl_id is then not looked at -- all ranks of a job
+ * create their handles in the same order, so the cache hits on every rank or on none.  smm_shutdown() ends them
+ * (every handle must have been destroyed); the next smm_bgp_create starts over with a fresh nccl_id. */
+void smm_shutdown(void);
 
 /* run iterations i+1 .. i+n_iters; blocking (returns after the device finished and the sticky
  * device error flag was checked).  elapsed_ms (may be NULL) receives the CUDA-event time of the

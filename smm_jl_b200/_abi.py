@@ -190,7 +190,7 @@ class BGPConfig:
         s.seed_algo = int(self.seed_algo)
         s.device, s.world_size, s.rank = int(self.device), int(self.world_size), int(self.rank)
         idb = bytes(self.nccl_id)[:SMM_NCCL_ID_BYTES].ljust(SMM_NCCL_ID_BYTES, b"\0")
-        s.nccl_id[:] = list(idb)
+        C.memmove(s.nccl_id, idb, SMM_NCCL_ID_BYTES)
         s.exchange_mode = int(self.exchange_mode)
         s.n_split = int(self.n_split)
         return s

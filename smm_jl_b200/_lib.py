@@ -22,7 +22,7 @@ EXPORTS = [
     "smm_bgp_state_bytes", "smm_bgp_export_state", "smm_bgp_import_state", "smm_debug_normals", "smm_debug_zig_normals",
     "smm_debug_pairs", "smm_debug_rng_throughput", "smm_stream_acc_uniforms", "smm_bgp_set_profiling",
     "smm_bgp_kernel_times", "smm_debug_phase_ts", "smm_debug_sim_throughput", "smm_debug_barrier_bench",
-    "smm_bgp_run", "smm_host_alloc", "smm_host_free",
+    "smm_bgp_run", "smm_host_alloc", "smm_host_free", "smm_shutdown",
 ]
 
 
@@ -59,6 +59,7 @@ def lib():
     L.smm_host_alloc.argtypes = [C.c_int64, C.POINTER(vp)]
     L.smm_host_free.argtypes = [vp]
     L.smm_host_free.restype = None
+    L.smm_shutdown.restype = None
     L.smm_bgp_local_chains.argtypes = [vp]
     L.smm_bgp_stream.argtypes = [vp]
     L.smm_bgp_stream.restype = vp
@@ -81,6 +82,8 @@ def lib():
     L.smm_debug_barrier_bench.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
     L.smm_debug_sim_throughput.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
     _lib = L
+    import atexit
+    atexit.register(L.smm_shutdown)   # cached communicators / exchange arenas / streams end with the process
     return L
 
 

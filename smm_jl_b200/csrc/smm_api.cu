@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -95,14 +96,16 @@ struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
   bool plain = false;
+  bool owned = true;  // false: carved out of the handle's slab (or the exchange arena) by SlabPlan
   cudaError_t alloc(size_t count, bool ipc = false) {
     n = count;
     plain = ipc;
+    owned = true;
     if (ipc) return cudaMalloc((void **)&p, sizeof(T) * (count ? count : 1));
     return cudaMallocAsync((void **)&p, sizeof(T) * (count ? count : 1), (cudaStream_t)0);
   }
   void free() {
-    if (p) {
+    if (p && owned) {
       if (plain)
         cudaFree(p);
       else
@@ -111,6 +114,205 @@ struct DevBuf {
     p = nullptr;
   }
 };
+
+// ---- one allocation, one upload, one initialisation kernel per handle ---------------------------------------------
+// smm_bgp_create used to make ~45 pool allocations, 8 blocking cudaMemcpy and ~30 fill launches (0.4 ms, a third of a
+// short run).  Now every buffer of a handle is a 256-byte aligned piece of ONE stream-ordered allocation (space 0) --
+// the buffers the peers write into live in the process-wide exchange arena instead (space 1, CUDA IPC) -- the
+// problem definition travels in ONE cudaMemcpyAsync, and ONE kernel writes every initial value.
+constexpr int kMaxInitSegs = 56;
+struct InitSeg {
+  void *p;
+  unsigned long long n16;  // 16-byte words to fill
+  unsigned long long pat;  // 8-byte pattern (narrower element values are replicated)
+};
+struct InitTable {
+  int n;
+  InitSeg seg[kMaxInitSegs];
+};
+
+__global__ void __launch_bounds__(256) init_kernel(InitTable t) {
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+  for (int s = 0; s < t.n; ++s) {
+    ulonglong2 *p = (ulonglong2 *)t.seg[s].p;
+    const ulonglong2 v = make_ulonglong2(t.seg[s].pat, t.seg[s].pat);
+    for (size_t i = gtid; i < t.seg[s].n16; i += gsz) p[i] = v;
+  }
+}
+
+template <typename T>
+unsigned long long fill_pattern(T v) {
+  unsigned long long pat = 0;
+  unsigned char *b = (unsigned char *)&pat;
+  static_assert(sizeof(T) <= 8 && 8 % sizeof(T) == 0, "element size must divide 8");
+  for (size_t i = 0; i < 8; i += sizeof(T)) memcpy(b + i, &v, sizeof(T));
+  return pat;
+}
+
+struct SlabPlan {
+  struct Item {
+    void **pp;
+    size_t bytes, off;
+    int space;
+    bool fill;
+    unsigned long long pat;
+    const void *src;  // host data to upload (space 0 only), or null
+  };
+  std::vector<Item> items;
+  size_t total[2] = {0, 0};
+  static size_t pad(size_t b) { return (b + 255) / 256 * 256; }
+  template <typename T>
+  void add(DevBuf<T> &b, size_t n, int space, bool fill, T v, const T *src = nullptr) {
+    b.n = n;
+    b.owned = false;
+    b.plain = false;
+    const size_t bytes = pad(sizeof(T) * (n ? n : 1));
+    items.push_back({(void **)&b.p, bytes, total[space], space, fill && n > 0, fill_pattern(v), (const void *)src});
+    if (src) items.back().bytes = sizeof(T) * n;  // uploaded pieces: exact length (the padding is not copied)
+    total[space] += bytes;
+  }
+  template <typename T>
+  void filled(DevBuf<T> &b, size_t n, T v, int space = 0) { add(b, n, space, true, v); }
+  template <typename T>
+  void upload(DevBuf<T> &b, const T *src, size_t n) { add(b, n, 0, false, T(), src); }
+  void assign(void *base0, void *base1) {
+    for (Item &it : items) *it.pp = (char *)(it.space ? base1 : base0) + it.off;
+  }
+};
+
+// ---- process-wide caches: streams/events per device, communicator + exchange arena per (device, world, rank) -------
+// A C2 ensemble is at most ~1000 iterations (60 ms), so estimations create handles over and over: stream / event
+// creation, ncclCommInitRank (~1 s at 8 ranks) and the CUDA-IPC mapping of the peers' gather buffers (~0.3 s) must
+// not be paid per handle.  They are made once per process and handed from handle to handle; smm_shutdown() (or
+// process exit) ends them.
+struct StreamSet {
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int *h_err = nullptr;  // page-locked word the sticky device error flag is copied into
+};
+
+struct Arena {  // cudaMalloc'ed memory of this rank that every peer has mapped (and vice versa)
+  void *base = nullptr;
+  size_t bytes = 0;
+  void *peer[kMaxWorld] = {nullptr};  // [rank] = base
+};
+
+struct RankCtx {
+  int device = 0, world = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  Arena arena;
+  bool arena_busy = false;  // one live handle at a time uses the cached arena; a second one maps its own
+  float *d_token = nullptr;  // operand of the cross-rank barrier (a one-element all-reduce)
+};
+
+std::mutex g_cache_mu;
+std::vector<StreamSet> g_stream_cache[64];
+std::vector<RankCtx *> g_rank_ctx;
+
+cudaError_t stream_set_acquire(int device, StreamSet &out) {
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (device >= 0 && device < 64 && !g_stream_cache[device].empty()) {
+      out = g_stream_cache[device].back();
+      g_stream_cache[device].pop_back();
+      return cudaSuccess;
+    }
+  }
+  out = StreamSet();
+  cudaError_t e = cudaStreamCreateWithFlags(&out.stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&out.copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&out.ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&out.ev1);
+  if (e == cudaSuccess) e = cudaHostAlloc((void **)&out.h_err, sizeof(int), cudaHostAllocDefault);
+  return e;
+}
+
+void stream_set_destroy(StreamSet &ss) {
+  if (ss.ev0) cudaEventDestroy(ss.ev0);
+  if (ss.ev1) cudaEventDestroy(ss.ev1);
+  if (ss.copy_stream) cudaStreamDestroy(ss.copy_stream);
+  if (ss.stream) cudaStreamDestroy(ss.stream);
+  if (ss.h_err) cudaFreeHost(ss.h_err);
+  ss = StreamSet();
+}
+
+void stream_set_release(int device, StreamSet &ss) {  // the streams are idle (the caller synchronised them)
+  if (!ss.stream) return;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  if (device >= 0 && device < 64 && g_stream_cache[device].size() < 4) {
+    g_stream_cache[device].push_back(ss);
+    ss = StreamSet();
+  } else {
+    stream_set_destroy(ss);
+  }
+}
+
+void arena_destroy(Arena &a, int rank) {
+  for (int r = 0; r < kMaxWorld; ++r) {
+    if (a.peer[r] && r != rank) cudaIpcCloseMemHandle(a.peer[r]);
+    a.peer[r] = nullptr;
+  }
+  if (a.base) cudaFree(a.base);
+  a.base = nullptr;
+  a.bytes = 0;
+}
+
+// collective over the communicator: allocate `bytes` on every rank and map everybody's allocation everywhere
+int arena_create(Arena &a, ncclComm_t comm, int world, int rank, size_t bytes, cudaStream_t s) {
+  CUDA_TRY(cudaMalloc(&a.base, bytes));
+  a.bytes = bytes;
+  a.peer[rank] = a.base;
+  cudaIpcMemHandle_t mine;
+  CUDA_TRY(cudaIpcGetMemHandle(&mine, a.base));
+  char *d_all = nullptr;  // the handles travel over the communicator
+  CUDA_TRY(cudaMalloc((void **)&d_all, sizeof(mine) * (size_t)world));
+  cudaError_t ce = cudaMemcpyAsync(d_all + sizeof(mine) * (size_t)rank, &mine, sizeof mine, cudaMemcpyHostToDevice, s);
+  ncclResult_t nr = ncclSuccess;
+  if (ce == cudaSuccess)
+    nr = ncclAllGather(d_all + sizeof(mine) * (size_t)rank, d_all, sizeof(mine), ncclChar, comm, s);
+  std::vector<cudaIpcMemHandle_t> all(world);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  if (ce == cudaSuccess) ce = cudaMemcpy(all.data(), d_all, sizeof(mine) * (size_t)world, cudaMemcpyDeviceToHost);
+  cudaFree(d_all);
+  NCCL_TRY(nr);
+  CUDA_TRY(ce);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    CUDA_TRY(cudaIpcOpenMemHandle(&a.peer[r], all[r], cudaIpcMemLazyEnablePeerAccess));
+  }
+  return 0;
+}
+
+// the communicator of (device, world, rank): made from `id` on first use, reused afterwards (the id of later handles is
+// not looked at -- every rank of a job makes the same sequence of handles, so the cache hits on all ranks or on none)
+int rank_ctx_get(int device, int world, int rank, const uint8_t *id_bytes, RankCtx **out) {
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (RankCtx *c : g_rank_ctx)
+      if (c->device == device && c->world == world && c->rank == rank) {
+        *out = c;
+        return 0;
+      }
+  }
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof id);
+  ncclComm_t comm = nullptr;
+  NCCL_TRY(ncclCommInitRank(&comm, world, id, rank));
+  RankCtx *c = new RankCtx();
+  c->device = device;
+  c->world = world;
+  c->rank = rank;
+  c->comm = comm;
+  if (cudaMalloc((void **)&c->d_token, sizeof(float)) != cudaSuccess || cudaMemset(c->d_token, 0, sizeof(float)) != cudaSuccess) {
+    ncclCommDestroy(comm);
+    delete c;
+    return fail(SMM_E_CUDA, "cudaMalloc of the barrier token failed");
+  }
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  g_rank_ctx.push_back(c);
+  *out = c;
+  return 0;
+}
 
 }  // namespace
 
@@ -124,17 +326,22 @@ struct smm_bgp {
   int panel_grid = 0;     // CTAs of the panel simulation kernel (one resident wave)
   int panel_variant = 2;  // register budget of the K = 8 instantiation (CTAs per SM)
   std::vector<double> h_lb, h_ub;
+  uint64_t seed_algo = 0, seed_sim = 0;
   int mode = 0;           // 0 = multi-launch (+ NCCL), 1 = persistent kernel (+ fused peer-store all-gather),
-                          // 2 = persistent kernel without grid barriers (per-chain completion tags)
+                          // 2 = persistent kernel without grid barriers (one completion counter per rank)
   int grid = 0, max_seg = 1, cta_seg = 1;  // persistent kernel: CTAs, partial slots per chain, chains per CTA share
-  void *peer_ptrs[3 * kMaxWorld] = {nullptr};  // IPC-opened peer buffers (closed in release)
   int iter = 0;      // iterations completed (algo.i)
   unsigned long long done_base = 0;  // exchange_mode 2: value of the completion counter once everything enqueued has run
   int sched_iter0 = -1, sched_n = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  StreamSet ss;      // from the per-device cache
+  cudaStream_t stream = nullptr, copy_stream = nullptr;  // = ss.stream, ss.copy_stream
   std::vector<cudaEvent_t> win_ev;  // window boundaries of smm_bgp_run
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  ncclComm_t comm = nullptr;
+  RankCtx *ctx = nullptr;    // world > 1: cached communicator (+ exchange arena)
+  ncclComm_t comm = nullptr;  // = ctx->comm
+  Arena own_arena;            // only when the cached arena was busy
+  bool uses_ctx_arena = false;
+  void *slab = nullptr;       // every private device buffer of the handle
   DevProblem pb{};
   DevState st{};
   smm_counters ctr{};
@@ -144,7 +351,7 @@ struct smm_bgp {
   double prof_ms[4] = {0, 0, 0, 0};
   int64_t prof_iters = 0;                    // iterations covered by the kind-0 launches
   int64_t prof_n[4] = {0, 0, 0, 0};
-  // owned device memory
+  // device memory (pieces of `slab` / of the exchange arena)
   DevBuf<double> lb, ub, init, data, w, acc_tuner, min_improve;
   DevBuf<double> sigma, accept_rate, la_cur, la_pub, la_all, val_all, pp;
   DevBuf<GridBarrier> bar;
@@ -159,34 +366,30 @@ struct smm_bgp {
   DevBuf<unsigned long long> counters, phase_ts;
 
   void release() {
-    // the buffers go back to the pool in legacy-stream order: drain this handle's own streams first
+    // the slab goes back to the pool in stream order: drain this handle's own streams first
     if (stream) cudaStreamSynchronize(stream);
     if (copy_stream) cudaStreamSynchronize(copy_stream);
-    for (void *&q : peer_ptrs) {
-      if (q) cudaIpcCloseMemHandle(q);
-      q = nullptr;
+    if (uses_ctx_arena && ctx) {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      ctx->arena_busy = false;
     }
-    if (comm) ncclCommDestroy(comm);
-    comm = nullptr;
-    val_all.free(); pp.free(); bar.free(); sync_seq.free(); flags.free(); applied.free();
-    lb.free(); ub.free(); init.free(); data.free(); w.free(); acc_tuner.free(); min_improve.free();
-    sigma.free(); accept_rate.free(); la_cur.free(); la_pub.free(); la_all.free();
-    n_noex.free(); n_acc.free();
-    t_value.free(); t_prob.free(); t_curr.free(); t_best.free(); t_params.free(); t_mom.free();
-    t_acc.free(); t_status.free(); t_exch.free(); t_bestid.free();
-    partials.free(); arrive.free(); unit_ctr.free(); sched_ij.free(); sched_off.free(); sched_nlev.free(); err.free();
-    counters.free(); phase_ts.free();
+    uses_ctx_arena = false;
+    arena_destroy(own_arena, rank);
+    comm = nullptr;  // owned by the cache
+    if (slab) {
+      if (stream)
+        cudaFreeAsync(slab, stream);
+      else
+        cudaFree(slab);
+    }
+    slab = nullptr;
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
     prof_ev.clear();
     for (cudaEvent_t e : win_ev) cudaEventDestroy(e);
     win_ev.clear();
-    if (copy_stream) cudaStreamDestroy(copy_stream);
-    copy_stream = nullptr;
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
+    stream_set_release(device, ss);
+    stream = copy_stream = nullptr;
     ev0 = ev1 = nullptr;
-    stream = nullptr;
   }
 };
 
@@ -245,29 +448,6 @@ int check_config(const smm_bgp_config *cfg) {
   if (cfg->n_chains % cfg->world_size != 0)
     return fail(SMM_E_UNSUPPORTED_SHAPE, "n_chains must be a multiple of world_size");
   if (cfg->n_chains > 8192) return fail(SMM_E_UNSUPPORTED_SHAPE, "n_chains > 8192 not supported");
-  return 0;
-}
-
-template <typename T>
-int upload(DevBuf<T> &buf, const T *src, size_t n) {
-  CUDA_TRY(buf.alloc(n));
-  CUDA_TRY(cudaMemcpy(buf.p, src, sizeof(T) * n, cudaMemcpyHostToDevice));
-  return 0;
-}
-
-template <typename T>
-__global__ void fill_kernel(T *p, size_t n, T v) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
-}
-
-// allocate + fill on the device (asynchronous on the legacy stream; smm_bgp_create synchronises at its end)
-template <typename T>
-int fill(DevBuf<T> &buf, size_t n, T v, bool ipc = false) {
-  CUDA_TRY(buf.alloc(n, ipc));
-  if (n == 0) return 0;
-  const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
-  fill_kernel<T><<<blocks, 256>>>(buf.p, n, v);
-  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -375,52 +555,21 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   h->n_s = h->N < 3 ? h->N - 1 : h->N;
   const int P = h->P, M = h->M, N = h->N, L = h->L, R = h->R, I = h->max_iter;
 
-  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreate(&h->ev0));
-  CUDA_TRY(cudaEventCreate(&h->ev1));
-
+  CUDA_TRY(stream_set_acquire(cfg->device, h->ss));
+  h->stream = h->ss.stream;
+  h->copy_stream = h->ss.copy_stream;
+  h->ev0 = h->ss.ev0;
+  h->ev1 = h->ss.ev1;
+  *h->ss.h_err = 0;
   stamp("stream + events");
-  if (int rc = upload(h->lb, cfg->lb, P)) return rc;
-  if (int rc = upload(h->ub, cfg->ub, P)) return rc;
-  if (int rc = upload(h->init, cfg->init, P)) return rc;
-  if (int rc = upload(h->data, cfg->data_mom, M)) return rc;
-  if (int rc = upload(h->w, cfg->data_w, M)) return rc;
-  if (int rc = upload(h->acc_tuner, cfg->acc_tuner, N)) return rc;
-  if (int rc = upload(h->min_improve, cfg->min_improve, N)) return rc;
-  if (int rc = upload(h->sigma, cfg->sigma0 + h->chain0, L)) return rc;
-  if (int rc = fill(h->accept_rate, (size_t)L, 0.0)) return rc;
-  if (int rc = fill(h->n_noex, (size_t)L, 0)) return rc;
-  if (int rc = fill(h->n_acc, (size_t)L, 0)) return rc;
-  const double nan = std::numeric_limits<double>::quiet_NaN(), inf = std::numeric_limits<double>::infinity();
-  if (int rc = fill(h->la_cur, (size_t)L * R, nan)) return rc;
-  if (int rc = fill(h->la_pub, (size_t)L * R, nan)) return rc;
+
   if (cfg->exchange_mode < 0 || cfg->exchange_mode > 2) return fail(SMM_E_ARG, "exchange_mode must be 0, 1 or 2");
   h->mode = cfg->exchange_mode;
-  if (h->world > 1 || h->mode == 2) {
-    if (int rc = fill(h->la_all, (size_t)(h->mode ? 2 : 1) * N * R, nan, h->world > 1 && h->mode >= 1)) return rc;
-  }
-  // [2][N] values by iteration parity, followed by [N] 64-bit completion tags (exchange_mode 2), zero = nothing done
-  if (int rc = fill(h->val_all, (size_t)3 * N, nan, h->world > 1 && h->mode >= 1)) return rc;
-  CUDA_TRY(cudaMemset(h->val_all.p + 2 * (size_t)N, 0, sizeof(double) * N));
-  if (int rc = fill(h->applied, (size_t)L, 0u)) return rc;
-  if (int rc = fill(h->pp, (size_t)L * P, nan)) return rc;
-  if (int rc = fill(h->bar, 1, GridBarrier{0u, 0u})) return rc;
-  if (int rc = fill(h->sync_seq, 1, 0ull)) return rc;
-  if (int rc = fill(h->flags, (size_t)kMaxWorld, 0ull, h->world > 1 && h->mode >= 1)) return rc;
-  // trace: unrun slots look like a fresh BGPChain (AlgoBGP.jl:81-89); Eval slots are `undef` -> NaN
-  const size_t IL = (size_t)I * L;
-  if (int rc = fill(h->t_value, IL, nan)) return rc;
-  if (int rc = fill(h->t_prob, IL, nan)) return rc;
-  if (int rc = fill(h->t_curr, IL, inf)) return rc;
-  if (int rc = fill(h->t_best, IL, inf)) return rc;
-  if (int rc = fill(h->t_params, IL * P, nan)) return rc;
-  if (int rc = fill(h->t_mom, IL * M, nan)) return rc;
-  if (int rc = fill(h->t_acc, IL, (uint8_t)0)) return rc;
-  if (int rc = fill(h->t_status, IL, 0)) return rc;
-  if (int rc = fill(h->t_exch, IL, 0)) return rc;
-  if (int rc = fill(h->t_bestid, IL, -1)) return rc;
+  if (h->world > kMaxWorld) return fail(SMM_E_ARG, "world_size > 8");
+  h->seed_algo = cfg->seed_algo;
+  h->seed_sim = cfg->seed_sim;
 
-  stamp("buffers + trace fill");
+  // ---- kernel configuration (host-side arithmetic and function attributes; no device work) ----
   struct {
     int multiProcessorCount = 0;
   } prop;  // (cudaGetDeviceProperties costs milliseconds; one attribute is all that is needed)
@@ -442,7 +591,6 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     h->panel_grid = prop.multiProcessorCount * per_sm;
     if (cfg->n_split > 0 && cfg->n_split < h->panel_grid) h->panel_grid = cfg->n_split;  // n_split caps the CTA count
   }
-  if (int rc = fill(h->unit_ctr, 1, 0u)) return rc;
   if (N > 1) CUDA_TRY(configure_kernels(N, h->n_s));
   h->max_seg = h->n_split;
   if (h->mode >= 1) {
@@ -451,7 +599,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     if (!coop) return fail(SMM_E_CUDA, "device does not support cooperative launches (exchange_mode 1)");
     if (P > 32)
       return fail(SMM_E_UNSUPPORTED_SHAPE, "exchange_mode 1/2 (persistent kernel) needs n_params <= 32; use exchange_mode 0");
-    h->grid = prop.multiProcessorCount;  // one 1024-thread CTA per SM
+    h->grid = prop.multiProcessorCount;  // one 768-thread CTA per SM
     if (cfg->n_split > 0 && cfg->n_split < h->grid) h->grid = cfg->n_split;  // n_split caps the CTA count in this mode
     const long long Tj = (long long)L * n_blocks_philox;
     const long long gw = Tj < h->grid ? Tj : h->grid;
@@ -465,15 +613,129 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     const int per_chain = (int)((gw + L - 1) / L + 1);
     if (per_chain > h->max_seg) h->max_seg = per_chain;
   }
-  if (int rc = fill(h->partials, (size_t)L * h->max_seg * h->part_len, 0.0)) return rc;
-  if (int rc = fill(h->arrive, (size_t)L, 0u)) return rc;
+  stamp("kernel configuration");
+
+  // ---- memory plan: every buffer of the handle is a piece of one allocation ----
+  const double nan = std::numeric_limits<double>::quiet_NaN(), inf = std::numeric_limits<double>::infinity();
+  const bool fused_peers = h->world > 1 && h->mode >= 1;  // the peers store into la_all / val_all / flags
+  const int xs = fused_peers ? 1 : 0;                     // ... which then live in the exchange arena
+  SlabPlan plan;
+  plan.upload(h->lb, cfg->lb, P);
+  plan.upload(h->ub, cfg->ub, P);
+  plan.upload(h->init, cfg->init, P);
+  plan.upload(h->data, cfg->data_mom, M);
+  plan.upload(h->w, cfg->data_w, M);
+  plan.upload(h->acc_tuner, cfg->acc_tuner, N);
+  plan.upload(h->min_improve, cfg->min_improve, N);
+  plan.upload(h->sigma, cfg->sigma0 + h->chain0, L);
+  const size_t upload_end = plan.total[0];
+  plan.filled(h->accept_rate, (size_t)L, 0.0);
+  plan.filled(h->n_noex, (size_t)L, 0);
+  plan.filled(h->n_acc, (size_t)L, 0);
+  plan.filled(h->la_cur, (size_t)L * R, nan);
+  plan.filled(h->la_pub, (size_t)L * R, nan);
+  const bool have_la_all = h->world > 1 || h->mode == 2;
+  if (have_la_all) plan.filled(h->la_all, (size_t)(h->mode ? 2 : 1) * N * R, nan, xs);
+  // [2][N] values by iteration parity, followed by [N] 64-bit words whose first is the rank's completion counter
+  // (exchange_mode 2), zero = nothing done
+  plan.add(h->val_all, (size_t)3 * N, xs, false, 0.0);
+  plan.filled(h->flags, (size_t)kMaxWorld, 0ull, xs);
+  plan.filled(h->applied, (size_t)L, 0u);
+  plan.filled(h->pp, (size_t)L * P, nan);
+  plan.filled(h->bar, 1, GridBarrier{0u, 0u});
+  plan.filled(h->sync_seq, 1, 0ull);
+  // trace: unrun slots look like a fresh BGPChain (AlgoBGP.jl:81-89); Eval slots are `undef` -> NaN
+  const size_t IL = (size_t)I * L;
+  plan.filled(h->t_value, IL, nan);
+  plan.filled(h->t_prob, IL, nan);
+  plan.filled(h->t_curr, IL, inf);
+  plan.filled(h->t_best, IL, inf);
+  plan.filled(h->t_params, IL * P, nan);
+  plan.filled(h->t_mom, IL * M, nan);
+  plan.filled(h->t_acc, IL, (uint8_t)0);
+  plan.filled(h->t_status, IL, 0);
+  plan.filled(h->t_exch, IL, 0);
+  plan.filled(h->t_bestid, IL, -1);
+  plan.filled(h->unit_ctr, 1, 0u);
+  plan.filled(h->partials, (size_t)L * h->max_seg * h->part_len, 0.0);
+  plan.filled(h->arrive, (size_t)L, 0u);
   if (h->N > 1) {
-    if (int rc = fill(h->sched_ij, (size_t)kPairChunk * h->n_s * 2, 0)) return rc;
-    if (int rc = fill(h->sched_off, (size_t)kPairChunk * (h->n_s + 1), 0)) return rc;
-    if (int rc = fill(h->sched_nlev, (size_t)kPairChunk, 0)) return rc;
+    plan.filled(h->sched_ij, (size_t)kPairChunk * h->n_s * 2, 0);
+    plan.filled(h->sched_off, (size_t)kPairChunk * (h->n_s + 1), 0);
+    plan.filled(h->sched_nlev, (size_t)kPairChunk, 0);
   }
-  if (int rc = fill(h->err, 1, 0)) return rc;
-  if (int rc = fill(h->counters, 4, 0ull)) return rc;
+  plan.filled(h->err, 1, 0);
+  plan.filled(h->counters, 4, 0ull);
+  const bool want_phase_ts = getenv("SMM_PHASE_TS") != nullptr;
+  if (want_phase_ts) {
+    size_t slots = (size_t)L * h->n_split;
+    if ((size_t)h->grid * 4 + L > slots) slots = (size_t)h->grid * 4 + L;
+    plan.filled(h->phase_ts, slots * 4, 0ull);
+  }
+
+  // ---- communicator and exchange arena (world > 1): cached per process ----
+  void *arena_base = nullptr;
+  Arena *arena = nullptr;
+  if (h->world > 1) {
+    if (int rc = rank_ctx_get(cfg->device, h->world, h->rank, cfg->nccl_id, &h->ctx)) return rc;
+    h->comm = h->ctx->comm;
+    if (fused_peers) {
+      const size_t need = plan.total[1];
+      bool busy;
+      {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        busy = h->ctx->arena_busy;
+        if (!busy) h->ctx->arena_busy = true;
+      }
+      if (!busy) {
+        h->uses_ctx_arena = true;
+        arena = &h->ctx->arena;
+        if (arena->bytes < need) {  // (re)made collectively: every rank sees the same sizes in the same order
+          arena_destroy(*arena, h->rank);
+          size_t min_cap = (size_t)4 << 20;  // holds 8192 chains of the MvNormal shapes; SMM_ARENA_MIN_BYTES: tests
+          if (const char *v = getenv("SMM_ARENA_MIN_BYTES")) min_cap = (size_t)atoll(v) > 4096 ? (size_t)atoll(v) : 4096;
+          const size_t cap = need * 2 > min_cap ? need * 2 : min_cap;
+          if (int rc = arena_create(*arena, h->comm, h->world, h->rank, cap, h->stream)) return rc;
+        }
+      } else {  // a second live fused handle in this process: its own mapping (slow path, seconds at 8 ranks)
+        arena = &h->own_arena;
+        if (int rc = arena_create(*arena, h->comm, h->world, h->rank, need, h->stream)) return rc;
+      }
+      arena_base = arena->base;
+    }
+  }
+  stamp("communicator + arena");
+
+  CUDA_TRY(cudaMallocAsync(&h->slab, plan.total[0], h->stream));
+  plan.assign(h->slab, arena_base);
+  {
+    // one upload: the problem definition sits at the head of the slab (pageable source: the call returns once the
+    // bytes are staged, so the vector may die right after it)
+    std::vector<char> stage(upload_end, 0);
+    for (const SlabPlan::Item &it : plan.items)
+      if (it.src) memcpy(stage.data() + it.off, it.src, it.bytes);
+    CUDA_TRY(cudaMemcpyAsync(h->slab, stage.data(), upload_end, cudaMemcpyHostToDevice, h->stream));
+  }
+  {
+    InitTable tab;
+    tab.n = 0;
+    auto seg = [&](void *p, size_t bytes, unsigned long long pat) {
+      tab.seg[tab.n++] = InitSeg{p, (unsigned long long)((bytes + 15) / 16), pat};
+    };
+    for (const SlabPlan::Item &it : plan.items)
+      if (it.fill) seg(*it.pp, it.bytes, it.pat);
+    seg(h->val_all.p, sizeof(double) * 2 * (size_t)N, fill_pattern(nan));
+    seg(h->val_all.p + 2 * (size_t)N, sizeof(double) * (size_t)N, 0ull);
+    if (tab.n > kMaxInitSegs) return fail(SMM_E_STATE, "init table overflow");
+    size_t words = 0;
+    for (int i = 0; i < tab.n; ++i) words += tab.seg[i].n16;
+    int blocks = (int)((words + 1023) / 1024);
+    blocks = blocks < 1 ? 1 : (blocks > 8 * prop.multiProcessorCount ? 8 * prop.multiProcessorCount : blocks);
+    init_kernel<<<blocks, 256, 0, h->stream>>>(tab);
+    CUDA_TRY(cudaGetLastError());
+    h->ctr.kernel_launches++;
+  }
+  stamp("slab + upload + init kernel");
 
   DevProblem &pb = h->pb;
   pb.P = P; pb.M = M; pb.S = cfg->n_sim; pb.obj = cfg->objective_id; pb.noseed = cfg->noseed;
@@ -546,7 +808,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   DevState &st = h->st;
   st.sigma = h->sigma.p; st.accept_rate = h->accept_rate.p; st.n_noex = h->n_noex.p; st.n_acc = h->n_acc.p;
   st.la_cur = h->la_cur.p; st.la_pub = h->la_pub.p;
-  st.la_all = (h->world > 1 || h->mode == 2) ? h->la_all.p : h->la_pub.p;
+  st.la_all = have_la_all ? h->la_all.p : h->la_pub.p;
   st.applied = h->applied.p;
   st.t_value = h->t_value.p; st.t_prob = h->t_prob.p; st.t_curr = h->t_curr.p; st.t_best = h->t_best.p;
   st.t_params = h->t_params.p; st.t_mom = h->t_mom.p; st.t_acc = h->t_acc.p; st.t_status = h->t_status.p;
@@ -564,66 +826,65 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     st.peer_la_all[0] = h->la_all.p;
     st.peer_val_all[0] = h->val_all.p;
   }
-  st.phase_ts = nullptr;
-  if (getenv("SMM_PHASE_TS")) {
-    size_t slots = (size_t)L * h->n_split;
-    if ((size_t)h->grid * 4 + L > slots) slots = (size_t)h->grid * 4 + L;
-    if (int rc = fill(h->phase_ts, slots * 4, 0ull)) return rc;
-    st.phase_ts = h->phase_ts.p;
-  }
-
-  stamp("kernel configuration");
-  if (h->world > 1) {
-    if (h->world > kMaxWorld) return fail(SMM_E_ARG, "world_size > 8");
-    ncclUniqueId id;
-    memcpy(&id, cfg->nccl_id, sizeof id);
-    NCCL_TRY(ncclCommInitRank(&h->comm, h->world, id, h->rank));
-    if (h->mode >= 1) {
-      // fused all-gather: map every peer's gather buffers (CUDA IPC); the handles travel over the communicator
-      struct Handles {
-        cudaIpcMemHandle_t la, val, flags;
-      } mine;
-      CUDA_TRY(cudaIpcGetMemHandle(&mine.la, h->la_all.p));
-      CUDA_TRY(cudaIpcGetMemHandle(&mine.val, h->val_all.p));
-      CUDA_TRY(cudaIpcGetMemHandle(&mine.flags, h->flags.p));
-      DevBuf<char> d_mine, d_all;
-      CUDA_TRY(d_mine.alloc(sizeof(Handles), true));
-      CUDA_TRY(d_all.alloc(sizeof(Handles) * h->world, true));
-      CUDA_TRY(cudaMemcpy(d_mine.p, &mine, sizeof mine, cudaMemcpyHostToDevice));
-      ncclResult_t nr = ncclAllGather(d_mine.p, d_all.p, sizeof(Handles), ncclChar, h->comm, h->stream);
-      std::vector<Handles> all(h->world);
-      cudaError_t ce = cudaStreamSynchronize(h->stream);
-      if (ce == cudaSuccess) ce = cudaMemcpy(all.data(), d_all.p, sizeof(Handles) * h->world, cudaMemcpyDeviceToHost);
-      d_mine.free();
-      d_all.free();
-      NCCL_TRY(nr);
-      CUDA_TRY(ce);
-      for (int r = 0; r < h->world; ++r) {
-        if (r == h->rank) {
-          st.peer_la_all[r] = h->la_all.p;
-          st.peer_val_all[r] = h->val_all.p;
-          st.peer_flags[r] = h->flags.p;
-          continue;
-        }
-        void *q = nullptr;
-        CUDA_TRY(cudaIpcOpenMemHandle(&q, all[r].la, cudaIpcMemLazyEnablePeerAccess));
-        h->peer_ptrs[3 * r] = q;
-        st.peer_la_all[r] = (double *)q;
-        CUDA_TRY(cudaIpcOpenMemHandle(&q, all[r].val, cudaIpcMemLazyEnablePeerAccess));
-        h->peer_ptrs[3 * r + 1] = q;
-        st.peer_val_all[r] = (double *)q;
-        CUDA_TRY(cudaIpcOpenMemHandle(&q, all[r].flags, cudaIpcMemLazyEnablePeerAccess));
-        h->peer_ptrs[3 * r + 2] = q;
-        st.peer_flags[r] = (unsigned long long *)q;
-      }
+  if (fused_peers) {
+    // the same plan on every rank: a peer's buffers sit at the same offsets of its arena
+    const size_t o_la = (char *)h->la_all.p - (char *)arena_base, o_val = (char *)h->val_all.p - (char *)arena_base,
+                 o_fl = (char *)h->flags.p - (char *)arena_base;
+    for (int r = 0; r < h->world; ++r) {
+      st.peer_la_all[r] = (double *)((char *)arena->peer[r] + o_la);
+      st.peer_val_all[r] = (double *)((char *)arena->peer[r] + o_val);
+      st.peer_flags[r] = (unsigned long long *)((char *)arena->peer[r] + o_fl);
     }
   }
-  stamp("communicator");
-  CUDA_TRY(cudaDeviceSynchronize());
-  stamp("device synchronize");
+  st.phase_ts = want_phase_ts ? h->phase_ts.p : nullptr;
+
+  if (h->N > 1 && I >= 2) {
+    // Pairs[2 .. ] and their level schedules are data independent: the first window is computed right here, behind the
+    // initialisation, instead of in front of the first iteration
+    const int w = I - 1 < kPairChunk ? I - 1 : kPairChunk;
+    launch_pairs(h->pb, h->st, 2, w, h->n_s, h->stream);
+    CUDA_TRY(cudaGetLastError());
+    h->ctr.kernel_launches++;
+    h->sched_iter0 = 2;
+    h->sched_n = w;
+  }
+  if (h->world > 1) {
+    // Cross-rank barrier on the device: a peer's first kernel must not store into this rank's arena before the
+    // initialisation above has run.  (The other direction needs nothing: a handle's last kernel ends only after every
+    // rank's last record has arrived, so nobody still writes into an arena whose handle was destroyed.)
+    NCCL_TRY(ncclAllReduce(h->ctx->d_token, h->ctx->d_token, 1, ncclFloat, ncclSum, h->comm, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  stamp("pairs + barrier");
   guard.ok = true;
   *out = h;
   return 0;
+}
+
+/* ends the process-wide caches (communicators, exchange arenas, streams); every handle must have been destroyed */
+void smm_shutdown(void) {
+  std::vector<RankCtx *> ctxs;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    ctxs.swap(g_rank_ctx);
+  }
+  for (RankCtx *c : ctxs) {
+    cudaSetDevice(c->device);
+    arena_destroy(c->arena, c->rank);
+    if (c->d_token) cudaFree(c->d_token);
+    if (c->comm) ncclCommDestroy(c->comm);
+    delete c;
+  }
+  for (int d = 0; d < 64; ++d) {
+    std::vector<StreamSet> v;
+    {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      v.swap(g_stream_cache[d]);
+    }
+    if (v.empty()) continue;
+    cudaSetDevice(d);
+    for (StreamSet &ss : v) stream_set_destroy(ss);
+  }
 }
 
 int smm_bgp_iteration(const smm_bgp *h) { return h ? h->iter : -1; }
@@ -740,9 +1001,7 @@ int finish_step(smm_bgp *h) {
   }
   h->ctr.iterations = h->iter;
   h->ctr.evaluations = (int64_t)h->iter * h->L;
-  int flags = 0;
-  CUDA_TRY(cudaMemcpy(&flags, h->st.err, sizeof flags, cudaMemcpyDeviceToHost));
-  return device_error_to_rc(flags);
+  return device_error_to_rc(*h->ss.h_err);  // copied behind the last kernel by the caller (page-locked word)
 }
 
 // D2H of trace rows [iter_lo, iter_hi] into `out`, whose row 0 is iteration `out_iter0`, on stream s
@@ -781,6 +1040,7 @@ int smm_bgp_step(smm_bgp *h, int32_t n_iters, float *elapsed_ms) {
   h->prof_kind.clear();
   if (int rc = enqueue_iterations(h, n_iters)) return rc;
   CUDA_TRY(cudaEventRecord(h->ev1, s));
+  CUDA_TRY(cudaMemcpyAsync(h->ss.h_err, h->st.err, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
   return finish_step(h);
@@ -795,7 +1055,6 @@ int smm_bgp_run(smm_bgp *h, int32_t n_iters, int32_t window, const smm_trace_vie
   CUDA_TRY(cudaSetDevice(h->device));
   if (window <= 0) window = kPairChunk;
   cudaStream_t s = h->stream;
-  if (!h->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventRecord(h->ev0, s));
   h->prof_kind.clear();
   const int first = h->iter + 1;
@@ -822,6 +1081,7 @@ int smm_bgp_run(smm_bgp *h, int32_t n_iters, int32_t window, const smm_trace_vie
     }
   }
   CUDA_TRY(cudaEventRecord(h->ev1, s));
+  CUDA_TRY(cudaMemcpyAsync(h->ss.h_err, h->st.err, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   if (host_out) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
   if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
@@ -991,13 +1251,15 @@ int smm_bgp_kernel_times(smm_bgp *h, double ms_sum[4], int64_t launches[4]) {
 }
 
 // ---- checkpoint ----------------------------------------------------------------------------------
-// layout: header {magic, P, M, L, R, iter} (6 x int64) | sigma[L] accept_rate[L] | n_noex[L] n_acc[L] (int32)
+// layout: header {magic, P, M, L, R, iter, N, world, rank, seed_algo, seed_sim} (11 x int64) | sigma[L] accept_rate[L] | n_noex[L] n_acc[L] (int32)
 //         | la_cur[L][R] | trace rows 1..iter of every column
 namespace {
 struct StateHeader {
   int64_t magic, P, M, L, R, iter;
+  int64_t N, world, rank;        // whose chains these are: a blob of another rank / ensemble / seed is rejected
+  uint64_t seed_algo, seed_sim;  // the streams the trace was drawn from
 };
-const int64_t kMagic = 0x534d4d4232303031ll;  // "SMMB2001"
+const int64_t kMagic = 0x534d4d4232303032ll;  // "SMMB2002"
 }  // namespace
 
 int64_t smm_bgp_state_bytes(const smm_bgp *h) {
@@ -1012,7 +1274,7 @@ int smm_bgp_export_state(smm_bgp *h, void *buf, int64_t nbytes) {
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   char *p = (char *)buf;
-  StateHeader hd{kMagic, h->P, h->M, h->L, h->R, h->iter};
+  StateHeader hd{kMagic, h->P, h->M, h->L, h->R, h->iter, h->N, h->world, h->rank, h->seed_algo, h->seed_sim};
   memcpy(p, &hd, sizeof hd);
   p += sizeof hd;
   const size_t L = h->L, n = (size_t)h->iter * L;
@@ -1049,6 +1311,10 @@ int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes) {
   p += sizeof hd;
   if (hd.magic != kMagic || hd.P != h->P || hd.M != h->M || hd.L != h->L || hd.R != h->R)
     return fail(SMM_E_STATE, "checkpoint does not match this handle's shape");
+  if (hd.N != h->N || hd.world != h->world || hd.rank != h->rank)
+    return fail(SMM_E_STATE, "checkpoint belongs to another rank or ensemble (n_chains / world_size / rank differ)");
+  if (hd.seed_algo != h->seed_algo || hd.seed_sim != h->seed_sim)
+    return fail(SMM_E_STATE, "checkpoint was drawn from other streams (seed_algo / seed_sim differ)");
   if (hd.iter < 0 || hd.iter > h->max_iter) return fail(SMM_E_STATE, "checkpoint has more iterations than max_iter");
   const size_t L = h->L, n = (size_t)hd.iter * L;
   const int64_t need = (int64_t)sizeof(StateHeader) + 8 * 2 * (int64_t)L + 4 * 2 * (int64_t)L + 8 * (int64_t)L * h->R +
@@ -1058,7 +1324,7 @@ int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes) {
   CUDA_TRY(cudaStreamSynchronize(h->stream));
 #define IN(dst, T, count)                                                                \
   do {                                                                                   \
-    CUDA_TRY(cudaMemcpy(dst, p, sizeof(T) * (count), cudaMemcpyHostToDevice));           \
+    CUDA_TRY(cudaMemcpyAsync(dst, p, sizeof(T) * (count), cudaMemcpyHostToDevice, h->stream)); \
     p += sizeof(T) * (count);                                                            \
   } while (0)
   IN(h->st.sigma, double, L);
@@ -1079,9 +1345,10 @@ int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes) {
 #undef IN
   // completion counter / applied marks of exchange_mode 2 refer to the run that is being replaced.  (With several ranks
   // every rank imports between the same two steps, and a step ends only when all ranks have finished it.)
-  CUDA_TRY(cudaMemset(h->val_all.p + 2 * (size_t)h->N, 0, sizeof(double) * h->N));
+  CUDA_TRY(cudaMemsetAsync(h->val_all.p + 2 * (size_t)h->N, 0, sizeof(double) * h->N, h->stream));
   h->done_base = 0;
-  CUDA_TRY(cudaMemset(h->applied.p, 0, sizeof(unsigned) * L));
+  CUDA_TRY(cudaMemsetAsync(h->applied.p, 0, sizeof(unsigned) * L, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->iter = (int)hd.iter;
   h->sched_iter0 = -1;
   h->sched_n = 0;
