@@ -597,20 +597,45 @@ def run(algo: MAlgoBGP):
     return algo
 
 
+def _rank_filename(filename: str, cfg: BGPConfig) -> str:
+    """One checkpoint file per rank: a rank's blob holds only the chains it owns, so with several ranks
+    the files are `<filename>.rank<r>of<world>`; with one rank the name is used as given (AlgoAbstract.jl:83)."""
+    return filename if cfg.world_size == 1 else f"{filename}.rank{cfg.rank}of{cfg.world_size}"
+
+
 def save(algo: MAlgoBGP, filename: str):
-    """save(algo, filename) (AlgoAbstract.jl:83-88): problem + opts + device state checkpoint."""
+    """save(algo, filename) (AlgoAbstract.jl:83-88): problem + opts + device state checkpoint.  With world_size > 1
+    every rank writes its own shard next to the others (`_rank_filename`); the blob itself records rank, world size,
+    chain count and seeds, and `smm_bgp_import_state` refuses a blob that belongs to another rank or ensemble."""
+    if algo.i > 0 and algo._h is None:
+        raise RuntimeError("save: this MAlgoBGP was closed after running -- its device state is gone (save before close())")
     blob = algo._handle().export_state() if algo.i > 0 else b""
-    with open(filename, "wb") as f:
-        pickle.dump({"m": algo.m, "opts": algo.opts, "i": algo.i, "state": blob}, f)
+    if algo.i > 0 and algo._handle().iteration != algo.i:
+        raise RuntimeError(f"save: the device is at iteration {algo._handle().iteration}, the algorithm object at {algo.i}")
+    opts = {k: v for k, v in algo.opts.items() if k != "nccl_id"}     # a communicator id does not survive the process
+    with open(_rank_filename(filename, algo._cfg), "wb") as f:
+        pickle.dump({"m": algo.m, "opts": opts, "i": algo.i, "state": blob, "rank": algo._cfg.rank,
+                     "world_size": algo._cfg.world_size}, f)
 
 
-def readMalgo(filename: str) -> MAlgoBGP:
-    """readMalgo(filename) (AlgoAbstract.jl:95-102)"""
-    with open(filename, "rb") as f:
+def readMalgo(filename: str, opts_override: Optional[dict] = None) -> MAlgoBGP:
+    """readMalgo(filename) (AlgoAbstract.jl:95-102).  With several ranks each rank reads its own shard; pass the
+    placement of the new job (`rank`, `world_size`, `device`, `nccl_id`) in `opts_override`."""
+    o = dict(opts_override or {})
+    probe = BGPConfig(lb=[0.0], ub=[1.0], init=[0.5], data_mom=[0.0], data_w=[1.0], n_chains=1, max_iter=1, sigma0=[1.0],
+                      acc_tuner=[1.0], min_improve=[0.0], world_size=int(o.get("world_size", 1)), rank=int(o.get("rank", 0)))
+    with open(_rank_filename(filename, probe), "rb") as f:
         d = pickle.load(f)
-    algo = MAlgoBGP(d["m"], d["opts"])
+    if d.get("world_size", 1) != probe.world_size or d.get("rank", 0) != probe.rank:
+        raise ValueError(f"{filename}: checkpoint of rank {d.get('rank')} of {d.get('world_size')}, "
+                         f"asked for rank {probe.rank} of {probe.world_size}")
+    opts = dict(d["opts"])
+    opts.update(o)
+    algo = MAlgoBGP(d["m"], opts)
     if d["i"] > 0:
         algo._handle().import_state(d["state"])
+        if algo._handle().iteration != d["i"]:
+            raise RuntimeError("readMalgo: the checkpoint's iteration count does not match its state blob")
         algo.i = d["i"]
     return algo
 

@@ -36,8 +36,8 @@ class Slice:
         xs = np.array(list(self.res[p].keys()), dtype=float)
         if m == "value":
             ys = np.array([v["value"] for v in self.res[p].values()], dtype=float)
-        else:
-            ys = np.array([v["moments"][m] for v in self.res[p].values()], dtype=float)
+        else:  # a failed evaluation is stored without moments (mprob.jl:183-186): NaN along the slice
+            ys = np.array([v["moments"].get(m, np.nan) for v in self.res[p].values()], dtype=float)
         ix = np.argsort(xs)
         return {"x": xs[ix], "y": ys[ix]}
 
@@ -69,7 +69,10 @@ def _evaluate(m, plist, noseed=False, rep0=0, evaluator: Optional[Evaluator] = N
 def doSlices(m: "api.MProb", npoints: int, parallel: bool = False, evaluator: Optional[Evaluator] = None) -> Slice:
     """doSlices(m, npoints, parallel) (slices.jl:242-281): for every sampled parameter, the objective along
     range(lb, ub, npoints) with the other parameters at their initial values.  All P x npoints evaluations travel in
-    one batch (`parallel` is accepted for signature compatibility: the batch is the parallelism)."""
+    one batch (`parallel` is accepted for signature compatibility: the batch is the parallelism).  A failing objective
+    does not stop the slice: as upstream, `evaluateObjective` turns the failure into an Eval with status -2, value -1.0
+    and no moments (mprob.jl:181-186), and that record is stored like any other (the `<: Exception` branch of
+    slices.jl:270 never fires, because the exception was already caught)."""
     res = Slice(m.initial_value, m.moments)
     plist, owner = [], []
     for pp, bb in m.params_to_sample.items():
@@ -79,8 +82,7 @@ def doSlices(m: "api.MProb", npoints: int, parallel: bool = False, evaluator: Op
             plist.append(p)
             owner.append(pp)
     for pp, ev in zip(owner, _evaluate(m, plist, evaluator=evaluator)):
-        if ev.status >= 0:  # "exception received. value not stored." (slices.jl:270-272)
-            res.add(pp, ev)
+        res.add(pp, ev)
     return res
 
 
@@ -89,7 +91,9 @@ def optSlices(m: "api.MProb", npoints: int, parallel: bool = False, tol: float =
     """optSlices (slices.jl:114-240): naive cyclic coordinate descent.  Within a cycle the parameters are searched one
     after the other on a grid of `npoints`, each starting from the best point found so far; the search ranges shrink
     around the best point by the factor `update` after every cycle; stop when the cycle moved the point by less than
-    `tol` (Euclidean norm).  One batched launch per (cycle, parameter).  Returns {"best": {"p", "value"},
+    `tol` (Euclidean norm).  One batched launch per (cycle, parameter).  Deliberate deviation: failed evaluations
+    (status < 0, value -1.0) are skipped when the best grid point is chosen -- upstream compares their -1.0 like any
+    value (slices.jl:188-200) and would walk towards the failures.  Returns {"best": {"p", "value"},
     "history": rows of {iter, param, val_idx, <params>, value}} (the reference also writes a JLD2 file)."""
     ranges = OrderedDict((k, dict(v)) for k, v in m.params_to_sample.items())
     bestp = OrderedDict(m.initial_value)

@@ -103,6 +103,33 @@ def test_save_read_restart(tmp_path, oracle):
     MB.close()
 
 
+def test_checkpoint_blob_is_bound_to_its_ensemble(tmp_path, smm):
+    """a state blob names the ensemble it belongs to (chains, world, rank, seeds): importing it anywhere else fails
+    instead of resuming the wrong chains; save() after close() raises instead of writing an empty trace"""
+    cfg = configs.mvnormal(16, 12, n_sim=300)
+    with smm.BGPHandle(cfg) as h:
+        h.step(6)
+        blob = h.export_state()
+    with smm.BGPHandle(configs.mvnormal(16, 12, n_sim=300, seed_algo=7)) as h2:
+        with pytest.raises(smm.SMMError, match="streams"):
+            h2.import_state(blob)
+    with smm.BGPHandle(configs.mvnormal(16, 12, n_sim=300, seed_sim=99)) as h2:
+        with pytest.raises(smm.SMMError, match="streams"):
+            h2.import_state(blob)
+    with smm.BGPHandle(configs.mvnormal(32, 12, n_sim=300)) as h2:
+        with pytest.raises(smm.SMMError):
+            h2.import_state(blob)
+    with smm.BGPHandle(configs.mvnormal(16, 40, n_sim=300)) as h2:     # a longer run of the same ensemble: fine
+        h2.import_state(blob)
+        assert h2.iteration == 6
+    m, opts = serial_normal_problem()
+    MA = api.MAlgoBGP(m, dict(opts, maxiter=5))
+    api.run(MA)
+    MA.close()
+    with pytest.raises(RuntimeError, match="closed"):
+        api.save(MA, os.path.join(tmp_path, "late.pkl"))
+
+
 @pytest.mark.parametrize("mode,window", [(0, 0), (1, 0), (1, 7), (1, 50), (0, 13)])
 def test_streaming_run_equals_step_and_read(smm, mode, window):
     """smm_bgp_run (windows computed while the previous window's rows travel to the host) = step + read_trace"""

@@ -80,12 +80,15 @@ def test_slices_read_and_write(oracle, tmp_path):
 
 
 def test_slices_survive_a_failing_objective(oracle):
-    """test_slices.jl:39-60: doSlices(mprob_fail, 30) with Testobj_fails completes; failed evaluations are not stored"""
+    """test_slices.jl:39-60: doSlices(mprob_fail, 30) with Testobj_fails completes; as upstream the failed evaluations are
+    stored as status -2 records: value -1.0, no moments (mprob.jl:181-186)"""
     from smm_jl_b200 import api
     m = _problem_2x2()
     m.objfunc = api.Testobj_fails
     sl = slices.doSlices(m, 30, evaluator=oracle_evaluator(oracle))
-    assert all(len(v) == 0 for v in sl.res.values())
+    assert all(len(v) == 30 for v in sl.res.values())
+    assert all(e["value"] == -1.0 and len(e["moments"]) == 0 for v in sl.res.values() for e in v.values())
+    assert np.isnan(sl.get("p1", "mu1")["y"]).all() and (sl.get("p1", "value")["y"] == -1.0).all()
 
 
 def test_naive_coordinate_descent_works(oracle):
