@@ -165,6 +165,16 @@ int smm_bgp_read_trace(smm_bgp *h, int32_t iter_lo, int32_t iter_hi, const smm_t
 int smm_bgp_read_chain_state(smm_bgp *h, double *sigma, double *accept_rate); /* [L] each */
 int smm_bgp_get_counters(smm_bgp *h, smm_counters *out);
 
+/* Accepted-only statistics of the parameter draws of every local chain over iterations [iter_lo, iter_hi], reduced on
+ * the device (mean(c), median(c), CI(c) of AlgoBGP.jl:174-188 without shipping the trace to the host): count[L] accepted
+ * iterations, mean[L][P], quantiles[L][P][n_probs] at the probabilities probs[n_probs] with the definition of Julia's
+ * `quantile` (type 7: linear interpolation around (n-1) p).  A chain without accepted iterations gives NaN.  Any output
+ * may be NULL.  smm_bgp_chain_summary: the columns of summary(c) (AlgoBGP.jl:197-206) that need the trace -- iterations
+ * with an exchange, the partner exchanged with most often (1-based id, smallest on ties, 0 = none), best_val. */
+int smm_bgp_accepted_stats(smm_bgp *h, int32_t iter_lo, int32_t iter_hi, const double *probs, int32_t n_probs,
+                           int64_t *count, double *mean, double *quantiles);
+int smm_bgp_chain_summary(smm_bgp *h, int64_t *n_exchanged, int32_t *exchanged_most_with, double *best_val);
+
 /* batched bare objective: value[B], moments[B][M], status[B] at params[B][P] (host pointers).
  * noseed != 0 draws fresh shocks indexed by (entry b, rep0 + b). */
 int smm_bgp_eval_batch(smm_bgp *h, const double *params, int32_t B, int32_t noseed, uint32_t rep0,

@@ -245,6 +245,38 @@ function history(algo::MAlgoBGPB200, chain::Int)
     return d
 end
 
+"""
+    accepted_stats(algo, probs) -> (count[L], mean[P, L], quantiles[length(probs), P, L])
+
+Accepted-only statistics of every local chain reduced on the device (`smm_bgp_accepted_stats`): what `mean(c)`,
+`median(c)`, `CI(c)` (AlgoBGP.jl:174-188) compute from `params(c)`, without reading the trace back.
+"""
+function accepted_stats(algo::MAlgoBGPB200, probs::Vector{Float64})
+    L = length(algo.chains); np = length(algo.m.params_to_sample); nq = length(probs)
+    cnt = zeros(Int64, L); mu = zeros(np, L); q = zeros(max(nq, 1), np, L)
+    smm_check(ccall((:smm_bgp_accepted_stats, LIBSMM_B200), Cint,
+                    (Ptr{Cvoid}, Int32, Int32, Ptr{Cdouble}, Int32, Ptr{Int64}, Ptr{Cdouble}, Ptr{Cdouble}),
+                    algo.handle, 1, algo.i, probs, nq, cnt, mu, q))
+    return cnt, mu, q[1:nq, :, :]
+end
+_named(algo::MAlgoBGPB200, v) = Dict(zip(collect(keys(algo.m.params_to_sample)), v))
+mean(algo::MAlgoBGPB200) = [_named(algo, accepted_stats(algo, Float64[])[2][:, c]) for c in 1:length(algo.chains)]
+median(algo::MAlgoBGPB200) = (q = accepted_stats(algo, [0.5])[3]; [_named(algo, q[1, :, c]) for c in 1:length(algo.chains)])
+function CI(algo::MAlgoBGPB200; level = 0.95)
+    q = accepted_stats(algo, [(1 - level) / 2, 1 - (1 - level) / 2])[3]
+    return [_named(algo, [q[:, k, c] for k in 1:size(q, 2)]) for c in 1:length(algo.chains)]
+end
+
+"summary(algo) (AlgoBGP.jl:541-550) from device-side reductions (`smm_bgp_chain_summary`): no trace read-back"
+function summary(algo::MAlgoBGPB200)
+    L = length(algo.chains)
+    nx = zeros(Int64, L); mw = zeros(Int32, L); bv = zeros(L); sig = zeros(L); ar = zeros(L)
+    smm_check(ccall((:smm_bgp_chain_summary, LIBSMM_B200), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}, Ptr{Cdouble}), algo.handle, nx, mw, bv))
+    smm_check(ccall((:smm_bgp_read_chain_state, LIBSMM_B200), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), algo.handle, sig, ar))
+    return DataFrame(id = [c.id for c in algo.chains], acc_rate = ar, perc_exchanged = 100 .* nx ./ algo["maxiter"],
+                     exchanged_most_with = Int.(mw), best_val = bv)
+end
+
 "computeNextIteration!(algo) (AlgoBGP.jl:589-640): the whole iteration -- proposals, objective, accept/reject, exchange -- on the device"
 function computeNextIteration!(algo::MAlgoBGPB200)
     smm_check(ccall((:smm_bgp_step, LIBSMM_B200), Cint, (Ptr{Cvoid}, Int32, Ptr{Cfloat}), algo.handle, 1, C_NULL))

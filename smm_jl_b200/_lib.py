@@ -22,7 +22,7 @@ EXPORTS = [
     "smm_bgp_state_bytes", "smm_bgp_export_state", "smm_bgp_import_state", "smm_debug_normals", "smm_debug_zig_normals",
     "smm_debug_pairs", "smm_debug_rng_throughput", "smm_stream_acc_uniforms", "smm_bgp_set_profiling",
     "smm_bgp_kernel_times", "smm_debug_phase_ts", "smm_debug_sim_throughput", "smm_debug_barrier_bench",
-    "smm_bgp_run", "smm_host_alloc", "smm_host_free", "smm_shutdown",
+    "smm_bgp_run", "smm_host_alloc", "smm_host_free", "smm_shutdown", "smm_bgp_accepted_stats", "smm_bgp_chain_summary",
 ]
 
 
@@ -60,6 +60,8 @@ def lib():
     L.smm_host_free.argtypes = [vp]
     L.smm_host_free.restype = None
     L.smm_shutdown.restype = None
+    L.smm_bgp_accepted_stats.argtypes = [vp, C.c_int32, C.c_int32, dp, C.c_int32, C.POINTER(C.c_int64), dp, dp]
+    L.smm_bgp_chain_summary.argtypes = [vp, C.POINTER(C.c_int64), ip, dp]
     L.smm_bgp_local_chains.argtypes = [vp]
     L.smm_bgp_stream.argtypes = [vp]
     L.smm_bgp_stream.restype = vp
@@ -233,6 +235,25 @@ class BGPHandle:
         check(lib().smm_bgp_eval_batch(self._h, params.ctypes.data_as(dp), B, noseed, rep0, value.ctypes.data_as(dp),
                                        mom.ctypes.data_as(dp), status.ctypes.data_as(C.POINTER(C.c_int32))))
         return value, mom, status
+
+    def accepted_stats(self, probs=(0.5,), iter_lo: int = 1, iter_hi: int | None = None):
+        """(count [L], mean [L][P], quantiles [L][P][len(probs)]) of the accepted parameter draws, reduced on the device"""
+        hi = self.iteration if iter_hi is None else iter_hi
+        P = self.cfg.n_params
+        pr = np.ascontiguousarray(np.asarray(probs, dtype=np.float64).reshape(-1))
+        cnt = np.zeros(self.L, dtype=np.int64)
+        mean, q = np.zeros((self.L, P)), np.zeros((self.L, P, max(pr.size, 1)))
+        dp = C.POINTER(C.c_double)
+        check(lib().smm_bgp_accepted_stats(self._h, iter_lo, hi, pr.ctypes.data_as(dp), pr.size,
+                                           cnt.ctypes.data_as(C.POINTER(C.c_int64)), mean.ctypes.data_as(dp), q.ctypes.data_as(dp)))
+        return cnt, mean, q[:, :, :pr.size]
+
+    def chain_summary(self):
+        """(iterations with an exchange [L], partner exchanged with most often [L] (1-based, 0 = none), best_val [L])"""
+        nx, mw, bv = np.zeros(self.L, dtype=np.int64), np.zeros(self.L, dtype=np.int32), np.zeros(self.L)
+        check(lib().smm_bgp_chain_summary(self._h, nx.ctypes.data_as(C.POINTER(C.c_int64)), mw.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          bv.ctypes.data_as(C.POINTER(C.c_double))))
+        return nx, mw, bv
 
     def set_profiling(self, on: bool):
         check(lib().smm_bgp_set_profiling(self._h, int(on)))

@@ -442,16 +442,40 @@ def best(c: BGPChain):
     return float(v[i]), i + 1
 
 
-def mean(c: BGPChain):
+def _device_stats(algo: "MAlgoBGP", probs):
+    """accepted-only mean / quantiles of every local chain, reduced on the device (smm_bgp_accepted_stats): the trace
+    stays in HBM -- a 1024-chain x 1000-iteration run would otherwise ship 240 MB to the host to print a summary"""
+    if algo.i == 0 or algo._h is None:
+        raise RuntimeError("no device trace: run the algorithm first (and before close())")
+    return algo._handle().accepted_stats(probs, 1, algo.i)
+
+
+def mean(c):
+    """mean(c::BGPChain) (AlgoBGP.jl:174-176) over the accepted draws; mean(algo): every local chain, on the device"""
+    if isinstance(c, MAlgoBGP):
+        names = list(c.m.params_to_sample.keys())
+        _, mu, _ = _device_stats(c, ())
+        return [dict(zip(names, map(float, row))) for row in mu]
     return {k: float(np.mean(v)) for k, v in params(c).items()}
 
 
-def median(c: BGPChain):
+def median(c):
+    """median(c::BGPChain) (AlgoBGP.jl:178-180); median(algo): every local chain, on the device"""
+    if isinstance(c, MAlgoBGP):
+        names = list(c.m.params_to_sample.keys())
+        _, _, q = _device_stats(c, (0.5,))
+        return [dict(zip(names, map(float, row[:, 0]))) for row in q]
     return {k: float(np.median(v)) for k, v in params(c).items()}
 
 
-def CI(c: BGPChain, level: float = 0.95):
+def CI(c, level: float = 0.95):
+    """CI(c::BGPChain; level) (AlgoBGP.jl:182-188): the (1-level)/2 and 1-(1-level)/2 quantiles of the accepted draws;
+    CI(algo): every local chain, on the device"""
     q = [(1 - level) / 2, 1 - (1 - level) / 2]
+    if isinstance(c, MAlgoBGP):
+        names = list(c.m.params_to_sample.keys())
+        _, _, qq = _device_stats(c, q)
+        return [{k: row[j].copy() for j, k in enumerate(names)} for row in qq]
     return {k: np.quantile(v, q) for k, v in params(c).items()}
 
 
@@ -463,7 +487,15 @@ def _mode(x):
 def summary(x):
     """summary(c::BGPChain) (AlgoBGP.jl:197-206) / summary(algo) (:541-550)"""
     if isinstance(x, MAlgoBGP):
-        rows = [summary(c) for c in x.chains]
+        if x.i > 0 and x._h is not None:     # reduced on the device: no trace read-back, no chain objects
+            h, cfg = x._handle(), x._cfg
+            nx, mw, bv = h.chain_summary()
+            _, acc = h.chain_state()
+            c0 = cfg.rank * h.L
+            rows = [OrderedDict(id=c0 + c + 1, acc_rate=float(acc[c]), perc_exchanged=100.0 * int(nx[c]) / cfg.max_iter,
+                                exchanged_most_with=int(mw[c]), best_val=float(bv[c])) for c in range(h.L)]
+        else:
+            rows = [summary(c) for c in x.chains]
         try:
             import pandas as pd
             return pd.DataFrame(rows)

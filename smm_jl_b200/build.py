@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 SO = os.path.join(HERE, "libsmm_b200.so")
-SOURCES = ["smm_kernels.cu", "smm_api.cu"]
+SOURCES = ["smm_kernels.cu", "smm_api.cu", "smm_stats.cu"]
 HEADERS = [os.path.join(CSRC, "smm_device.cuh"), os.path.join(CSRC, "smm_panel.cuh"), os.path.join(INCLUDE, "smm_b200.h"),
            os.path.join(INCLUDE, "smm_stream.h"), os.path.join(INCLUDE, "smm_stream_tables.h")]
 

@@ -47,6 +47,12 @@ void launch_rng_throughput(long long n_per_thread, int blocks, double *out, cuda
 cudaError_t launch_barrier_bench(const DevProblem &pb, const DevState &st, int variant, int n, int grid, cudaStream_t s);
 void launch_sim_throughput(const DevProblem &pb, int n_per_thread, int blocks, int threads, int dyn, double *out,
                            cudaStream_t s);
+// smm_stats.cu
+int stats_smem_cap();
+cudaError_t launch_accepted_stats(const DevState &st, int L, int P, int it_lo, int it_hi, const double *probs, int n_probs,
+                                  long long *count, double *mean, double *quant, double *scratch, int cap2, cudaStream_t s);
+cudaError_t launch_chain_summary(const DevState &st, int L, int N, int iter, long long *n_exchanged, int *most_with,
+                                 double *best_val, cudaStream_t s);
 }  // namespace smm
 
 using namespace smm;
@@ -1221,6 +1227,61 @@ int smm_bgp_eval_batch(smm_bgp *h, const double *params, int32_t B, int32_t nose
   if (moments) CUDA_TRY(cudaMemcpyAsync(moments, d_mom.p, sizeof(double) * B * M, cudaMemcpyDeviceToHost, s));
   if (status) CUDA_TRY(cudaMemcpyAsync(status, d_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ---- accepted-only statistics and summary(c), reduced on the device (AlgoBGP.jl:174-206) -----------------------------
+int smm_bgp_accepted_stats(smm_bgp *h, int32_t iter_lo, int32_t iter_hi, const double *probs, int32_t n_probs,
+                           int64_t *count, double *mean, double *quantiles) {
+  if (!h) return fail(SMM_E_ARG, "null handle");
+  if (iter_lo < 1 || iter_hi < iter_lo || iter_hi > h->iter) return fail(SMM_E_ARG, "bad iteration range (1 <= lo <= hi <= iterations run)");
+  if (n_probs < 0 || (n_probs > 0 && (!probs || !quantiles))) return fail(SMM_E_ARG, "bad quantile arguments");
+  for (int q = 0; q < n_probs; ++q)
+    if (!(probs[q] >= 0.0 && probs[q] <= 1.0)) return fail(SMM_E_ARG, "quantile probabilities must lie in [0, 1]");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int L = h->L, P = h->P, n = iter_hi - iter_lo + 1;
+  int cap2 = 1;
+  while (cap2 < n) cap2 <<= 1;
+  const bool need_scratch = cap2 > stats_smem_cap();  // more accepted values than the shared-memory sort holds
+  const size_t nq = (size_t)L * P * (n_probs > 0 ? n_probs : 1);
+  cudaStream_t s = h->stream;
+  char *d = nullptr;
+  const size_t o_cnt = 0, o_mean = o_cnt + 8 * (size_t)L, o_q = o_mean + 8 * (size_t)L * P, o_p = o_q + 8 * nq,
+               o_scr = o_p + 8 * (size_t)(n_probs > 0 ? n_probs : 1),
+               total = o_scr + (need_scratch ? 8 * (size_t)L * P * cap2 : 8);
+  CUDA_TRY(cudaMallocAsync((void **)&d, total, s));
+  cudaError_t e = cudaSuccess;
+  if (n_probs > 0) e = cudaMemcpyAsync(d + o_p, probs, 8 * (size_t)n_probs, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess)
+    e = launch_accepted_stats(h->st, L, P, iter_lo, iter_hi, (const double *)(d + o_p), n_probs, (long long *)(d + o_cnt),
+                              (double *)(d + o_mean), (double *)(d + o_q), (double *)(d + o_scr), cap2, s);
+  h->ctr.kernel_launches++;
+  if (e == cudaSuccess && count) e = cudaMemcpyAsync(count, d + o_cnt, 8 * (size_t)L, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && mean) e = cudaMemcpyAsync(mean, d + o_mean, 8 * (size_t)L * P, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && n_probs > 0) e = cudaMemcpyAsync(quantiles, d + o_q, 8 * nq, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFreeAsync(d, s);
+  CUDA_TRY(e);
+  return 0;
+}
+
+int smm_bgp_chain_summary(smm_bgp *h, int64_t *n_exchanged, int32_t *exchanged_most_with, double *best_val) {
+  if (!h) return fail(SMM_E_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int L = h->L;
+  cudaStream_t s = h->stream;
+  char *d = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&d, 24 * (size_t)L, s));
+  cudaError_t e = launch_chain_summary(h->st, L, h->N, h->iter, (long long *)d, (int *)(d + 16 * (size_t)L),
+                                       (double *)(d + 8 * (size_t)L), s);
+  h->ctr.kernel_launches++;
+  if (e == cudaSuccess && n_exchanged) e = cudaMemcpyAsync(n_exchanged, d, 8 * (size_t)L, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && best_val) e = cudaMemcpyAsync(best_val, d + 8 * (size_t)L, 8 * (size_t)L, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && exchanged_most_with)
+    e = cudaMemcpyAsync(exchanged_most_with, d + 16 * (size_t)L, 4 * (size_t)L, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFreeAsync(d, s);
+  CUDA_TRY(e);
   return 0;
 }
 

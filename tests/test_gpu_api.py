@@ -180,3 +180,35 @@ def test_run_serves_chains_from_the_streamed_trace(smm, oracle):
         np.testing.assert_allclose(ch.curr_val, ref.trace.curr_val[:, c], rtol=1e-9)
     algo.close()
     assert algo._streamed is None
+
+
+@pytest.mark.parametrize("n_iter", [60, 9000])
+def test_device_side_statistics_equal_the_host_ones(n_iter, smm):
+    """mean / median / CI / summary of an algorithm are reduced on the device (smm_bgp_accepted_stats,
+    smm_bgp_chain_summary; AlgoBGP.jl:174-206) and equal what the host computes from the full trace -- with a trace
+    short enough for the shared-memory sort and one that needs the global scratch (> 8192 accepted draws possible)"""
+    cfg = configs.mvnormal(12, n_iter, 4, n_sim=30, exchange_mode=2 if n_iter < 100 else 0)
+    m = api.MProb()
+    for k in range(4):
+        api.addSampledParam(m, f"p{k + 1}", cfg.init[k], cfg.lb[k], cfg.ub[k])
+    for k in range(8):
+        api.addMoment(m, f"m{k + 1}", cfg.data_mom[k], cfg.data_w[k])
+    api.addEvalFunc(m, api.objfunc_norm_mv)
+    api.addEvalFuncOpts(m, {"n_sim": 30})
+    MA = api.MAlgoBGP(m, {"N": 12, "maxiter": n_iter, "maxtemp": 5.0, "acc_tuners": list(np.asarray(cfg.acc_tuner)),
+                          "min_improve": [0.0] * 12, "smpl_iters": 100000, "exchange_mode": cfg.exchange_mode})
+    api.computeNextIteration(MA, n_iter)
+    dev_mean, dev_med, dev_ci, dev_sum = api.mean(MA), api.median(MA), api.CI(MA, 0.9), api.summary(MA)
+    cnt, _, _ = MA._handle().accepted_stats(())
+    for ic, c in enumerate(MA.chains):
+        assert cnt[ic] == int(c.accepted.sum())
+        hm, hmed, hci, hs = api.mean(c), api.median(c), api.CI(c, 0.9), api.summary(c)
+        for k in hm:
+            np.testing.assert_allclose(dev_mean[ic][k], hm[k], rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(dev_med[ic][k], hmed[k], rtol=1e-13, atol=0)
+            np.testing.assert_allclose(dev_ci[ic][k], hci[k], rtol=1e-13, atol=0)
+        row = dev_sum.iloc[ic] if hasattr(dev_sum, "iloc") else dev_sum[ic]
+        assert int(row["id"]) == hs["id"] and int(row["exchanged_most_with"]) == hs["exchanged_most_with"]
+        assert float(row["best_val"]) == hs["best_val"] and float(row["acc_rate"]) == hs["acc_rate"]
+        np.testing.assert_allclose(float(row["perc_exchanged"]), hs["perc_exchanged"], rtol=1e-15)
+    MA.close()
