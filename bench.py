@@ -8,7 +8,8 @@
 
 A "step" is one BGP iteration over every chain: proposal -> simulate -> moments -> distance ->
 accept/reject -> exchange.  N = 1 runs BASELINE config C2 (256 chains, 8 params, 16 moments, 10 000
-draws per evaluation); N > 1 keeps 256 chains per GPU (weak scaling) with one all-gather per iteration.
+draws per evaluation); N > 1 keeps 256 chains per GPU (weak scaling, chains dealt round robin) with one all-gather
+per iteration.
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
@@ -214,7 +215,7 @@ def parity_leg(args, world, rank, local_rank, fresh_id, dist):
         tr = sd.gather_trace(tr, device="cuda")
         sig = [torch.empty(len(sigma), dtype=torch.float64, device="cuda") for _ in range(world)]
         dist.all_gather(sig, torch.from_numpy(sigma).cuda())
-        sigma = np.concatenate([t.cpu().numpy() for t in sig])
+        sigma = sd.interleave([t.cpu().numpy() for t in sig])
     if rank != 0:
         return None
     from oracle import oracle_lib                     # checker only

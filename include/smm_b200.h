@@ -94,7 +94,9 @@ typedef struct smm_bgp_config {
   /* placement */
   int32_t device;      /* CUDA device ordinal of this process                                        */
   int32_t world_size;  /* number of processes/GPUs sharing the chains (1, 2, 4, 8)                   */
-  int32_t rank;        /* this process: owns chains [rank*N/world, (rank+1)*N/world)                  */
+  int32_t rank;        /* this process owns the chains rank, rank + world, rank + 2 world, ... (0-based global
+                          ids, dealt round robin so that every rank holds the same mix of temperatures); its local
+                          chain c -- column c of every trace view -- is global chain c * world_size + rank      */
   uint8_t nccl_id[SMM_NCCL_ID_BYTES]; /* from smm_nccl_unique_id on rank 0 (ignored if world == 1)   */
   int32_t exchange_mode; /* 0 = one launch per iteration (+ ncclAllGather + exchange kernel when world > 1);
                             1 = persistent cooperative kernel; with world > 1 the all-gather is fused into it

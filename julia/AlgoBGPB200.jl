@@ -106,13 +106,13 @@ mutable struct MAlgoBGPB200 <: MAlgo
     m::MProb
     opts::Dict
     i::Int
-    chains::Array{BGPChain}      # this rank's chains (all of them when world_size == 1)
+    chains::Array{BGPChain}      # this rank's chains: ids rank + 1, rank + 1 + world, ... (round robin; all of them when world_size == 1)
     anim::Plots.Animation
     dist_fun::Function
     handle::Ptr{Cvoid}
     synced::Int                  # iterations already copied into `chains`
     exchange_mode::Int
-    chain0::Int                  # global id - 1 of chains[1]
+    world::Int                   # local chain i (1-based) is global chain (i - 1) * world + rank + 1
 
     function MAlgoBGPB200(m::MProb, opts::Dict)
         haskey(opts, "dist_fun") && opts["dist_fun"] !== (-) && error("dist_fun: only the default `-` runs on the device")
@@ -123,7 +123,8 @@ mutable struct MAlgoBGPB200 <: MAlgo
         np = length(m.params_to_sample)
         world = get(opts, "world_size", 1); rank = get(opts, "rank", 0)
         N % world == 0 || error("N must be a multiple of world_size")
-        L = N ÷ world; chain0 = rank * L
+        L = N ÷ world
+        gid = [(i - 1) * world + rank + 1 for i in 1:L]          # global ids of this rank's chains
         temps = N > 1 ? collect(range(1.0, stop = Float64(get(opts, "maxtemp", 1.0)), length = N)) : [1.0]   # AlgoBGP.jl:508
         sigma0 = get(opts, "sigma", 0.05) .* temps
         tuners = Float64.(get(opts, "acc_tuners", [2.0 for j in 1:N]))
@@ -159,15 +160,15 @@ mutable struct MAlgoBGPB200 <: MAlgo
             smm_check(rc)
         end
         # the chain objects the rest of the package (summary, history, plotting) reads; probs_acc is the Uacc stream
-        chains = BGPChain[BGPChain(chain0 + i, n, m = m, sig = sigma0[chain0 + i], upd = get(opts, "sigma_update_steps", 10),
+        chains = BGPChain[BGPChain(gid[i], n, m = m, sig = sigma0[gid[i]], upd = get(opts, "sigma_update_steps", 10),
                                    upd_by = get(opts, "sigma_adjust_by", 0.01), smpl_iters = get(opts, "smpl_iters", 1000),
-                                   min_improve = minimp[chain0 + i], acc_tuner = tuners[chain0 + i],
+                                   min_improve = minimp[gid[i]], acc_tuner = tuners[gid[i]],
                                    batch_size = get(opts, "batch_size", np)) for i in 1:L]
         for c in chains
             smm_check(ccall((:smm_stream_acc_uniforms, LIBSMM_B200), Cint, (UInt64, UInt32, Int32, Int32, Ptr{Cdouble}),
                             UInt64(get(opts, "seed", 20261017)), c.id - 1, 1, n, c.probs_acc))
         end
-        this = new(m, opts, 0, chains, Animation(), -, h[], 0, mode, chain0)
+        this = new(m, opts, 0, chains, Animation(), -, h[], 0, mode, world)
         finalizer(a -> (a.handle == C_NULL || ccall((:smm_bgp_destroy, LIBSMM_B200), Cvoid, (Ptr{Cvoid},), a.handle); a.handle = C_NULL), this)
         return this
     end

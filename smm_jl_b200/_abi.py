@@ -225,10 +225,12 @@ class Trace:
         return v
 
     @staticmethod
-    def concat_chains(parts: "list[Trace]") -> "Trace":
-        """Join per-rank traces (each [n][L_r]) along the chain axis, rank order = chain order."""
-        n, P, M = parts[0].n, parts[0].P, parts[0].M
+    def interleave_ranks(parts: "list[Trace]") -> "Trace":
+        """Join per-rank traces (each [n][L]) into the full [n][N] trace: rank r's column c is global chain
+        c * world + r (chains are dealt to the ranks round robin)."""
+        n, P, M, W = parts[0].n, parts[0].P, parts[0].M, len(parts)
         out = Trace(n, sum(p.L for p in parts), P, M)
         for f in Trace.FLOAT_FIELDS + Trace.INT_FIELDS:
-            setattr(out, f, np.concatenate([getattr(p, f) for p in parts], axis=1))
+            a = np.stack([getattr(p, f) for p in parts], axis=2)           # [n][L][W](...)
+            setattr(out, f, np.ascontiguousarray(a.reshape((n, parts[0].L * W) + a.shape[3:])))
         return out

@@ -491,8 +491,7 @@ def summary(x):
             h, cfg = x._handle(), x._cfg
             nx, mw, bv = h.chain_summary()
             _, acc = h.chain_state()
-            c0 = cfg.rank * h.L
-            rows = [OrderedDict(id=c0 + c + 1, acc_rate=float(acc[c]), perc_exchanged=100.0 * int(nx[c]) / cfg.max_iter,
+            rows = [OrderedDict(id=c * cfg.world_size + cfg.rank + 1, acc_rate=float(acc[c]), perc_exchanged=100.0 * int(nx[c]) / cfg.max_iter,
                                 exchanged_most_with=int(mw[c]), best_val=float(bv[c])) for c in range(h.L)]
         else:
             rows = [summary(c) for c in x.chains]
@@ -563,7 +562,8 @@ class MAlgoBGP:
 
     @property
     def chains(self) -> "list[BGPChain]":
-        """`algo.chains` -- this process's chains (all of them when world_size == 1)."""
+        """`algo.chains` -- this process's chains (all of them when world_size == 1; with several ranks the chains
+        with ids rank + 1, rank + 1 + world, ...)."""
         if self._chains is None:
             self._materialise()
         return self._chains
@@ -571,10 +571,10 @@ class MAlgoBGP:
     def _materialise(self):
         cfg, n = self._cfg, self._cfg.max_iter
         L = cfg.n_chains // cfg.world_size
-        c0 = cfg.rank * L
+        gid = np.arange(L) * cfg.world_size + cfg.rank      # local chain c is global chain c * world + rank
         if self.i == 0:
             tr = Trace(0, L, cfg.n_params, cfg.n_moments)
-            sigma = np.asarray(cfg.sigma0, float)[c0:c0 + L]
+            sigma = np.asarray(cfg.sigma0, float)[gid]
             acc = np.zeros(L)
         else:
             if self._h is None:
@@ -586,8 +586,8 @@ class MAlgoBGP:
         self._trace = tr
         self._chains = []
         for c in range(L):
-            pa = _lib.acc_uniforms(cfg.seed_algo, c0 + c, 1, n)
-            self._chains.append(BGPChain(c0 + c + 1, self.m, n, tr, c, self.i, sigma[c], acc[c], pa, cfg))
+            pa = _lib.acc_uniforms(cfg.seed_algo, int(gid[c]), 1, n)
+            self._chains.append(BGPChain(int(gid[c]) + 1, self.m, n, tr, c, self.i, sigma[c], acc[c], pa, cfg))
 
     def __repr__(self):
         return (f"\nBGP Algorithm with {self.opts['N']} BGPChains\n============================\n\nAlgorithm\n---------\n"

@@ -197,18 +197,50 @@ struct StreamSet {
   int *h_err = nullptr;  // page-locked word the sticky device error flag is copied into
 };
 
+constexpr size_t kArenaHead = 256;  // bytes at the head of an arena that no handle re-initialises: the barrier slots
 struct Arena {  // cudaMalloc'ed memory of this rank that every peer has mapped (and vice versa)
   void *base = nullptr;
   size_t bytes = 0;
   void *peer[kMaxWorld] = {nullptr};  // [rank] = base
+  unsigned long long epoch = 0;       // barriers done on this arena (the same number on every rank)
 };
+
+// Cross-rank barrier on the device, over the mapped arenas: thread r stores this barrier's epoch into slot [rank] of
+// rank r's arena head and waits until rank r's epoch has arrived in slot [r] of our own.  Stream ordered: everything
+// enqueued before it on this rank (the handle's initialisation) has completed before any peer passes the barrier.
+struct PeerBarrierArgs {
+  unsigned long long *slots[kMaxWorld];  // every rank's arena head
+  int world, rank;
+  unsigned long long epoch;
+  int *err;
+};
+__global__ void peer_barrier_kernel(PeerBarrierArgs a) {
+  const int r = threadIdx.x;
+  if (r >= a.world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.slots[r] + a.rank), "l"(a.epoch) : "memory");
+  const unsigned long long *mine = a.slots[a.rank] + r;
+  unsigned long long t0 = 0, v = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v >= a.epoch) break;
+    if ((spins & 1023u) == 1023u) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) {  // 20 s: a rank that never created its handle becomes an error, not a hang
+        atomicOr(a.err, kErrTimeout);
+        break;
+      }
+    }
+  }
+}
 
 struct RankCtx {
   int device = 0, world = 1, rank = 0;
   ncclComm_t comm = nullptr;
   Arena arena;
   bool arena_busy = false;  // one live handle at a time uses the cached arena; a second one maps its own
-  float *d_token = nullptr;  // operand of the cross-rank barrier (a one-element all-reduce)
 };
 
 std::mutex g_cache_mu;
@@ -266,7 +298,10 @@ void arena_destroy(Arena &a, int rank) {
 // collective over the communicator: allocate `bytes` on every rank and map everybody's allocation everywhere
 int arena_create(Arena &a, ncclComm_t comm, int world, int rank, size_t bytes, cudaStream_t s) {
   CUDA_TRY(cudaMalloc(&a.base, bytes));
+  CUDA_TRY(cudaMemset(a.base, 0, kArenaHead));  // barrier slots: zero before any peer can reach them
+  CUDA_TRY(cudaDeviceSynchronize());
   a.bytes = bytes;
+  a.epoch = 0;
   a.peer[rank] = a.base;
   cudaIpcMemHandle_t mine;
   CUDA_TRY(cudaIpcGetMemHandle(&mine, a.base));
@@ -309,11 +344,6 @@ int rank_ctx_get(int device, int world, int rank, const uint8_t *id_bytes, RankC
   c->world = world;
   c->rank = rank;
   c->comm = comm;
-  if (cudaMalloc((void **)&c->d_token, sizeof(float)) != cudaSuccess || cudaMemset(c->d_token, 0, sizeof(float)) != cudaSuccess) {
-    ncclCommDestroy(comm);
-    delete c;
-    return fail(SMM_E_CUDA, "cudaMalloc of the barrier token failed");
-  }
   std::lock_guard<std::mutex> lk(g_cache_mu);
   g_rank_ctx.push_back(c);
   *out = c;
@@ -324,7 +354,7 @@ int rank_ctx_get(int device, int world, int rank, const uint8_t *id_bytes, RankC
 
 struct smm_bgp {
   int device = 0;
-  int P = 0, M = 0, N = 0, L = 0, chain0 = 0, R = 0, max_iter = 0, world = 1, rank = 0;
+  int P = 0, M = 0, N = 0, L = 0, R = 0, max_iter = 0, world = 1, rank = 0;
   int n_s = 0;       // pairs per iteration
   int n_split = 1, part_len = 0;
   double eval_param_limit = 0.0;  // |param| bound for which the fixed-point accumulators are sized
@@ -555,7 +585,6 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   h->world = cfg->world_size;
   h->rank = cfg->rank;
   h->L = h->N / h->world;
-  h->chain0 = h->rank * h->L;
   h->R = rec_len(h->P, h->M);
   h->max_iter = cfg->max_iter;
   h->n_s = h->N < 3 ? h->N - 1 : h->N;
@@ -626,6 +655,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   const bool fused_peers = h->world > 1 && h->mode >= 1;  // the peers store into la_all / val_all / flags
   const int xs = fused_peers ? 1 : 0;                     // ... which then live in the exchange arena
   SlabPlan plan;
+  if (fused_peers) plan.total[1] = kArenaHead;  // the arena's head holds the barrier slots
   plan.upload(h->lb, cfg->lb, P);
   plan.upload(h->ub, cfg->ub, P);
   plan.upload(h->init, cfg->init, P);
@@ -633,7 +663,9 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   plan.upload(h->w, cfg->data_w, M);
   plan.upload(h->acc_tuner, cfg->acc_tuner, N);
   plan.upload(h->min_improve, cfg->min_improve, N);
-  plan.upload(h->sigma, cfg->sigma0 + h->chain0, L);
+  std::vector<double> sigma_local(L);  // local chain c is global chain c * world + rank (round robin, smm_device.cuh)
+  for (int c = 0; c < L; ++c) sigma_local[c] = cfg->sigma0[(size_t)c * h->world + h->rank];
+  plan.upload(h->sigma, sigma_local.data(), L);
   const size_t upload_end = plan.total[0];
   plan.filled(h->accept_rate, (size_t)L, 0.0);
   plan.filled(h->n_noex, (size_t)L, 0);
@@ -745,7 +777,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
 
   DevProblem &pb = h->pb;
   pb.P = P; pb.M = M; pb.S = cfg->n_sim; pb.obj = cfg->objective_id; pb.noseed = cfg->noseed;
-  pb.N = N; pb.L = L; pb.chain0 = h->chain0; pb.max_iter = I; pb.world = h->world; pb.rank = h->rank;
+  pb.N = N; pb.L = L; pb.max_iter = I; pb.world = h->world; pb.rank = h->rank;
   {
     uint32_t k0 = (uint32_t)cfg->seed_sim, k1 = (uint32_t)(cfg->seed_sim >> 32);
     for (int r = 0; r < 10; ++r) {
@@ -854,12 +886,20 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     h->sched_iter0 = 2;
     h->sched_n = w;
   }
-  if (h->world > 1) {
+  if (fused_peers) {
     // Cross-rank barrier on the device: a peer's first kernel must not store into this rank's arena before the
     // initialisation above has run.  (The other direction needs nothing: a handle's last kernel ends only after every
-    // rank's last record has arrived, so nobody still writes into an arena whose handle was destroyed.)
-    NCCL_TRY(ncclAllReduce(h->ctx->d_token, h->ctx->d_token, 1, ncclFloat, ncclSum, h->comm, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    // rank's last record has arrived, so nobody still writes into an arena whose handle was destroyed.)  Stream
+    // ordered, no host synchronisation: the first iteration simply starts behind it.
+    PeerBarrierArgs ba{};
+    for (int r = 0; r < h->world; ++r) ba.slots[r] = (unsigned long long *)arena->peer[r];
+    ba.world = h->world;
+    ba.rank = h->rank;
+    ba.epoch = ++arena->epoch;
+    ba.err = h->err.p;
+    peer_barrier_kernel<<<1, 32, 0, h->stream>>>(ba);
+    CUDA_TRY(cudaGetLastError());
+    h->ctr.kernel_launches++;
   }
   stamp("pairs + barrier");
   guard.ok = true;
@@ -877,7 +917,6 @@ void smm_shutdown(void) {
   for (RankCtx *c : ctxs) {
     cudaSetDevice(c->device);
     arena_destroy(c->arena, c->rank);
-    if (c->d_token) cudaFree(c->d_token);
     if (c->comm) ncclCommDestroy(c->comm);
     delete c;
   }

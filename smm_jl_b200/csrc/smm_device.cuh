@@ -28,6 +28,11 @@ __host__ __device__ inline int zig_blocks(int S) { return (S + SMM_ZIG_PER_BLOCK
 //   [0] value  [1] prob  [2] status (as double)  [3..3+P) params  [3+P..3+P+M) simMoments
 __host__ __device__ inline int rec_len(int P, int M) { return 3 + P + M; }
 
+// Chains are dealt to the ranks round robin: local chain c of rank r is global chain c * world + r (0-based).  The
+// temperature ladder runs along the global id (AlgoBGP.jl:508), and a hot chain's truncated proposal needs more
+// rejection attempts than a cold one's, so contiguous blocks would make the last rank the straggler of every iteration.
+// (global_chain / gather_slot below.)
+
 // device error flags (sticky, OR-ed into DevState::err)
 constexpr int kErrNegative = 1;
 constexpr int kErrExhausted = 2;
@@ -35,7 +40,7 @@ constexpr int kErrTimeout = 4;
 
 struct DevProblem {
   int P, M, S, obj, noseed;
-  int N, L, chain0, max_iter, world, rank;
+  int N, L, max_iter, world, rank;
   int sigma_update_steps, smpl_iters, batch_size;
   int panel_T, panel_N, panel_K;
   double sigma_adjust_by, slow_seconds;
@@ -48,6 +53,10 @@ struct DevProblem {
   const double *lb, *ub, *init, *data, *w;  // [P] x3, [M] x2
   const double *acc_tuner, *min_improve;    // [N]
 };
+
+__host__ __device__ inline int global_chain(const DevProblem &pb, int c) { return c * pb.world + pb.rank; }
+// slot of global chain g in a rank-major gather buffer (ncclAllGather of the ranks' [L] records, exchange_mode 0)
+__host__ __device__ inline int gather_slot(const DevProblem &pb, int g) { return (g % pb.world) * pb.L + g / pb.world; }
 
 struct GridBarrier {
   unsigned arrive;

@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_eval_kernel(DevProblem pb, D
   __shared__ EvalSmem sm;
   __shared__ unsigned long long s_zigtab[kZigBufEntries];  // 16 KB: the 8 KB-aligned half holds the table (see load_zigtab)
   const int c = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
-  const int gc = pb.chain0 + c;
+  const int gc = global_chain(pb, c);
   const Grp g{tid, (int)blockDim.x, 0};
   const size_t stamp = (size_t)c * n_split + split;
   PHASE_STAMP(stamp, 0);
@@ -1005,18 +1005,18 @@ __global__ void __launch_bounds__(kExchThreads) bgp_exchange_kernel(DevProblem p
   double *val = smem_d;
   unsigned short *own = (unsigned short *)(val + N), *exch = own + N;
   for (int i = tid; i < N; i += nthr) {
-    val[i] = st.la_all[(size_t)i * R];
+    val[i] = st.la_all[(size_t)gather_slot(pb, i) * R];  // (with one rank la_all is la_pub and the slot is i)
     own[i] = (unsigned short)i;
     exch[i] = 0;
   }
   __syncthreads();
   const unsigned n_swaps = exchange_levels(pb, st, g, sched_idx, n_s, val, own, exch);
-  if (pb.chain0 == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
+  if (pb.rank == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
   for (int c = tid / 32; c < L; c += nthr / 32) {  // one warp per chain
-    const int gc = pb.chain0 + c;
+    const int gc = global_chain(pb, c);
     const int partner = exch[gc];
     if (partner == 0) continue;
-    exchange_apply_chain(pb, st, iter, c, partner, st.la_all + (size_t)own[gc] * R, tid & 31);
+    exchange_apply_chain(pb, st, iter, c, partner, st.la_all + (size_t)gather_slot(pb, own[gc]) * R, tid & 31);
   }
 }
 
@@ -1148,7 +1148,7 @@ __device__ void persistent_exchange_apply(const DevProblem &pb, const DevState &
   const double *la_all = st.la_all + (size_t)(fused ? (pit & 1) : 0) * N * R;
   const int warp = tid >> 5, nwarps = blockDim.x >> 5;
   for (int c = b + warp * G; c < L; c += nwarps * G) {  // one warp per owned chain
-    const int gc = pb.chain0 + c;
+    const int gc = global_chain(pb, c);
     const int partner = exch[gc];
     if (partner != 0) {
       exchange_apply_chain(pb, st, pit, c, partner, la_all + (size_t)own[gc] * R, tid & 31);
@@ -1205,7 +1205,7 @@ __device__ void persistent_exchange(const DevProblem &pb, const DevState &st, in
       else
         asm volatile("bar.sync %0, %1;" ::"n"(kExchBarrier), "r"(32 * nw) : "memory");
     }
-    if (b == 0 && pb.chain0 == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
+    if (b == 0 && pb.rank == 0 && n_swaps) atomicAdd(&st.counters[1], (unsigned long long)n_swaps);
   }
   __syncthreads();
   if (!apply) return;
@@ -1286,7 +1286,7 @@ __device__ bool warp_publish_segment(const DevProblem &pb, const DevState &st, P
   // these loads together with the partial stores, instead of a second and third L2 round trip after it.  (Whether
   // this CTA is the chain's last is not known yet; the few wasted loads of the others cost nothing.)
   const Grp gw{lane, 32, 0};
-  const int gc = pb.chain0 + c;
+  const int gc = global_chain(pb, c);
   const unsigned long long t_pub = st.phase_ts ? gtimer() : 0ull;  // debug: when this warp started publishing
   AcceptPre pre;
   if (flow && exch && exch[gc] != 0) wait_exchange_applied(st, gw, c, it);
@@ -1378,7 +1378,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       sm.seg_unit0[n] = u0;
       sm.seg_slot[n] = b - b_first;
       sm.seg_nseg[n] = b_last - b_first + 1;
-      sm.seg_c2[n] = pb.noseed ? (uint32_t)(pb.chain0 + c) : 0u;
+      sm.seg_c2[n] = pb.noseed ? (uint32_t)(global_chain(pb, c)) : 0u;
       u0 += (sm.seg_j1[n] - sm.seg_j0[n] + unit_j - 1) / unit_j;
       ++n;
       x = xe;
@@ -1422,7 +1422,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       for (int r = 0; r * ngroups < n_seg; ++r) {
         const int sidx = r * ngroups + gi;
         if (sidx < n_seg) {
-          const int c = sm.seg_c[sidx], gc = pb.chain0 + c;
+          const int c = sm.seg_c[sidx], gc = global_chain(pb, c);
           // centre: the record that sits on this chain after the exchange (its own last accepted one if not swapped)
           const double *centre = have_ex ? la_prev + (size_t)own[gc] * rec_len(P, pb.M) : nullptr;
           group_proposal(pb, st, gprop, ps, c, gc, it, sm.seg_slot[sidx] == 0, centre);
@@ -1440,7 +1440,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
         const int o = r * ngroups + gi;  // index among the owned chains
         if (o < n_owned) {
           const int c = b + o * G;
-          group_proposal(pb, st, gprop, ps, c, pb.chain0 + c, it, true);
+          group_proposal(pb, st, gprop, ps, c, global_chain(pb, c), it, true);
           for (int q = gprop.tid; q < P; q += gsize) st.pp[(size_t)c * P + q] = ps.pp[q];
         }
       }

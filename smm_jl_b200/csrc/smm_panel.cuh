@@ -29,8 +29,8 @@ struct PanelWork {
   unsigned *unit_ctr;         // queue head; zero on entry
   int n_eval, units_per_eval;
   int noseed;
-  uint32_t uid0, rep0;        // evaluation e draws from stream (uid0 + e, rep0 + rep_stride * e) when noseed
-  uint32_t rep_stride;
+  uint32_t uid0, rep0;        // evaluation e draws from stream (uid0 + uid_stride * e, rep0 + rep_stride * e) when noseed
+  uint32_t uid_stride, rep_stride;
   int iter;                   // chain mode: BGP iteration (>= 1); batch mode: 0
   double *value, *moments;    // batch mode outputs
   int *status;
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kPanelThreads, MINB)
           const Grp gw{lane, 32, 0};
           group_distance(pb, gw, fs);
           if (w.iter > 0) {
-            group_accept_store(pb, st, gw, fs, cur, pb.chain0 + cur, w.iter, false);
+            group_accept_store(pb, st, gw, fs, cur, global_chain(pb, cur), w.iter, false);
           } else {
             if (lane == 0) {
               w.value[cur] = fs.value[0];
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kPanelThreads, MINB)
       units_cur = 0;
       if (e >= 0) {
         for (int k = lane; k < P; k += 32) theta[k] = __ldcg(w.params + (size_t)e * P + k);
-        c2 = w.noseed ? w.uid0 + (uint32_t)e : 0u;
+        c2 = w.noseed ? w.uid0 + w.uid_stride * (uint32_t)e : 0u;
         c3 = (SMM_STREAM_SIM << 28) | (w.noseed ? ((w.rep0 + w.rep_stride * (uint32_t)e) & SMM_ITER_MASK) : 0u);
         __syncwarp();
       }
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_propose_kernel(DevProblem pb
   const Grp g{tid, (int)blockDim.x, 0};
   load_logtab(sm.logtab);
   __syncthreads();
-  group_proposal(pb, st, g, prop_scratch(sm), c, pb.chain0 + c, iter, true);
+  group_proposal(pb, st, g, prop_scratch(sm), c, global_chain(pb, c), iter, true);
   for (int k = tid; k < pb.P; k += blockDim.x) st.pp[(size_t)c * pb.P + k] = sm.pp[k];
   unsigned long long *acc = (unsigned long long *)st.partials + (size_t)c * zero_len;
   for (int a = tid; a < zero_len; a += blockDim.x) acc[a] = 0ull;
@@ -392,7 +392,8 @@ void launch_panel_chains(const DevProblem &pb, const DevState &st, int iter, int
   w.n_eval = pb.L;
   w.units_per_eval = (pb.panel_N + 31) / 32;
   w.noseed = pb.noseed;
-  w.uid0 = (uint32_t)pb.chain0;
+  w.uid0 = (uint32_t)pb.rank;  // evaluation e = local chain e = global chain e * world + rank
+  w.uid_stride = (uint32_t)pb.world;
   w.rep0 = (uint32_t)iter;
   w.rep_stride = 0u;
   w.iter = iter;
@@ -411,6 +412,7 @@ void launch_panel_batch(const DevProblem &pb, const DevState &st, const double *
   w.units_per_eval = (pb.panel_N + 31) / 32;
   w.noseed = noseed;
   w.uid0 = uid0;
+  w.uid_stride = 1u;
   w.rep0 = rep0;
   w.rep_stride = 1u;
   w.iter = 0;

@@ -12,16 +12,22 @@ import numpy as np
 from ._abi import SMM_NCCL_ID_BYTES, Trace
 
 
-def shard_range(n_chains: int, world_size: int, rank: int) -> "tuple[int, int]":
-    """chains [lo, hi) owned by `rank`: contiguous by id."""
+def shard_chains(n_chains: int, world_size: int, rank: int) -> np.ndarray:
+    """0-based global ids of the chains `rank` owns, in the order of its local columns: rank, rank + world, ...
+    Chains are dealt round robin (include/smm_b200.h): the temperature ladder runs along the global id, and a hot
+    chain's truncated proposal needs more rejection attempts, so every rank should hold the same mix (SURVEY.md 8e
+    shards contiguously; with contiguous blocks the last rank is the straggler of every iteration)."""
     if n_chains % world_size != 0:
         raise ValueError("n_chains must be a multiple of world_size")
-    L = n_chains // world_size
-    return rank * L, (rank + 1) * L
+    return np.arange(rank, n_chains, world_size)
 
 
 def owner_of(chain: int, n_chains: int, world_size: int) -> int:
-    return chain // (n_chains // world_size)
+    return chain % world_size
+
+
+def local_index(chain: int, world_size: int) -> int:
+    return chain // world_size
 
 
 def env_rank_world() -> "tuple[int, int, int]":
@@ -42,7 +48,7 @@ def broadcast_id(make_id, pg=None, device: Optional[str] = None) -> bytes:
 
 
 def gather_trace(local: Trace, pg=None, device: Optional[str] = None) -> Trace:
-    """All ranks receive the full [n][N] trace: per-rank [n][L] blocks joined in rank (= chain) order.
+    """All ranks receive the full [n][N] trace: column c of rank r's [n][L] block is global chain c * world + r.
     `device`: where the collective's tensors live ("cuda" for an NCCL process group; default: host, gloo)."""
     import torch
     import torch.distributed as dist
@@ -56,11 +62,18 @@ def gather_trace(local: Trace, pg=None, device: Optional[str] = None) -> Trace:
         dist.all_gather(bufs, mine, group=pg)
         for r in range(world):
             setattr(parts[r], f, bufs[r].cpu().numpy())
-    return Trace.concat_chains(parts)
+    return Trace.interleave_ranks(parts)
 
 
-def slice_trace(full: Trace, lo: int, hi: int) -> Trace:
-    out = Trace(full.n, hi - lo, full.P, full.M)
+def slice_trace(full: Trace, chains) -> Trace:
+    """the columns `chains` (global ids, e.g. shard_chains(N, world, rank)) of a full trace"""
+    chains = np.asarray(chains)
+    out = Trace(full.n, len(chains), full.P, full.M)
     for f in Trace.FLOAT_FIELDS + Trace.INT_FIELDS:
-        setattr(out, f, np.ascontiguousarray(getattr(full, f)[:, lo:hi]))
+        setattr(out, f, np.ascontiguousarray(getattr(full, f)[:, chains]))
     return out
+
+
+def interleave(per_rank) -> np.ndarray:
+    """per-chain vectors of every rank ([L] each, rank order) -> the [N] vector in global chain order"""
+    return np.stack([np.asarray(v) for v in per_rank], axis=1).reshape(-1)

@@ -144,13 +144,13 @@ def test_eval_accessors():
 
 def test_temperature_ladder_and_shards():
     from smm_jl_b200.configs import temperature_ladder
-    from smm_jl_b200.dist import shard_range, owner_of
+    from smm_jl_b200.dist import shard_chains, owner_of, local_index
     np.testing.assert_allclose(temperature_ladder(3, 5), [1, 3, 5])
     np.testing.assert_allclose(temperature_ladder(1, 5), [1])
-    assert [shard_range(1024, 8, r) for r in (0, 7)] == [(0, 128), (896, 1024)]
-    assert owner_of(129, 1024, 8) == 1
+    assert shard_chains(1024, 8, 7)[:3].tolist() == [7, 15, 23] and len(shard_chains(1024, 8, 0)) == 128
+    assert owner_of(129, 1024, 8) == 1 and local_index(129, 8) == 16
     with pytest.raises(ValueError):
-        shard_range(10, 4, 0)
+        shard_chains(10, 4, 0)
 
 
 def _toy_problem(api, n_params=2, objective=None):

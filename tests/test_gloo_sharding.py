@@ -1,6 +1,6 @@
 """world_size-2 `gloo` test of the N > 1 host path on CPU: rendezvous, broadcast of the library's NCCL id,
 chain sharding and trace gathering.  The oracle's full-run trace stands in for the per-rank device traces
-(no GPU here), so the test checks that shards gathered in rank order reproduce the single-process run."""
+(no GPU here), so the test checks that the round-robin shards, gathered, reproduce the single-process run."""
 import os
 import socket
 import sys
@@ -37,13 +37,17 @@ def _worker(rank, world, port, q):
         cfg = configs.mvnormal(8, 6, n_sim=200, world_size=world, rank=rank, nccl_id=idb)
         cs = cfg.c_struct()
         assert cs.rank == rank and cs.world_size == world and bytes(cs.nccl_id) == idb
-        lo, hi = sd.shard_range(cfg.n_chains, world, rank)
+        mine_ids = sd.shard_chains(cfg.n_chains, world, rank)
+        assert mine_ids.tolist() == list(range(rank, 8, world))
         # 3. every rank's shard of the (deterministic) run, gathered back = the single-process run
         full = oracle_lib.run(configs.mvnormal(8, 6, n_sim=200), 6).trace
-        mine = sd.slice_trace(full, lo, hi)
+        mine = sd.slice_trace(full, mine_ids)
         got = sd.gather_trace(mine)
         for f in Trace.FLOAT_FIELDS + Trace.INT_FIELDS:
             assert np.array_equal(getattr(got, f), getattr(full, f), equal_nan=True), f
+        sig = [None] * world
+        dist.all_gather_object(sig, np.asarray(cfg.sigma0)[mine_ids])
+        assert np.array_equal(sd.interleave(sig), np.asarray(cfg.sigma0))
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

@@ -196,7 +196,8 @@ def test_device_side_statistics_equal_the_host_ones(n_iter, smm):
     api.addEvalFunc(m, api.objfunc_norm_mv)
     api.addEvalFuncOpts(m, {"n_sim": 30})
     MA = api.MAlgoBGP(m, {"N": 12, "maxiter": n_iter, "maxtemp": 5.0, "acc_tuners": list(np.asarray(cfg.acc_tuner)),
-                          "min_improve": [0.0] * 12, "smpl_iters": 100000, "exchange_mode": cfg.exchange_mode})
+                          "min_improve": [0.0] * 12, "smpl_iters": 100000, "exchange_mode": cfg.exchange_mode,
+                          "sigma_adjust_by": 0.0})   # constant sigma: the adaptation grows it without bound over 9000 iterations
     api.computeNextIteration(MA, n_iter)
     dev_mean, dev_med, dev_ci, dev_sum = api.mean(MA), api.median(MA), api.CI(MA, 0.9), api.summary(MA)
     cnt, _, _ = MA._handle().accepted_stats(())

@@ -47,7 +47,7 @@ def _worker(rank, world, port, n_chains, n_iter, mode, q, kind="mvnormal", data_
         full = sd.gather_trace(tr)
         sig = [None] * world
         dist.all_gather_object(sig, sigma)
-        q.put((rank, "ok", full if rank == 0 else None, np.concatenate(sig) if rank == 0 else None, ctr))
+        q.put((rank, "ok", full if rank == 0 else None, sd.interleave(sig) if rank == 0 else None, ctr))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e), None, None, None))
     finally:
@@ -131,7 +131,7 @@ def _seq_worker(rank, world, port, plan, q):
             full = sd.gather_trace(tr)
             sig = [None] * world
             dist.all_gather_object(sig, sigma)
-            out.append((full, np.concatenate(sig)) if rank == 0 else None)
+            out.append((full, sd.interleave(sig)) if rank == 0 else None)
             if i == len(plan) - 2:
                 keep = h          # stays alive while the last handle is created and run
             else:
