@@ -33,7 +33,7 @@ void launch_exchange(const DevProblem &pb, const DevState &st, int iter, int sch
 void launch_objective(const DevProblem &pb, const double *params, int B, int noseed, uint32_t rep0, int n_split,
                       int part_len, double *partials, unsigned *arrive, double *value, double *moments, int *status,
                       cudaStream_t s);
-size_t panel_smem_bytes(int K, int P);
+size_t panel_smem_bytes(int K, int P, int variant);
 cudaError_t configure_panel(int K, int P, int variant);
 int panel_max_blocks_per_sm(int K, int P, int variant);
 void launch_propose(const DevProblem &pb, const DevState &st, int iter, int zero_len, cudaStream_t s);
@@ -360,7 +360,8 @@ struct smm_bgp {
   double eval_param_limit = 0.0;  // |param| bound for which the fixed-point accumulators are sized
   bool panel = false;     // SMM_OBJ_PANEL: propose kernel + panel simulation kernel instead of bgp_eval_kernel
   int panel_grid = 0;     // CTAs of the panel simulation kernel (one resident wave)
-  int panel_variant = 2;  // register budget of the K = 8 instantiation (CTAs per SM)
+  int panel_variant = 2;  // K = 8 instantiation: 2..5 thread per individual (2 = default), 6..8 eight lanes per individual
+                          // (smm_panel.cuh; SMM_PANEL_VARIANT picks another one for experiments)
   std::vector<double> h_lb, h_ub;
   uint64_t seed_algo = 0, seed_sim = 0;
   int mode = 0;           // 0 = multi-launch (+ NCCL), 1 = persistent kernel (+ fused peer-store all-gather),
@@ -619,7 +620,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   if (h->panel) {
     h->n_split = 1;
     h->part_len = 2 * panel_na(cfg->panel_K);  // (hi, lo) fixed-point words per raw sum
-    if (const char *v = getenv("SMM_PANEL_VARIANT")) h->panel_variant = atoi(v) == 3 ? 3 : 2;
+    if (const char *v = getenv("SMM_PANEL_VARIANT")) h->panel_variant = (atoi(v) >= 2 && atoi(v) <= 8) ? atoi(v) : 2;
     CUDA_TRY(configure_panel(cfg->panel_K, P, h->panel_variant));
     const int per_sm = panel_max_blocks_per_sm(cfg->panel_K, P, h->panel_variant);
     if (per_sm < 1) return fail(SMM_E_CUDA, "panel simulation kernel does not fit on an SM");

@@ -95,18 +95,21 @@ struct NormalRow {
 //   14 + 2K + k     Syxl_k = sum y_t x_k,t-1   14 + 3K + k  Sxxl_k = sum x_kt x_k,t-1
 //   14 + 4K + k     Sxx_k  = sum x_kt^2        14 + 5K + k  XL_k   = sum x_k,t-1
 // KT > 0: K known at compile time (everything in registers); KT == 0: run-time K <= kPanelMaxK (local memory).
-template <int KT>
+// SACC: the 5K per-regressor sums are accumulated IN PLACE in `out` (the warp's shared staging tile, one conflict-free
+// column per lane) instead of in registers -- 80 registers less at K = 8, which is what lets a third CTA live on the SM.
+template <int KT, bool SACC = false>
 __device__ __forceinline__ void panel_individual(const DevProblem &pb, const smm_logent *tab, const double *th, int Krt,
                                                  int T, uint32_t row, uint32_t c2, uint32_t c3, double *out,
                                                  int ostride) {
   constexpr int KM = KT > 0 ? KT : kPanelMaxK;
+  constexpr int KA = SACC ? 1 : KM;  // register copies of the per-regressor sums (unused with SACC)
   const int K = KT > 0 ? KT : Krt;
   const double rho = th[0];
   const double *beta = th + 1, *phi = th + 1 + K;
   const double sig_a = th[1 + 2 * K], sig_e = th[2 + 2 * K], mu0 = th[3 + 2 * K];
   NormalRow nr{0u, row, c2, c3, 0.0, false};
   double zt[KM + 1];
-  double x[KM], xp[KM], x0[KM], sx[KM], syx[KM], syxl[KM], sxxl[KM], sxx[KM];
+  double x[KM], xp[KM], x0[KM], sx[KA], syx[KA], syxl[KA], sxxl[KA], sxx[KA];
   if constexpr (KT > 0)
     nr.template fill<KM + 1>(pb, tab, zt);
   else
@@ -117,7 +120,12 @@ __device__ __forceinline__ void panel_individual(const DevProblem &pb, const smm
   for (int k = 0; k < K; ++k) {
     x[k] = __ddiv_rn(zt[1 + k], __dsqrt_rn(__fma_rn(-phi[k], phi[k], 1.0)));
     x0[k] = x[k];
-    sx[k] = syx[k] = syxl[k] = sxxl[k] = sxx[k] = 0.0;
+    if constexpr (SACC) {
+      out[(14 + k) * ostride] = out[(14 + K + k) * ostride] = out[(14 + 2 * K + k) * ostride] =
+          out[(14 + 3 * K + k) * ostride] = out[(14 + 4 * K + k) * ostride] = 0.0;
+    } else {
+      sx[k] = syx[k] = syxl[k] = sxxl[k] = sxx[k] = 0.0;
+    }
   }
   double yl[7] = {y0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // y_{t-1}, y_{t-2}, ...: zero where t-l < 0
   double sy = 0.0, syy[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -144,11 +152,20 @@ __device__ __forceinline__ void panel_individual(const DevProblem &pb, const smm
     for (int l = 2; l <= 6; ++l) hp[l - 2] = __dadd_rn(hp[l - 2], t < l ? y : 0.0);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      sx[k] = __dadd_rn(sx[k], x[k]);
-      sxx[k] = __fma_rn(x[k], x[k], sxx[k]);
-      sxxl[k] = __fma_rn(x[k], xp[k], sxxl[k]);
-      syx[k] = __fma_rn(y, x[k], syx[k]);
-      syxl[k] = __fma_rn(y, xp[k], syxl[k]);
+      if constexpr (SACC) {
+        double *o = out + (14 + k) * ostride;
+        o[0] = __dadd_rn(o[0], x[k]);
+        o[K * ostride] = __fma_rn(y, x[k], o[K * ostride]);
+        o[2 * K * ostride] = __fma_rn(y, xp[k], o[2 * K * ostride]);
+        o[3 * K * ostride] = __fma_rn(x[k], xp[k], o[3 * K * ostride]);
+        o[4 * K * ostride] = __fma_rn(x[k], x[k], o[4 * K * ostride]);
+      } else {
+        sx[k] = __dadd_rn(sx[k], x[k]);
+        sxx[k] = __fma_rn(x[k], x[k], sxx[k]);
+        sxxl[k] = __fma_rn(x[k], xp[k], sxxl[k]);
+        syx[k] = __fma_rn(y, x[k], syx[k]);
+        syxl[k] = __fma_rn(y, xp[k], syxl[k]);
+      }
     }
 #pragma unroll
     for (int l = 6; l >= 1; --l) yl[l] = yl[l - 1];
@@ -171,12 +188,16 @@ __device__ __forceinline__ void panel_individual(const DevProblem &pb, const smm
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    out[(14 + k) * ostride] = sx[k];
-    out[(14 + K + k) * ostride] = syx[k];
-    out[(14 + 2 * K + k) * ostride] = syxl[k];
-    out[(14 + 3 * K + k) * ostride] = sxxl[k];
-    out[(14 + 4 * K + k) * ostride] = sxx[k];
-    out[(14 + 5 * K + k) * ostride] = __dsub_rn(__dadd_rn(x0[k], sx[k]), x[k]);
+    if constexpr (SACC) {
+      out[(14 + 5 * K + k) * ostride] = __dsub_rn(__dadd_rn(x0[k], out[(14 + k) * ostride]), x[k]);
+    } else {
+      out[(14 + k) * ostride] = sx[k];
+      out[(14 + K + k) * ostride] = syx[k];
+      out[(14 + 2 * K + k) * ostride] = syxl[k];
+      out[(14 + 3 * K + k) * ostride] = sxxl[k];
+      out[(14 + 4 * K + k) * ostride] = sxx[k];
+      out[(14 + 5 * K + k) * ostride] = __dsub_rn(__dadd_rn(x0[k], sx[k]), x[k]);
+    }
   }
 }
 
@@ -237,7 +258,7 @@ __host__ __device__ inline size_t panel_warp_smem_doubles(int K, int P) {
   return (size_t)panel_na(K) * kPanelStageStride + (size_t)P;
 }
 
-template <int KT, int MINB>
+template <int KT, int MINB, bool SACC = false>
 __global__ void __launch_bounds__(kPanelThreads, MINB)
     panel_sim_kernel(DevProblem pb, DevState st, PanelWork w) {
   constexpr int KM = KT > 0 ? KT : kPanelMaxK;
@@ -323,7 +344,7 @@ __global__ void __launch_bounds__(kPanelThreads, MINB)
     ++units_cur;
     const int i = (u - e * w.units_per_eval) * 32 + lane;
     if (i < NI) {
-      panel_individual<KT>(pb, logtab, theta, K, T, (uint32_t)i, c2, c3, stage + lane, kPanelStageStride);
+      panel_individual<KT, SACC>(pb, logtab, theta, K, T, (uint32_t)i, c2, c3, stage + lane, kPanelStageStride);
     } else {
       for (int a = 0; a < NA; ++a) stage[a * kPanelStageStride + lane] = 0.0;
     }
@@ -336,6 +357,201 @@ __global__ void __launch_bounds__(kPanelThreads, MINB)
         const double *row = stage + (size_t)a * kPanelStageStride;
 #pragma unroll 8
         for (int s = 0; s < 32; ++s) panel_split(pb, row[s], ahi[q], alo[q]);
+      }
+    }
+    __syncwarp();
+    next = __shfl_sync(0xffffffffu, next, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K = 8, EIGHT LANES PER INDIVIDUAL (one regressor per lane): the thread-per-individual kernel above needs 255
+// registers (two CTAs of four warps per SM, issue slots 45 % busy: fixed-latency stalls with two warps per scheduler).
+// Here a warp simulates 4 individuals at a time, lane (g, k) = individual g, regressor k:
+//   * normals: the 8 lanes of an individual compute 8 consecutive Philox blocks of its stream row per round (16
+//     Box-Muller normals) into a 32-entry shared ring; a period consumes 9 (eta_0..7 from slot k, eps from slot 8);
+//   * recurrence: x_k in lane k; sum_k beta_k x_k by a three-step butterfly over the 8 lanes (every lane gets the same
+//     bits; NOT the oracle's sequential fma chain: values agree to ~1e-15 relative, inside the 1e-6 contract and the
+//     1e-9 the tests ask for); y is computed redundantly by the 8 lanes;
+//   * moments: lane k owns its regressor's six sums; lane l = 0..6 owns Syy_l (its y_{t-l} arrives through a shuffle
+//     delay line: one shfl_up per period instead of seven registers) and HG_l; lane 7 owns Sy;
+//   * pooling: every raw sum is split exactly into the two fixed-point words and added to the warp's shared 64-bit
+//     accumulators (red.shared), which go to the evaluation's global accumulators when the warp leaves it.
+// 80-108 registers per thread: 16-24 warps per SM.  Same work queue, same exact pooling, same finalisation as above.
+// MEASURED (profiles/panel_variants_r2.txt, ncu prof_panel_v7): issue slots 67 % busy instead of 45 %, but 760 M warp
+// instructions per launch instead of 382 M -- the recurrence costs ~116 instructions per warp-period for 4 individuals
+// (shuffles, selects, ring addressing, redundant y) against ~180 thread-instructions per individual-period in the
+// register-resident kernel -- so C4 runs at 1.02 ms per iteration instead of 0.78 ms.  Kept as SMM_PANEL_VARIANT=6..8
+// for the record; the thread-per-individual kernel (variant 2) stays the default.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kLaneK = 8;
+
+// per warp: ring[4][32] | theta[P] (padded) | fin scratch tot[NA] mom[M] value[2] flags[2] | acc u64 [2 NA]
+__host__ __device__ inline size_t panel_lanes_warp_doubles(int P, int M) {
+  const int NA = panel_na(kLaneK);
+  return 128 + (size_t)((P + 1) & ~1) + (size_t)NA + (size_t)M + 4 + 2 * (size_t)NA;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kPanelThreads, MINB) panel_lanes_kernel(DevProblem pb, DevState st, PanelWork w) {
+  constexpr int K = kLaneK, NA = 14 + 6 * K;
+  __shared__ smm_logent logtab[1 << SMM_LOG_BITS];
+  extern __shared__ double smem_d[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = lane & 7, grp = lane >> 3;
+  const int T = pb.panel_T, NI = pb.panel_N, P = pb.P, M = pb.M;
+  double *base = smem_d + (size_t)warp * panel_lanes_warp_doubles(P, M);
+  double *ring = base + grp * 32;
+  double *theta = base + 128;
+  double *fin = theta + ((P + 1) & ~1);
+  unsigned long long *sacc = (unsigned long long *)(fin + NA + M + 4);  // [2 NA] (hi, lo) per raw sum
+  load_logtab(logtab);
+  __syncthreads();
+  const int total = w.n_eval * w.units_per_eval;
+  int cur = -1, units_cur = 0;
+  uint32_t c2 = 0u, c3 = SMM_STREAM_SIM << 28;
+  double rho = 0.0, beta = 0.0, phi = 0.0, sig_a = 0.0, sig_e = 0.0, mu0 = 0.0, x0scale = 0.0;
+  int next = 0;
+  if (lane == 0) next = (int)atomicAdd(w.unit_ctr, 1u);
+  next = __shfl_sync(0xffffffffu, next, 0);
+  for (;;) {
+    const int u = next;
+    const int e = u < total ? u / w.units_per_eval : -1;
+    if (e != cur) {
+      if (cur >= 0) {
+        // leave evaluation `cur`: the warp's exact sums go to the evaluation's, its units are counted
+        unsigned long long *acc = w.acc + (size_t)cur * 2 * NA;
+        __syncwarp();
+        for (int a = lane; a < 2 * NA; a += 32) atomicAdd(acc + a, sacc[a]);
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          const unsigned prev = atom_acq_rel_gpu(w.done + cur, (unsigned)units_cur);
+          last = (prev + (unsigned)units_cur == (unsigned)w.units_per_eval);
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          const FinScratch fs{theta, fin, fin + NA, fin + NA + M, (int *)(fin + NA + M + 2)};
+          for (int a = lane; a < NA; a += 32) {
+            const long long hi = (long long)__ldcg(acc + 2 * a), lo = (long long)__ldcg(acc + 2 * a + 1);
+            fs.tot[a] = __fma_rn((double)lo, pb.pan_lo_inv, __dmul_rn((double)hi, pb.pan_hi_inv));
+          }
+          __syncwarp();
+          panel_moments(pb, fs, lane);
+          const Grp gw{lane, 32, 0};
+          group_distance(pb, gw, fs);
+          if (w.iter > 0) {
+            group_accept_store(pb, st, gw, fs, cur, global_chain(pb, cur), w.iter, false);
+          } else {
+            if (lane == 0) {
+              w.value[cur] = fs.value[0];
+              w.status[cur] = fs.flags[1];
+            }
+            for (int m = lane; m < M; m += 32) w.moments[(size_t)cur * M + m] = fs.mom[m];
+          }
+          __syncwarp();
+        }
+      }
+      cur = e;
+      units_cur = 0;
+      if (e >= 0) {
+        for (int q = lane; q < P; q += 32) theta[q] = __ldcg(w.params + (size_t)e * P + q);
+        for (int a = lane; a < 2 * NA; a += 32) sacc[a] = 0ull;
+        c2 = w.noseed ? w.uid0 + w.uid_stride * (uint32_t)e : 0u;
+        c3 = (SMM_STREAM_SIM << 28) | (w.noseed ? ((w.rep0 + w.rep_stride * (uint32_t)e) & SMM_ITER_MASK) : 0u);
+        __syncwarp();
+        rho = theta[0];
+        beta = theta[1 + k];
+        phi = theta[1 + K + k];
+        sig_a = theta[1 + 2 * K];
+        sig_e = theta[2 + 2 * K];
+        mu0 = theta[3 + 2 * K];
+        x0scale = __dsqrt_rn(__fma_rn(-phi, phi, 1.0));
+      }
+    }
+    if (e < 0) break;
+    if (lane == 0) next = (int)atomicAdd(w.unit_ctr, 1u);  // prefetch: the latency hides behind the simulation
+    ++units_cur;
+    const int i_unit = (u - e * w.units_per_eval) * 32;
+#pragma unroll 1
+    for (int pass = 0; pass < 8; ++pass) {
+      const int i = i_unit + pass * 4 + grp;
+      if (i_unit + pass * 4 >= NI) break;  // warp uniform: nobody left in this unit
+      const bool valid = i < NI;
+      const uint32_t row = valid ? (uint32_t)i : 0u;
+      // ---- normals: rounds of 8 blocks per individual into the ring ----
+      int avail = 0, rd = 0, wr = 0;
+      uint32_t jblk = 0u;
+      auto produce = [&]() {
+        __syncwarp();  // everybody has read the slots that are overwritten now
+        double z0, z1;
+        smm_normal_pair_tab(philox_sim(pb, jblk + (uint32_t)k, row, c2, c3), logtab, &z0, &z1);
+        ring[(wr + 2 * k) & 31] = z0;
+        ring[(wr + 2 * k + 1) & 31] = z1;
+        __syncwarp();
+        jblk += 8u;
+        wr = (wr + 16) & 31;
+        avail += 16;
+      };
+      produce();
+      const double a_i = ring[rd & 31], e_init = ring[(rd + 1 + k) & 31];
+      rd = (rd + 9) & 31;
+      avail -= 9;
+      const double alpha = __fma_rn(sig_a, a_i, mu0);
+      const double y0 = __ddiv_rn(alpha, __dsub_rn(1.0, rho));
+      double x = __ddiv_rn(e_init, x0scale);
+      const double x0 = x;
+      double sx = 0.0, sxx = 0.0, sxxl = 0.0, syx = 0.0, syxl = 0.0;
+      double sy = 0.0, syy = 0.0, head = 0.0, tail = 0.0;
+      double d = k == 1 ? y0 : 0.0;  // lane l >= 1: y_{t-l} (0 where t - l < 0)
+      double yl = y0;
+#pragma unroll 1
+      for (int t = 1; t <= T; ++t) {
+        if (avail < 9) produce();
+        const double eta = ring[(rd + k) & 31], eps = ring[(rd + 8) & 31];
+        rd = (rd + 9) & 31;
+        avail -= 9;
+        const double xp = x;
+        x = __fma_rn(phi, xp, eta);
+        double bx = __dmul_rn(beta, x);
+        bx = __dadd_rn(bx, __shfl_xor_sync(0xffffffffu, bx, 1));
+        bx = __dadd_rn(bx, __shfl_xor_sync(0xffffffffu, bx, 2));
+        bx = __dadd_rn(bx, __shfl_xor_sync(0xffffffffu, bx, 4));
+        const double y = __fma_rn(sig_e, eps, __dadd_rn(__fma_rn(rho, yl, alpha), bx));
+        sy = __dadd_rn(sy, y);
+        syy = __fma_rn(y, k == 0 ? y : d, syy);
+        head = __dadd_rn(head, t < k ? y : 0.0);
+        tail = __dadd_rn(tail, t > T - k ? y : 0.0);
+        sx = __dadd_rn(sx, x);
+        sxx = __fma_rn(x, x, sxx);
+        sxxl = __fma_rn(x, xp, sxxl);
+        syx = __fma_rn(y, x, syx);
+        syxl = __fma_rn(y, xp, syxl);
+        const double dn = __shfl_up_sync(0xffffffffu, d, 1, 8);
+        d = k == 1 ? y : dn;
+        yl = y;
+      }
+      if (valid) {
+        // lane k: its regressor's six sums; lane l <= 6: Syy_l (and HG_l for l >= 1); lane 7: Sy
+        auto pool = [&](int a, double v) {
+          unsigned long long hi = 0ull, lo = 0ull;
+          panel_split(pb, v, hi, lo);
+          atomicAdd(sacc + 2 * a, hi);
+          atomicAdd(sacc + 2 * a + 1, lo);
+        };
+        pool(14 + k, sx);
+        pool(14 + K + k, syx);
+        pool(14 + 2 * K + k, syxl);
+        pool(14 + 3 * K + k, sxxl);
+        pool(14 + 4 * K + k, sxx);
+        pool(14 + 5 * K + k, __dsub_rn(__dadd_rn(x0, sx), x));
+        if (k == 7) {
+          pool(0, sy);
+        } else {
+          pool(1 + k, syy);
+          if (k >= 1) pool(7 + k, __dsub_rn(__dadd_rn(__dadd_rn(sy, sy), y0), __dadd_rn(head, tail)));
+        }
       }
     }
     __syncwarp();
@@ -360,23 +576,40 @@ __global__ void __launch_bounds__(kEvalThreads) bgp_propose_kernel(DevProblem pb
   }
 }
 
-size_t panel_smem_bytes(int K, int P) { return sizeof(double) * panel_warp_smem_doubles(K, P) * (kPanelThreads / 32); }
+static bool panel_is_lanes(int K, int variant) { return K == kLaneK && variant >= 6; }
+size_t panel_smem_bytes(int K, int P, int variant) {
+  if (panel_is_lanes(K, variant)) return sizeof(double) * panel_lanes_warp_doubles(P, 4 * K + 8) * (kPanelThreads / 32);
+  return sizeof(double) * panel_warp_smem_doubles(K, P) * (kPanelThreads / 32);
+}
 
-// K = 8 (the C4 shape) has a register-resident instantiation; `variant` picks its register budget
-// (CTAs per SM the compiler must make room for: 2 -> 255 registers, 3 -> 168 with some spills)
+// K = 8 (the C4 shape) has register-resident instantiations; `variant` picks the register budget (= CTAs per SM the
+// compiler must make room for) and where the 5K per-regressor sums live:
+//   2: 255 registers, sums in registers      3: 168 registers, sums in registers (spills)
+//   4: 168 registers, sums in the shared staging tile (3 CTAs per SM)      5: 128 registers, shared sums (4 CTAs)
+//   6 / 7 / 8: panel_lanes_kernel (eight lanes per individual) with room for 4 / 6 / 8 CTAs per SM
 typedef void (*PanelKernel)(DevProblem, DevState, PanelWork);
 static PanelKernel panel_kernel(int K, int variant) {
-  if (K == 8) return variant == 3 ? panel_sim_kernel<8, 3> : panel_sim_kernel<8, 2>;
+  if (K == 8) {
+    switch (variant) {
+      case 3: return panel_sim_kernel<8, 3>;
+      case 4: return panel_sim_kernel<8, 3, true>;
+      case 5: return panel_sim_kernel<8, 4, true>;
+      case 6: return panel_lanes_kernel<4>;
+      case 7: return panel_lanes_kernel<6>;
+      case 8: return panel_lanes_kernel<8>;
+      default: return panel_sim_kernel<8, 2>;
+    }
+  }
   return panel_sim_kernel<0, 1>;
 }
 
 cudaError_t configure_panel(int K, int P, int variant) {
   return cudaFuncSetAttribute(panel_kernel(K, variant), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)panel_smem_bytes(K, P));
+                              (int)panel_smem_bytes(K, P, variant));
 }
 int panel_max_blocks_per_sm(int K, int P, int variant) {
   int n = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, panel_kernel(K, variant), kPanelThreads, panel_smem_bytes(K, P));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, panel_kernel(K, variant), kPanelThreads, panel_smem_bytes(K, P, variant));
   return n;
 }
 void launch_propose(const DevProblem &pb, const DevState &st, int iter, int zero_len, cudaStream_t s) {
@@ -397,7 +630,7 @@ void launch_panel_chains(const DevProblem &pb, const DevState &st, int iter, int
   w.rep0 = (uint32_t)iter;
   w.rep_stride = 0u;
   w.iter = iter;
-  panel_kernel(pb.panel_K, variant)<<<grid, kPanelThreads, panel_smem_bytes(pb.panel_K, pb.P), s>>>(pb, st, w);
+  panel_kernel(pb.panel_K, variant)<<<grid, kPanelThreads, panel_smem_bytes(pb.panel_K, pb.P, variant), s>>>(pb, st, w);
 }
 // batch mode: bare objective at params[B][P]
 void launch_panel_batch(const DevProblem &pb, const DevState &st, const double *params, int B, int noseed, uint32_t uid0,
@@ -419,5 +652,5 @@ void launch_panel_batch(const DevProblem &pb, const DevState &st, const double *
   w.value = value;
   w.moments = moments;
   w.status = status;
-  panel_kernel(pb.panel_K, variant)<<<grid, kPanelThreads, panel_smem_bytes(pb.panel_K, pb.P), s>>>(pb, st, w);
+  panel_kernel(pb.panel_K, variant)<<<grid, kPanelThreads, panel_smem_bytes(pb.panel_K, pb.P, variant), s>>>(pb, st, w);
 }
