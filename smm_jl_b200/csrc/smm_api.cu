@@ -708,7 +708,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   const bool want_phase_ts = getenv("SMM_PHASE_TS") != nullptr;
   if (want_phase_ts) {
     size_t slots = (size_t)L * h->n_split;
-    if ((size_t)h->grid * 4 + L > slots) slots = (size_t)h->grid * 4 + L;
+    if ((size_t)h->grid * 6 + L > slots) slots = (size_t)h->grid * 6 + L;  // + two publish rows per CTA
     plan.filled(h->phase_ts, slots * 4, 0ull);
   }
 
@@ -1499,8 +1499,9 @@ int smm_debug_pairs(smm_bgp *h, int32_t iter, int32_t *ij, int32_t *level_offset
 int smm_debug_phase_ts(smm_bgp *h, uint64_t *out, int64_t n) {
   if (!h || !out) return fail(SMM_E_ARG, "null argument");
   if (!h->st.phase_ts) return fail(SMM_E_STATE, "set SMM_PHASE_TS=1 before smm_bgp_create");
-  // persistent modes: 4 rows per CTA, then one row per local chain {publish start, tag time, finishing CTA, iteration}
-  const int64_t blocks = h->mode >= 1 ? (int64_t)h->grid * 4 + h->L : (int64_t)h->L * h->n_split;
+  // persistent modes: 4 rows per CTA, then one row per local chain {publish start, tag time, finishing CTA, iteration},
+  // then 2 rows per CTA {before the system fence, after it, after the completion adds} (world > 1, exchange_mode 2)
+  const int64_t blocks = h->mode >= 1 ? (int64_t)h->grid * 6 + h->L : (int64_t)h->L * h->n_split;
   const int64_t have = blocks * 4;
   CUDA_TRY(cudaMemcpy(out, h->st.phase_ts, sizeof(uint64_t) * (n < have ? n : have), cudaMemcpyDeviceToHost));
   return (int)blocks;

@@ -1254,14 +1254,19 @@ __device__ bool wait_all_done(const DevProblem &pb, const DevState &st, unsigned
 // The other half: after the CTA's finishing warps have stored everything (CTA barrier by the caller), one thread fences
 // once -- system scope when the records went to peer GPUs -- and adds the number of chains this CTA finished to the
 // completion counter of every rank (a remote atomic over NVLink for the peers).
-__device__ __forceinline__ void publish_completions(const DevProblem &pb, const DevState &st, unsigned n_finished) {
+// `stamp` (debug, with SMM_PHASE_TS): {before the fence, after it, after the adds} of this CTA.
+__device__ __forceinline__ void publish_completions(const DevProblem &pb, const DevState &st, unsigned n_finished,
+                                                    unsigned long long *stamp = nullptr) {
   if (n_finished == 0) return;
   if (pb.world > 1) {
+    if (stamp) stamp[0] = gtimer();
     __threadfence_system();
+    if (stamp) stamp[1] = gtimer();
     for (int r = 0; r < pb.world; ++r)
       asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(done_counter(pb, st.peer_val_all[r])),
                    "l"((unsigned long long)n_finished)
                    : "memory");
+    if (stamp) stamp[2] = gtimer();
   } else {
     fence_acq_rel_gpu();
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(done_counter(pb, st.val_all)),
@@ -1591,7 +1596,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
     PHASE_STAMP((b * 2 + (it & 1)) * 2, 2);  // warp 0 done (incl. chain finalisation)
     if (kFlow) {  // one fence and one counter update per CTA tell every rank which chains are complete
       __syncthreads();
-      if (tid == 0) publish_completions(pb, st, sm.n_finished);
+      if (tid == 0)  // (debug rows behind the per-chain rows: two per CTA, by iteration parity)
+        publish_completions(pb, st, sm.n_finished,
+                            st.phase_ts ? st.phase_ts + ((size_t)G * 4 + L + (size_t)b * 2 + (it & 1)) * 4 : nullptr);
     }
     if (!kFlow) {
       if (!grid_barrier(pb, st, gen, fused, seq)) return;

@@ -24,8 +24,9 @@ with _lib.BGPHandle(cfg) as h:
         print("us/iter", ms * 10)
         raw = h.phase_ts().astype(np.int64)
         nchain = chains
-        per_chain = raw[-nchain:]                                    # {publish start, tag time, finishing CTA, iteration}
-        ts = raw[:-nchain].reshape(-1, 2, 2, 4)                      # [block][parity][half][stamp]
+        G = (raw.shape[0] - nchain) // 6                             # rows: 4 per CTA | one per chain | 2 per CTA
+        per_chain = raw[4 * G:4 * G + nchain]                        # {publish start, tag time, finishing CTA, iteration}
+        ts = raw[:4 * G].reshape(-1, 2, 2, 4)                        # [block][parity][half][stamp]
         last_par = h.iteration & 1
         cur, prev = ts[:, last_par], ts[:, 1 - last_par]
         t0 = prev[:, 0, 0].min()

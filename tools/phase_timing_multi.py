@@ -26,8 +26,10 @@ with _lib.BGPHandle(cfg) as h:
     ms = h.step(100)
     raw = h.phase_ts().astype(np.int64)
     L = chains
-    per_chain = raw[-L:]
-    ts = raw[:-L].reshape(-1, 2, 2, 4)
+    G = (raw.shape[0] - L) // 6                                      # rows: 4 per CTA | one per chain | 2 per CTA
+    per_chain = raw[4 * G:4 * G + L]
+    ts = raw[:4 * G].reshape(-1, 2, 2, 4)
+    pub = raw[4 * G + L:].reshape(G, 2, 4)                           # [CTA][parity]{before fence, after fence, after adds}
     last_par = h.iteration & 1
     cur, prev = ts[:, last_par], ts[:, 1 - last_par]
     t0 = prev[:, 0, 0].min()
@@ -42,6 +44,13 @@ with _lib.BGPHandle(cfg) as h:
         print("last: exchange done      us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[own, 1, 0])))
         print("last: proposals done     us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[own, 1, 1])))
         print("last: A start            us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(cur[:, 0, 0])))
+        pp = pub[:, 1 - last_par]                                    # the previous iteration's publish, complete for every CTA
+        okp = pp[:, 0] > 0
+        if okp.any():
+            print("prev: publish: fence start  us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(pp[okp, 0])))
+            print("prev: publish: fence took   us: min %.1f med %.1f p90 %.1f max %.1f" % pct((pp[okp, 1] - pp[okp, 0]) / 1e3))
+            print("prev: publish: adds issued  us: min %.1f med %.1f p90 %.1f max %.1f" % pct((pp[okp, 2] - pp[okp, 1]) / 1e3))
+            print("prev: publish: all done     us: min %.1f med %.1f p90 %.1f max %.1f" % pct(f(pp[okp, 2])))
         tags = (per_chain[:, 1] - np.median(cur[:, 0, 0])) / 1e3
         print("local chains' tags (relative to the last A start): med %.1f p90 %.1f max %.1f" % tuple(np.percentile(tags, [50, 90, 100])))
 if world > 1:
