@@ -337,7 +337,8 @@ def main():
     ap.add_argument("--exchange-mode", type=int, default=-1,
                     help="0 = one launch per iteration (+NCCL), 1 = persistent kernel with grid barriers (+fused peer "
                          "all-gather), 2 = barrier-free persistent kernel (records stored to every peer, one completion "
-                         "counter per rank); default: 2")
+                         "counter per rank), 3 = the same with flag-in-data words for the next iteration's critical "
+                         "path; default: the library's choice (smm_jl_b200/api.py)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -354,7 +355,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.exchange_mode < 0:
-        args.exchange_mode = 2
+        args.exchange_mode = 3 if world > 1 else 2     # the library's own choice (smm_jl_b200/api.py::_exchange_mode)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
@@ -578,7 +579,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(world), "n_chains": n_chains, "chains_per_gpu": L, "n_params": N_PARAMS,
                        "n_moments": N_MOMENTS, "n_sim": N_SIM, "objective": "norm_mv (means + variances)",
-                       "parallelism": f"chains sharded over {world} GPU(s)" + (({0: ", ncclAllGather per iteration", 1: ", all-gather fused into the persistent kernel (peer stores over NVLink + one flag exchange inside the grid barrier)", 2: ", all-gather fused into the barrier-free persistent kernel (records and values stored to every peer over NVLink, one remote atomic per CTA on each rank's completion counter)"}[args.exchange_mode]) if world > 1 else ""),
+                       "parallelism": f"chains sharded over {world} GPU(s)" + (({0: ", ncclAllGather per iteration", 1: ", all-gather fused into the persistent kernel (peer stores over NVLink + one flag exchange inside the grid barrier)", 2: ", all-gather fused into the barrier-free persistent kernel (records and values stored to every peer over NVLink, one remote atomic per CTA on each rank's completion counter)", 3: ", all-gather fused into the barrier-free persistent kernel (value, sigma and proposal centre of every chain stored to every peer over NVLink as flag-in-data words, full records behind a completion counter off the critical path)"}.get(args.exchange_mode, "")) if world > 1 else ""),
                        "exchange_mode": args.exchange_mode,
                        "l2": "no input is re-read between iterations: every draw is generated in registers; the only "
                              "carried data is the chains' own state (~60 KB), which the algorithm's data dependence requires",

@@ -101,8 +101,12 @@ typedef struct smm_bgp_config {
   int32_t exchange_mode; /* 0 = one launch per iteration (+ ncclAllGather + exchange kernel when world > 1);
                             1 = persistent cooperative kernel; with world > 1 the all-gather is fused into it
                             as peer stores over NVLink (CUDA IPC) and a flag exchange inside the grid barrier;
-                            2 = the same persistent kernel without any grid barrier: every CTA waits for per-chain
-                            completion tags (written by the warp that finished the chain, to every rank) instead    */
+                            2 = the same persistent kernel without any grid barrier: every CTA waits for its rank's
+                            completion counter, to which every CTA of every rank adds the chains it finished;
+                            3 = as 2, but what the next iteration's critical path needs (value, sigma and last accepted
+                            parameters of every chain) travels as flag-in-data words {32 payload bits | iteration tag},
+                            so no system fence and no counter round trip sits between two iterations; the counter
+                            only covers the full records the owners copy for swap_ev_ij! (fastest with world > 1)   */
   int32_t n_split;       /* mode 0: CTAs per chain evaluation; mode 1: cap on CTAs per SM; 0 = automatic      */
 } smm_bgp_config;
 

@@ -138,11 +138,12 @@ mutable struct MAlgoBGPB200 <: MAlgo
         obj = SMM_OBJ[m.objfunc]
         idb = get(opts, "nccl_id", zeros(UInt8, SMM_NCCL_ID_BYTES))
         world == 1 || length(idb) == SMM_NCCL_ID_BYTES || error("opts[\"nccl_id\"]: 128 bytes from smm_nccl_unique_id() on rank 0")
-        # exchange_mode: the fastest mode the shape allows (2 = barrier-free persistent kernel; 0 = one launch per
-        # iteration for the panel objective and for more than 32 parameters); a persistent mode that does not fit the
-        # shape falls back to 0 unless the user asked for it explicitly (same rule as smm_jl_b200/api.py)
+        # exchange_mode: the fastest mode the shape allows (2 = barrier-free persistent kernel on one GPU, 3 = the same
+        # with the flag-in-data hand-over on several; 0 = one launch per iteration for the panel objective and for more
+        # than 32 parameters); a persistent mode that does not fit the shape falls back to 0 unless the user asked for
+        # it explicitly (same rule as smm_jl_b200/api.py)
         explicit = haskey(opts, "exchange_mode")
-        mode = explicit ? opts["exchange_mode"] : ((obj == 3 || np > 32) ? 0 : 2)
+        mode = explicit ? opts["exchange_mode"] : ((obj == 3 || np > 32) ? 0 : (world > 1 ? 3 : 2))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         GC.@preserve lb ub init dm dw sigma0 tuners minimp begin
             mkcfg(md) = SmmBgpConfig(SMM_ABI_VERSION, np, length(dm), pointer(lb), pointer(ub), pointer(init), pointer(dm), pointer(dw),

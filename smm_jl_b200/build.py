@@ -13,8 +13,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SO = os.path.join(HERE, "libsmm_b200.so")
-SOURCES = ["smm_kernels.cu", "smm_api.cu", "smm_stats.cu"]
+SO = os.environ.get("SMM_B200_SO") or os.path.join(HERE, "libsmm_b200.so")   # (override: A/B runs of two builds)
+# (source, extra flags, object name): smm_kernels.cu is compiled twice, the second time with -DSMM_LL_TU (exchange_mode 3)
+UNITS = [("smm_kernels.cu", [], "smm_kernels.o"), ("smm_kernels.cu", ["-DSMM_LL_TU"], "smm_kernels_ll.o"),
+         ("smm_api.cu", [], "smm_api.o"), ("smm_stats.cu", [], "smm_stats.o")]
+SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = [os.path.join(CSRC, "smm_device.cuh"), os.path.join(CSRC, "smm_panel.cuh"), os.path.join(INCLUDE, "smm_b200.h"),
            os.path.join(INCLUDE, "smm_stream.h"), os.path.join(INCLUDE, "smm_stream_tables.h")]
 
@@ -25,7 +28,6 @@ NVCC_FLAGS = [
     "-fmad=false",              # products and sums stay separately rounded; fma only where written
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-ffp-contract=off",
-    "-shared",
 ]
 
 
@@ -47,14 +49,25 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
     if not force and not needs_build():
         return SO
-    cmd = [nvcc()] + NVCC_FLAGS + (extra or []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl"]
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src, flags, obj in UNITS:     # the translation units compile side by side
+        cmd = [nvcc()] + NVCC_FLAGS + flags + (extra or []) + ["-c", "-o", os.path.join(objdir, obj), os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out)
+        if verbose and out:
+            print(out, file=sys.stderr)
+    cmd = [nvcc(), "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + \
+          [os.path.join(objdir, u[2]) for u in UNITS] + ["-lnccl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose and (r.stdout or r.stderr):
-        print(r.stdout + r.stderr, file=sys.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return SO
 
 

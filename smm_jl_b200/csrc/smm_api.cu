@@ -47,6 +47,13 @@ void launch_rng_throughput(long long n_per_thread, int blocks, double *out, cuda
 cudaError_t launch_barrier_bench(const DevProblem &pb, const DevState &st, int variant, int n, int grid, cudaStream_t s);
 void launch_sim_throughput(const DevProblem &pb, int n_per_thread, int blocks, int threads, int dyn, double *out,
                            cudaStream_t s);
+namespace ll {  // smm_kernels.cu compiled with -DSMM_LL_TU: the persistent kernel with the flag-in-data hand-over (exchange_mode 3)
+int persistent_max_blocks_per_sm(int N, int D, int M, int cta_seg);
+cudaError_t configure_persistent(int N, int D, int M, int cta_seg);
+cudaError_t launch_persistent(const DevProblem &pb, const DevState &st, int iter0, int n_iters, int sched_iter0,
+                              int n_s, int part_len, int max_seg, int cta_seg, int grid, bool flow,
+                              unsigned long long done_base, cudaStream_t s);
+}  // namespace ll
 // smm_stats.cu
 int stats_smem_cap();
 cudaError_t launch_accepted_stats(const DevState &st, int L, int P, int it_lo, int it_hi, const double *probs, int n_probs,
@@ -365,7 +372,8 @@ struct smm_bgp {
   std::vector<double> h_lb, h_ub;
   uint64_t seed_algo = 0, seed_sim = 0;
   int mode = 0;           // 0 = multi-launch (+ NCCL), 1 = persistent kernel (+ fused peer-store all-gather),
-                          // 2 = persistent kernel without grid barriers (one completion counter per rank)
+                          // 2 = persistent kernel without grid barriers (one completion counter per rank),
+                          // 3 = the same with flag-in-data words for what the next iteration's critical path needs
   int grid = 0, max_seg = 1, cta_seg = 1;  // persistent kernel: CTAs, partial slots per chain, chains per CTA share
   int iter = 0;      // iterations completed (algo.i)
   unsigned long long done_base = 0;  // exchange_mode 2: value of the completion counter once everything enqueued has run
@@ -392,7 +400,7 @@ struct smm_bgp {
   DevBuf<double> lb, ub, init, data, w, acc_tuner, min_improve;
   DevBuf<double> sigma, accept_rate, la_cur, la_pub, la_all, val_all, pp;
   DevBuf<GridBarrier> bar;
-  DevBuf<unsigned long long> sync_seq, flags;
+  DevBuf<unsigned long long> sync_seq, flags, ll;
   DevBuf<int> n_noex, n_acc;
   DevBuf<double> t_value, t_prob, t_curr, t_best, t_params, t_mom;
   DevBuf<uint8_t> t_acc;
@@ -599,7 +607,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   *h->ss.h_err = 0;
   stamp("stream + events");
 
-  if (cfg->exchange_mode < 0 || cfg->exchange_mode > 2) return fail(SMM_E_ARG, "exchange_mode must be 0, 1 or 2");
+  if (cfg->exchange_mode < 0 || cfg->exchange_mode > 3) return fail(SMM_E_ARG, "exchange_mode must be 0, 1, 2 or 3");
   h->mode = cfg->exchange_mode;
   if (h->world > kMaxWorld) return fail(SMM_E_ARG, "world_size > 8");
   h->seed_algo = cfg->seed_algo;
@@ -642,8 +650,8 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     h->cta_seg = (int)((Tj / gw + 1 + n_blocks_philox - 1) / n_blocks_philox + 1);  // chains one CTA's share can touch
     if (h->cta_seg > persistent_max_cta_seg())
       return fail(SMM_E_UNSUPPORTED_SHAPE, "exchange_mode 1: too many chains per SM for the persistent kernel; use exchange_mode 0");
-    CUDA_TRY(configure_persistent(N, P, M, h->cta_seg));
-    if (persistent_max_blocks_per_sm(N, P, M, h->cta_seg) < 1)
+    CUDA_TRY(h->mode == 3 ? ll::configure_persistent(N, P, M, h->cta_seg) : configure_persistent(N, P, M, h->cta_seg));
+    if ((h->mode == 3 ? ll::persistent_max_blocks_per_sm(N, P, M, h->cta_seg) : persistent_max_blocks_per_sm(N, P, M, h->cta_seg)) < 1)
       return fail(SMM_E_UNSUPPORTED_SHAPE,
                   "persistent kernel does not fit on an SM (its shared memory grows with the chain count); use exchange_mode 0");
     const int per_chain = (int)((gw + L - 1) / L + 1);
@@ -673,12 +681,13 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
   plan.filled(h->n_acc, (size_t)L, 0);
   plan.filled(h->la_cur, (size_t)L * R, nan);
   plan.filled(h->la_pub, (size_t)L * R, nan);
-  const bool have_la_all = h->world > 1 || h->mode == 2;
+  const bool have_la_all = h->world > 1 || h->mode >= 2;
   if (have_la_all) plan.filled(h->la_all, (size_t)(h->mode ? 2 : 1) * N * R, nan, xs);
   // [2][N] values by iteration parity, followed by [N] 64-bit words whose first is the rank's completion counter
   // (exchange_mode 2), zero = nothing done
   plan.add(h->val_all, (size_t)3 * N, xs, false, 0.0);
   plan.filled(h->flags, (size_t)kMaxWorld, 0ull, xs);
+  if (h->mode == 3) plan.filled(h->ll, (size_t)2 * N * ll_words(P), 0ull, xs);  // tag 0 = nothing arrived
   plan.filled(h->applied, (size_t)L, 0u);
   plan.filled(h->pp, (size_t)L * P, nan);
   plan.filled(h->bar, 1, GridBarrier{0u, 0u});
@@ -861,9 +870,12 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
     st.peer_val_all[r] = nullptr;
     st.peer_flags[r] = nullptr;
   }
-  if (h->mode == 2) {  // the barrier-free kernel always uses the gather layout; with one rank the "peer" is this GPU
+  st.ll = h->mode == 3 ? h->ll.p : nullptr;
+  for (int r = 0; r < kMaxWorld; ++r) st.peer_ll[r] = nullptr;
+  if (h->mode >= 2) {  // the barrier-free kernel always uses the gather layout; with one rank the "peer" is this GPU
     st.peer_la_all[0] = h->la_all.p;
     st.peer_val_all[0] = h->val_all.p;
+    st.peer_ll[0] = st.ll;
   }
   if (fused_peers) {
     // the same plan on every rank: a peer's buffers sit at the same offsets of its arena
@@ -873,6 +885,7 @@ int smm_bgp_create(const smm_bgp_config *cfg, smm_bgp **out) {
       st.peer_la_all[r] = (double *)((char *)arena->peer[r] + o_la);
       st.peer_val_all[r] = (double *)((char *)arena->peer[r] + o_val);
       st.peer_flags[r] = (unsigned long long *)((char *)arena->peer[r] + o_fl);
+      if (st.ll) st.peer_ll[r] = (unsigned long long *)((char *)arena->peer[r] + ((char *)h->ll.p - (char *)arena_base));
     }
   }
   st.phase_ts = want_phase_ts ? h->phase_ts.p : nullptr;
@@ -985,9 +998,10 @@ int enqueue_iterations(smm_bgp *h, int n_iters) {
         if (h->sched_iter0 >= 0 && it0 + n > h->sched_iter0 + h->sched_n) n = h->sched_iter0 + h->sched_n - it0;
       }
       CUDA_TRY(prof_begin(h, 0));
-      CUDA_TRY(launch_persistent(h->pb, h->st, it0, n, h->sched_iter0 < 0 ? 2 : h->sched_iter0, h->n_s, h->part_len,
-                                 h->max_seg, h->cta_seg, h->grid, h->mode == 2, h->done_base, s));
-      if (h->mode == 2) h->done_base += (unsigned long long)h->N * (unsigned)n;  // every chain of every rank, n times
+      CUDA_TRY((h->mode == 3 ? ll::launch_persistent : launch_persistent)(
+          h->pb, h->st, it0, n, h->sched_iter0 < 0 ? 2 : h->sched_iter0, h->n_s, h->part_len, h->max_seg, h->cta_seg,
+          h->grid, h->mode >= 2, h->done_base, s));
+      if (h->mode >= 2) h->done_base += (unsigned long long)h->N * (unsigned)n;  // every chain of every rank, n times
       CUDA_TRY(prof_end(h));
       h->prof_iters += h->profiling ? n : 0;
       h->ctr.kernel_launches++;
@@ -1449,6 +1463,8 @@ int smm_bgp_import_state(smm_bgp *h, const void *buf, int64_t nbytes) {
   CUDA_TRY(cudaMemsetAsync(h->val_all.p + 2 * (size_t)h->N, 0, sizeof(double) * h->N, h->stream));
   h->done_base = 0;
   CUDA_TRY(cudaMemsetAsync(h->applied.p, 0, sizeof(unsigned) * L, h->stream));
+  // exchange_mode 3: stale flag-in-data words of the replaced run could carry the tags of the iterations to come
+  if (h->ll.p) CUDA_TRY(cudaMemsetAsync(h->ll.p, 0, sizeof(unsigned long long) * 2 * (size_t)h->N * ll_words(h->P), h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->iter = (int)hd.iter;
   h->sched_iter0 = -1;

@@ -58,6 +58,9 @@ __host__ __device__ inline int global_chain(const DevProblem &pb, int c) { retur
 // slot of global chain g in a rank-major gather buffer (ncclAllGather of the ranks' [L] records, exchange_mode 0)
 __host__ __device__ inline int gather_slot(const DevProblem &pb, int g) { return (g % pb.world) * pb.L + g / pb.world; }
 
+// exchange_mode 3: 8-byte words per chain in the LL table: doubles {value, sigma, params[P]}, two words each (hi, lo)
+__host__ __device__ inline int ll_words(int P) { return 2 * (P + 2); }
+
 struct GridBarrier {
   unsigned arrive;
   unsigned gen;
@@ -92,6 +95,10 @@ struct DevState {
   double *peer_val_all[kMaxWorld];
   unsigned long long *peer_flags[kMaxWorld];  // every rank's flags[kMaxWorld]; we write slot [our rank]
   unsigned long long *flags;               // our own flags[kMaxWorld], written by the peers
+  // exchange_mode 3: flag-in-data ("LL") table [2 parities][N][ll_words(P)] of {32 payload bits | 32-bit iteration tag}
+  // words holding each chain's last-accepted value, its sigma and its last-accepted parameters (null in other modes)
+  unsigned long long *ll;
+  unsigned long long *peer_ll[kMaxWorld];
   // diagnostics
   int *err;
   unsigned long long *phase_ts;  // debug: per-CTA globaltimer stamps of the last iteration (or null)

@@ -34,7 +34,16 @@
 // cut up.  Proposals and the panel simulator use the Box-Muller transform of the same header.
 #include "smm_device.cuh"
 
+// This file is compiled TWICE (smm_jl_b200/build.py): as it stands, and with -DSMM_LL_TU, which adds exchange_mode 3
+// (flag-in-data hand-over, see ll_store) to the barrier-free persistent kernel and puts everything into smm::ll, from
+// which smm_api.cu takes only the persistent launcher.  Two builds instead of one more template parameter because the
+// persistent kernel sits at its register budget: with the mode-3 code in the same instantiation family, ptxas moved
+// spills into the simulate loop of the OTHER modes (measured: 56.6 -> 58.8-61.4 us per C2 iteration in exchange_mode 2
+// from code that never executes there).
 namespace smm {
+#ifdef SMM_LL_TU
+namespace ll {
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // thread groups: a CTA or a warp-aligned part of one, synchronised with a named barrier
@@ -119,6 +128,41 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if (st.phase_ts && threadIdx.x == 0) st.phase_ts[(size_t)(slot)*4 + (i)] = gtimer();      \
   } while (0)
 
+#ifdef SMM_LL_TU
+// ---- flag-in-data words (exchange_mode 3; this translation unit is compiled a second time with -DSMM_LL_TU) ----------
+// A double travels as two 8-byte words {high half | tag}, {low half | tag}; an 8-byte store is single-copy atomic, so a
+// reader that sees the tag sees the payload -- no fence and no separate flag round trip between the producer's store and
+// the consumer's load (the LL protocol of collective libraries).  tag = iteration (never 0; the table starts zeroed).
+__device__ __forceinline__ void ll_store(unsigned long long *p, double v, uint32_t tag) {
+  const unsigned long long a = ((unsigned long long)(uint32_t)__double2hiint(v) << 32) | tag;
+  const unsigned long long b = ((unsigned long long)(uint32_t)__double2loint(v) << 32) | tag;
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+// spin until both words carry `tag`; false = gave up (another CTA aborted, or the timeout: sticky error flag)
+__device__ __forceinline__ bool ll_load(const DevState &st, const unsigned long long *p, uint32_t tag, double &v) {
+  unsigned long long a, b, t0 = 0ull;
+  for (unsigned spins = 0;;) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    if ((uint32_t)a == tag && (uint32_t)b == tag) break;
+    __nanosleep(40);  // back off: thousands of threads polling L2 in a tight loop slow down the chains still finishing
+    if ((++spins & 255u) == 0) {
+      if (t0 == 0ull) t0 = gtimer();
+      const bool aborted = (*(volatile unsigned *)&st.bar->gen & 0x80000000u) != 0u;
+      if (aborted || gtimer() - t0 > kSpinTimeoutNs) {
+        if (!aborted) {
+          atomicOr(st.err, kErrTimeout);
+          atomicOr(&st.bar->gen, 0x80000000u);
+        }
+        v = 0.0;
+        return false;
+      }
+    }
+  }
+  v = __hiloint2double((int)(a >> 32), (int)(b >> 32));
+  return true;
+}
+#endif
+
 __device__ __forceinline__ void load_logtab(smm_logent *dst) {
   const smm_logent *src = smm_logtab();
   for (int i = threadIdx.x; i < (1 << SMM_LOG_BITS); i += blockDim.x) dst[i] = src[i];
@@ -149,8 +193,14 @@ __device__ __forceinline__ smm_u32x4 philox_sim(const DevProblem &pb, uint32_t c
 // at once and the lowest in-support attempt wins: identical to the reference's sequential rejection loop.
 // Result in ps.pp.
 // ------------------------------------------------------------------------------------------------
+// centre_sh (exchange_mode 3 only): shared [P + 1] = the centre's parameters and the chain's sigma, already fetched.
 __device__ void group_proposal(const DevProblem &pb, const DevState &st, const Grp &g, const PropScratch &ps, int c,
-                               int gc, int iter, bool count, const double *centre = nullptr) {
+                               int gc, int iter, bool count, const double *centre = nullptr
+#ifdef SMM_LL_TU
+                               ,
+                               const double *centre_sh = nullptr
+#endif
+) {
   const int P = pb.P, tid = g.tid, nthr = g.n;
   if (iter == 1) {
     for (int k = tid; k < P; k += nthr) ps.pp[k] = pb.init[k];
@@ -159,12 +209,20 @@ __device__ void group_proposal(const DevProblem &pb, const DevState &st, const G
   }
   const int R = rec_len(pb.P, pb.M);
   const double *la = centre ? centre : st.la_cur + (size_t)c * R;  // record of the last accepted evaluation
+#ifdef SMM_LL_TU
+  const double sigma = centre_sh ? centre_sh[P] : __ldcg(st.sigma + c);
+#else
   const double sigma = __ldcg(st.sigma + c);
+#endif
   const int kp = (P + 1) >> 1;
   const int A = nthr / kp;  // attempts per round
   const int bs = pb.batch_size, nb = P / bs;
   for (int k = tid; k < P; k += nthr) {
+#ifdef SMM_LL_TU
+    ps.mu01[k] = __ddiv_rn(__dsub_rn(centre_sh ? centre_sh[k] : __ldcg(la + 3 + k), pb.lb[k]), __dsub_rn(pb.ub[k], pb.lb[k]));
+#else
     ps.mu01[k] = __ddiv_rn(__dsub_rn(__ldcg(la + 3 + k), pb.lb[k]), __dsub_rn(pb.ub[k], pb.lb[k]));
+#endif
     ps.pp[k] = 0.0;  // pp = zero(mu01) (:445)
   }
   for (int b = tid; b < nb; b += nthr) ps.resolved[b] = 0;
@@ -747,6 +805,9 @@ __device__ __forceinline__ void accept_prefetch(const DevProblem &pb, const DevS
 __device__ void group_accept_store(const DevProblem &pb, const DevState &st, const Grp &g, const FinScratch &fs, int c,
                                    int gc, int iter, bool fused, bool flow = false, bool wait_applied = false,
                                    const AcceptPre *pre = nullptr) {
+#ifdef SMM_LL_TU
+  const bool ll = flow && st.ll != nullptr && pre != nullptr;  // exchange_mode 3: one warp, chain state prefetched
+#endif
   const int tid = g.tid;
   const int P = pb.P, M = pb.M, R = rec_len(P, M), L = pb.L;
   if (flow && wait_applied && !pre) wait_exchange_applied(st, g, c, iter);
@@ -796,10 +857,20 @@ __device__ void group_accept_store(const DevProblem &pb, const DevState &st, con
     st.n_acc[c] = n_acc;
     const double rate = __ddiv_rn((double)n_acc, (double)n_noex);
     st.accept_rate[c] = rate;
+#ifdef SMM_LL_TU
+    double sigma_cur = sigma0;
+    if (iter > 1 && iter % pb.sigma_update_steps == 0) {
+      sigma_cur = rate > 0.234 ? __dmul_rn(sigma0, __dadd_rn(1.0, pb.sigma_adjust_by))
+                               : __dmul_rn(sigma0, __dsub_rn(1.0, pb.sigma_adjust_by));
+      st.sigma[c] = sigma_cur;
+    }
+    if (ll) ((double *)fs.flags)[1] = sigma_cur;  // (the spare double behind the two flags of the persistent kernel's scratch)
+#else
     if (iter > 1 && iter % pb.sigma_update_steps == 0) {
       st.sigma[c] = rate > 0.234 ? __dmul_rn(sigma0, __dadd_rn(1.0, pb.sigma_adjust_by))
                                  : __dmul_rn(sigma0, __dsub_rn(1.0, pb.sigma_adjust_by));
     }
+#endif
     // set_eval!
     double curr, best;
     int best_id;
@@ -836,6 +907,61 @@ __device__ void group_accept_store(const DevProblem &pb, const DevState &st, con
   for (int k = tid; k < P; k += g.n) st.t_params[slot * P + k] = fs.pp[k];
   for (int k = tid; k < M; k += g.n) st.t_mom[slot * M + k] = fs.mom[k];
   const int par = fused ? (iter & 1) : 0;
+#ifdef SMM_LL_TU
+  if (ll) {
+    // exchange_mode 3.  What the next iteration's critical path needs -- value (exchange), sigma and parameters
+    // (proposal centre) -- goes to every rank as flag-in-data words: no system fence, no counter round trip.  The
+    // chain's local state written above is ordered before them for this GPU's readers by a gpu-scope fence (the warp
+    // barrier makes it cumulative over the lanes); the full records for the owners' swap_ev_ij! follow and are covered
+    // by the completion counter, which nobody on the critical path waits for.
+    auto published = [&](int k, double old) -> double {  // entry k of the chain's last accepted record
+      if (!acc) return old;
+      return k == 0 ? fs.value[0] : k == 1 ? fs.value[1] : k == 2 ? (double)fs.flags[1] : k < 3 + P ? fs.pp[k - 3] : fs.mom[k - 3 - P];
+    };
+#pragma unroll
+    for (int j = 0; j < kPreRec; ++j) {  // entry tid + 32 j of la_cur[c] sits in pre->la[j] (static indices only)
+      const int k = tid + 32 * j;
+      if (k < R) {
+        const double v = published(k, pre->la[j]);
+        if (acc) la[k] = v;
+        pub[k] = v;
+      }
+    }
+    gsync(g);
+    const int W = ll_words(P);
+    const double sigma_cur = ((const double *)fs.flags)[1];
+    for (int q0 = 0; q0 < P + 2; q0 += 32) {
+      const int q = q0 + tid;                                                // double q of the LL record: value, sigma, params
+      const int kq = q == 0 ? 0 : (q >= 2 && q < P + 2 ? 3 + (q - 2) : -1);  // its entry of the record
+      double vold = 0.0;
+#pragma unroll
+      for (int j = 0; j < kPreRec; ++j) {
+        if (32 * j < 3 + P) {  // (warp uniform: value and parameters sit in the first 3 + P entries of the record)
+          const double t = __shfl_sync(0xffffffffu, pre->la[j], (kq < 0 ? 0 : kq) & 31);
+          if (kq >= 0 && (kq >> 5) == j) vold = t;
+        }
+      }
+      if (q < P + 2) {
+        const double v = q == 1 ? sigma_cur : (acc ? (kq == 0 ? fs.value[0] : fs.pp[kq - 3]) : vold);
+        fence_acq_rel_gpu();
+        for (int r = 0; r < pb.world; ++r)
+          ll_store(st.peer_ll[r] + ((size_t)par * pb.N + gc) * W + 2 * q, v, (uint32_t)iter);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kPreRec; ++j) {  // the all-gather of the full records: one coalesced row per peer
+      const int k = tid + 32 * j;
+      if (k < R) {
+        const double v = published(k, pre->la[j]);
+        for (int r = 0; r < pb.world; ++r) st.peer_la_all[r][((size_t)par * pb.N + gc) * R + k] = v;
+        if (k == 0)
+          for (int r = 0; r < pb.world; ++r) st.peer_val_all[r][(size_t)par * pb.N + gc] = v;
+      }
+    }
+    gsync(g);
+    return;
+  }
+#endif
   for (int k = tid; k < R; k += g.n) {
     double v;
     if (acc) {
@@ -1126,6 +1252,10 @@ struct PersistSmem {
   double g_mu01[kPGroups][SMM_MAX_PARAMS];
   int g_first[kPGroups][SMM_MAX_PARAMS];
   int g_resolved[kPGroups][SMM_MAX_PARAMS];
+#ifdef SMM_LL_TU
+  double g_cen[kPGroups][SMM_MAX_PARAMS + 1];  // exchange_mode 3: centre parameters + sigma of the group's proposal
+  unsigned n_finished_prev;                    // exchange_mode 3: completions of the previous iteration, published late
+#endif
 };
 
 // Level schedule of exchange `pit` -> shared memory (called at the start of phase A of iteration pit, far
@@ -1142,11 +1272,12 @@ __device__ __forceinline__ void prefetch_schedule(const DevState &st, int pit, i
 
 // swap_ev_ij! for the chains this CTA owns, one warp per chain, from the replayed outcome in shared memory
 __device__ void persistent_exchange_apply(const DevProblem &pb, const DevState &st, int pit, bool fused,
-                                          const unsigned short *own, const unsigned short *exch, bool flow) {
+                                          const unsigned short *own, const unsigned short *exch, bool flow,
+                                          bool one_warp = false) {
   const int tid = threadIdx.x, b = blockIdx.x, G = gridDim.x;
   const int N = pb.N, L = pb.L, R = rec_len(pb.P, pb.M);
   const double *la_all = st.la_all + (size_t)(fused ? (pit & 1) : 0) * N * R;
-  const int warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int warp = one_warp ? 0 : tid >> 5, nwarps = one_warp ? 1 : blockDim.x >> 5;  // one_warp: the caller's warp does them all
   for (int c = b + warp * G; c < L; c += nwarps * G) {  // one warp per owned chain
     const int gc = global_chain(pb, c);
     const int partner = exch[gc];
@@ -1172,12 +1303,17 @@ __device__ void persistent_exchange(const DevProblem &pb, const DevState &st, in
   const int par = fused ? (pit & 1) : 0;
   const double *la_all = st.la_all + (size_t)par * N * R;
   const double *val_all = st.val_all + (size_t)par * N;
-  for (int i = tid; i < N; i += blockDim.x) {
-    val[i] = __ldcg(val_all + i);
-    own[i] = (unsigned short)i;
-    exch[i] = 0;
+#ifdef SMM_LL_TU
+  if (!(flow && st.ll))  // (exchange_mode 3 filled val / own / exch while it waited for the values)
+#endif
+  {
+    for (int i = tid; i < N; i += blockDim.x) {
+      val[i] = __ldcg(val_all + i);
+      own[i] = (unsigned short)i;
+      exch[i] = 0;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // The levels are walked by one warp (a __syncwarp per level) or, when the levels are wide (many chains over several
   // GPUs), by kExchWarps warps with a named barrier per level; the pairs of a level share no chain.
   const int nw = N > 512 ? kExchWarps : 1;
@@ -1250,6 +1386,36 @@ __device__ bool wait_all_done(const DevProblem &pb, const DevState &st, unsigned
   __syncthreads();
   return s_bad == 0;
 }
+
+#ifdef SMM_LL_TU
+// exchange_mode 3, before persistent_exchange_apply: a warp that owns a swapped chain is about to copy full records, which
+// are covered by the completion counter (published a moment ago by every CTA of every rank): it waits for it here
+__device__ __forceinline__ void owner_wait_records(const DevProblem &pb, const DevState &st, const unsigned short *exch,
+                                                   unsigned long long target) {
+  bool mine = false;  // does this CTA own a chain that was swapped?
+  for (int c = blockIdx.x; c < pb.L; c += gridDim.x) mine = mine || exch[global_chain(pb, c)] != 0;
+  if (!mine) return;
+  if ((threadIdx.x & 31) == 0) {
+    const unsigned long long *ctr = done_counter(pb, st.val_all);
+    const unsigned long long t0 = gtimer();
+    for (unsigned spins = 0;;) {
+      unsigned long long v;
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
+      if ((++spins & 63u) == 0 && ((ld_relaxed_gpu(&st.bar->gen) & 0x80000000u) || gtimer() - t0 > kSpinTimeoutNs)) {
+        atomicOr(st.err, kErrTimeout);
+        atomicOr(&st.bar->gen, 0x80000000u);
+        break;
+      }
+    }
+    if (pb.world > 1)
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else
+      fence_acq_rel_gpu();
+  }
+  __syncwarp();
+}
+#endif
 
 // The other half: after the CTA's finishing warps have stored everything (CTA barrier by the caller), one thread fences
 // once -- system scope when the records went to peer GPUs -- and adds the number of chains this CTA finished to the
@@ -1397,7 +1563,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
   // work distribution inside the CTA: every warp first walks a fixed share (kStaticNum/kStaticDen of an equal split,
   // one queue access instead of many), the rest is handed out dynamically in shrinking grabs so that all 32 warps
   // finish within a step of each other whatever the warp scheduler favours
-  const int static_units = (int)(((long long)total_units * kStaticNum / kStaticDen) / (kPersistThreads / 32));
+#ifdef SMM_LL_TU
+  // exchange_mode 3: the last warp is the CTA's SERVICE warp -- at the start of phase A it publishes the previous
+  // iteration's completions (a system fence: ~3.5 us) and applies the exchange to the chains the CTA owns (after waiting
+  // for the completion counter: a few more) -- so it takes no fixed share and joins the dynamic hand-out when it is done;
+  // the other warps never stall on either
+  constexpr int kStaticWarps = kPersistThreads / 32 - 1;
+#else
+  constexpr int kStaticWarps = kPersistThreads / 32;
+#endif
+  const int static_units = (int)(((long long)total_units * kStaticNum / kStaticDen) / kStaticWarps);
   const int n_owned = b < L ? (L - b + G - 1) / G : 0;  // chains b, b + G, ...
   // proposal groups: as many threads per chain as the CTA can spare (more attempts per round)
   const int n_prop = kFlow ? n_seg : n_owned;  // chains this CTA computes proposals for
@@ -1417,7 +1592,29 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
     bool have_ex = false;
     if (kFlow) {
       // ---- wait for iteration it-1 of every chain, replay its exchange, propose for the chains simulated here ----
+#ifdef SMM_LL_TU
+      // exchange_mode 3: the values themselves say when they have arrived (flag-in-data words, no counter round trip)
+      const uint32_t tag = (uint32_t)(it - 1);
+      const int W = ll_words(P);
+      const unsigned long long *llp = st.ll + (size_t)((it - 1) & 1) * N * W;
+      if (it > iter0) {
+        int bad = 0;
+        // (four warps poll, the other twenty wait at the barrier: every poller is L2 traffic that competes with the
+        // warps still finishing their chains)
+        for (int i = tid; i < N; i += 128) {
+          if (tid >= 128) break;
+          double v;
+          if (!ll_load(st, llp + (size_t)i * W, tag, v)) bad = 1;
+          val[i] = v;
+          own[i] = (unsigned short)i;
+          exch[i] = 0;
+        }
+        fence_acq_rel_gpu();  // pairs with the finishing warp's fence: the chains' local state is visible behind the values
+        if (__syncthreads_or(bad)) return;
+      }
+#else
       if (it > iter0 && !wait_all_done(pb, st, done_base + (unsigned long long)N * (unsigned)(it - iter0))) return;
+#endif
       PHASE_STAMP((b * 2 + (it & 1)) * 2, 3);
       have_ex = N > 1 && it - 1 >= 2 && it > iter0;
       if (have_ex && (n_owned > 0 || n_seg > 0))
@@ -1430,7 +1627,25 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
           const int c = sm.seg_c[sidx], gc = global_chain(pb, c);
           // centre: the record that sits on this chain after the exchange (its own last accepted one if not swapped)
           const double *centre = have_ex ? la_prev + (size_t)own[gc] * rec_len(P, pb.M) : nullptr;
+#ifdef SMM_LL_TU
+          const double *centre_sh = nullptr;
+          if (it > iter0) {
+            // the parameters that sit on this chain after the exchange come from the flag-in-data table, like the chain's
+            // sigma (which stays with the chain): no read of a record that only the completion counter covers
+            const int o = have_ex ? (int)own[gc] : gc;
+            if (gprop.tid <= P) {
+              const int q = gprop.tid < P ? 2 + gprop.tid : 1, rec = gprop.tid < P ? o : gc;
+              double v;
+              ll_load(st, llp + (size_t)rec * W + 2 * q, tag, v);
+              sm.g_cen[gi][gprop.tid] = v;
+            }
+            gsync(gprop);
+            centre_sh = sm.g_cen[gi];
+          }
+          group_proposal(pb, st, gprop, ps, c, gc, it, sm.seg_slot[sidx] == 0, centre, centre_sh);
+#else
           group_proposal(pb, st, gprop, ps, c, gc, it, sm.seg_slot[sidx] == 0, centre);
+#endif
           for (int q = gprop.tid; q < P; q += gsize) pp_seg[(size_t)sidx * D + q] = ps.pp[q];
         }
       }
@@ -1461,11 +1676,29 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       for (int e = tid; e < n_seg * D; e += kPersistThreads) pp_seg[e] = __ldcg(st.pp + (size_t)sm.seg_c[e / D] * P + e % D);
     for (int e = tid; e < n_seg * 2 * D; e += kPersistThreads) acc[e] = 0ull;
     if (tid == 0) {
-      sm.next_unit = static_units * (kPersistThreads / 32);
+      sm.next_unit = static_units * kStaticWarps;
+#ifdef SMM_LL_TU
+      sm.n_finished_prev = sm.n_finished;
+#endif
       sm.n_finished = 0u;
     }
     if ((n_owned > 0 || (kFlow && n_seg > 0)) && N > 1 && it >= 2) prefetch_schedule(st, it, sched_iter0, n_s, sij, soff, &sm.nlev);
     __syncthreads();
+#ifdef SMM_LL_TU
+    // exchange_mode 3, service warp: the previous iteration's completions are published HERE, off the critical path
+    // (nobody on it reads the counter any more: only the swap_ev_ij! right below and the end of the launch do), then the
+    // exchange is applied to the chains this CTA owns
+    if (kFlow && (tid >> 5) == kStaticWarps) {
+      if (lane == 0 && it > iter0)
+        publish_completions(pb, st, sm.n_finished_prev,
+                            st.phase_ts ? st.phase_ts + ((size_t)G * 4 + L + (size_t)b * 2 + ((it - 1) & 1)) * 4 : nullptr);
+      __syncwarp();
+      if (have_ex && n_owned > 0) {
+        owner_wait_records(pb, st, exch, done_base + (unsigned long long)N * (unsigned)(it - iter0));
+        persistent_exchange_apply(pb, st, it - 1, true, own, exch, true, true);
+      }
+    }
+#endif
     if (pb.obj == SMM_OBJ_NORM_SLOW) slow_spin(pb.slow_seconds);
     {
       const uint32_t c3base = SMM_STREAM_SIM << 28;
@@ -1474,7 +1707,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       Acc a{0ull, 0ull};
       // barrier-free mode: the owner's part of the exchange (trace slot, state of the swapped chains) is off the
       // critical path -- its warps do it here, before their first units; finishers wait on applied[c] much later
+#ifndef SMM_LL_TU
       if (kFlow && have_ex && n_owned > 0) persistent_exchange_apply(pb, st, it - 1, true, own, exch, true);
+#endif
       ZigCtx cx = zig_ctx(s_zigtab, zq, S);
       cx.D = D;
       cx.c3 = c3base | (pb.noseed ? ((uint32_t)it & SMM_ITER_MASK) : 0u);
@@ -1504,6 +1739,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
       // Every warp first walks its fixed share of the CTA's units; what the fixed shares leave is handed out by guided
       // self-scheduling: a warp takes (remaining / 2 warps-worth, at most kMaxGrab, at least kMinGrab) consecutive units.
       int u = (tid >> 5) * static_units, uend = u + static_units;
+#ifdef SMM_LL_TU
+      if ((tid >> 5) == kStaticWarps) u = uend = 0;  // the service warp only takes from the dynamic hand-out
+#endif
       for (;;) {
         if (u >= uend) {
           int start = 0, g = 0;
@@ -1594,7 +1832,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) bgp_persistent_kernel(DevP
           lane == 0)
         atomicAdd(&sm.n_finished, 1u);
     PHASE_STAMP((b * 2 + (it & 1)) * 2, 2);  // warp 0 done (incl. chain finalisation)
+#ifdef SMM_LL_TU
+    if (kFlow && it == iter0 + n_iters - 1) {  // (exchange_mode 3: only the launch's last iteration is published here)
+#else
     if (kFlow) {  // one fence and one counter update per CTA tell every rank which chains are complete
+#endif
       __syncthreads();
       if (tid == 0)  // (debug rows behind the per-chain rows: two per CTA, by iteration parity)
         publish_completions(pb, st, sm.n_finished,
@@ -1919,7 +2161,9 @@ __global__ void __launch_bounds__(kBound) sim_throughput_kernel(DevProblem pb, i
 // ------------------------------------------------------------------------------------------------
 // dynamic-panel objective (C4): its kernels use the device functions above
 // ------------------------------------------------------------------------------------------------
+#ifndef SMM_LL_TU
 #include "smm_panel.cuh"
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // launchers (called from smm_api.cu)
@@ -2022,4 +2266,7 @@ void launch_sim_throughput(const DevProblem &pb, int n_per_thread, int blocks, i
     go(sim_throughput_kernel<1024>);
 }
 
+#ifdef SMM_LL_TU
+}  // namespace ll
+#endif
 }  // namespace smm

@@ -171,7 +171,7 @@ def test_exchange_mode_selection_and_fallback(monkeypatch):
     from smm_jl_b200._abi import SMM_E_UNSUPPORTED_SHAPE, SMM_E_CUDA
     m = _toy_problem(api)
     assert api._exchange_mode(m, {}, 2) == 2
-    assert api._exchange_mode(m, {"world_size": 8}, 2) == 2
+    assert api._exchange_mode(m, {"world_size": 8}, 2) == 3      # several GPUs: flag-in-data hand-over
     assert api._exchange_mode(m, {"exchange_mode": 1, "world_size": 8}, 2) == 1
     assert api._exchange_mode(m, {}, 40) == 0
     assert api._exchange_mode(_toy_problem(api, 2, api.objfunc_panel), {}, 2) == 0

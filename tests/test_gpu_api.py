@@ -130,7 +130,7 @@ def test_checkpoint_blob_is_bound_to_its_ensemble(tmp_path, smm):
         api.save(MA, os.path.join(tmp_path, "late.pkl"))
 
 
-@pytest.mark.parametrize("mode,window", [(0, 0), (1, 0), (1, 7), (1, 50), (0, 13)])
+@pytest.mark.parametrize("mode,window", [(0, 0), (1, 0), (1, 7), (1, 50), (0, 13), (3, 0), (3, 7)])
 def test_streaming_run_equals_step_and_read(smm, mode, window):
     """smm_bgp_run (windows computed while the previous window's rows travel to the host) = step + read_trace"""
     import numpy as np

@@ -54,7 +54,7 @@ def _worker(rank, world, port, n_chains, n_iter, mode, q, kind="mvnormal", data_
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_n_gpus_match_the_oracle(smm, oracle, world, mode):
     """world ranks x 16 chains: NCCL all-gather (mode 0), fused peer stores + flag exchange (mode 1), per-chain
@@ -154,7 +154,7 @@ def test_handles_in_sequence_share_the_communicator_and_arena(smm, oracle):
     # (chains, iterations, mode): fused, fused with a larger ensemble (same arena, other offsets), NCCL path on the
     # cached communicator, grid-barrier mode with an ensemble that outgrows the arena (it is remade collectively), and
     # a fused handle created while the previous one is still alive
-    plan = [(32, 24, 2), (64, 16, 2), (32, 12, 0), (1024, 6, 1), (32, 20, 2), (48, 12, 2)]
+    plan = [(32, 24, 2), (64, 16, 3), (32, 12, 0), (1024, 6, 1), (32, 20, 3), (48, 12, 2)]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

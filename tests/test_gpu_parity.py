@@ -220,7 +220,7 @@ def test_large_config_properties(smm):
     assert (sigma > 0).all() and ((acc >= 0) & (acc <= 1)).all()
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_c2_full_size_against_the_oracle(smm, oracle, mode):
     """BASELINE C2 at FULL size (256 chains x 10 000 draws, the benchmarked configuration) in every exchange mode the
     bench can run, compared entry by entry with the oracle: bookkeeping exact, floats to 1e-6 relative"""
@@ -237,7 +237,7 @@ def test_c2_full_size_against_the_oracle(smm, oracle, mode):
     assert max_rel_err(tr, ref.trace) < 1e-9
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_zero_and_negative_weights_on_device(smm, oracle, mode):
     """The reference's own fixture carries zero and negative moment weights (test/include/test-include.jl:78): a zero
     weight divides by zero (ObjExamples.jl:97) -> value = +Inf for every evaluation, a negative one is squared away.
@@ -254,7 +254,7 @@ def test_zero_and_negative_weights_on_device(smm, oracle, mode):
     assert (tr.accepted[0] == 1).all() and (tr.accepted[1:] == 0).all() and ctr["swaps"] == 0
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_nonfinite_branches_of_accept_reject_on_device(smm, oracle, mode):
     """A weight of 1e-155 makes ((sim - data) / w)^2 overflow unless |sim - data| < 0.13, so chains wander between
     finite (~1e300) and infinite objective values and doAcceptReject! takes every branch (AlgoBGP.jl:336-367) on the
@@ -275,7 +275,7 @@ def test_nonfinite_branches_of_accept_reject_on_device(smm, oracle, mode):
     assert ((tr.prob[1:] == 0) & (tr.status[1:] == 1) & np.isinf(tr.value[1:])).sum() > 10
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_nan_objective_is_the_reference_error(smm, oracle, mode):
     """`eval_new.value >= 0 || error(...)` (AlgoBGP.jl:341) also fires for NaN: a NaN data moment makes every value
     NaN, iteration 1 is accepted unconditionally (:327-333), iteration 2 aborts the run -- on both sides"""

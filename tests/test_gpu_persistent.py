@@ -10,9 +10,10 @@ from tests.parity import assert_trace_parity
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 2], ids=["barriers", "dataflow"])
+@pytest.fixture(params=[1, 2, 3], ids=["barriers", "dataflow", "flag-in-data"])
 def pmode(request):
-    """exchange_mode 1 = persistent kernel with grid barriers, 2 = barrier-free (per-chain completion tags)"""
+    """exchange_mode 1 = persistent kernel with grid barriers, 2 = barrier-free (one completion counter per rank),
+    3 = barrier-free with flag-in-data words for the values / proposal centres"""
     return request.param
 
 

@@ -18,7 +18,7 @@ if rank == 0 and world > 1:
 if world > 1:
     dist.broadcast(idt, 0)
 chains = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-cfg = configs.mvnormal(chains * world, 200, exchange_mode=2)
+cfg = configs.mvnormal(chains * world, 200, exchange_mode=int(os.environ.get("SMM_PHASE_MODE", "2")))
 cfg.device, cfg.world_size, cfg.rank, cfg.nccl_id = lr, world, rank, bytes(idt.cpu().tolist())
 pct = lambda a: tuple(np.percentile(a, [0, 50, 90, 100]))
 with _lib.BGPHandle(cfg) as h:
