@@ -20,7 +20,7 @@
 //         over NVLink]                                                                      -- barrier,
 //         folded with a cross-GPU flag exchange: the all-gather costs no launch and no extra barrier --
 //
-//  (C) persistent, barrier-free (exchange_mode 2): bgp_persistent_kernel<true>.  The warp that finishes a chain
+//  (C) persistent, barrier-free (exchange_mode 2; exchange_mode 3 in the -DSMM_LL_TU build): bgp_persistent_kernel<true>.  The warp that finishes a chain
 //      publishes a per-chain completion tag; every CTA waits for the tags of iteration i-1, replays the exchange,
 //      computes the proposals of the chains IT simulates, simulates, finishes -- no grid barrier anywhere.
 //
