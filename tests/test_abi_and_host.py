@@ -204,3 +204,14 @@ def test_exchange_mode_selection_and_fallback(monkeypatch):
     monkeypatch.setattr(_lib, "BGPHandle", Broken)
     with pytest.raises(_lib.SMMError):                                        # other failures are never retried
         api.MAlgoBGP(m, {"N": 4, "maxiter": 5})._handle()
+
+
+def test_library_holds_both_builds_of_the_persistent_kernel():
+    """smm_kernels.cu is compiled twice (smm_jl_b200/build.py): plain, and with -DSMM_LL_TU into smm::ll for
+    exchange_mode 3.  Both launchers and both kernels must be in the shared library (no GPU needed to check)."""
+    import subprocess
+    from smm_jl_b200 import _lib
+    _lib.lib()
+    syms = subprocess.run(["nm", "-C", _lib.lib_path()], capture_output=True, text=True).stdout
+    assert "smm::launch_persistent(" in syms and "smm::ll::launch_persistent(" in syms
+    assert "smm::bgp_persistent_kernel<true>" in syms and "smm::ll::bgp_persistent_kernel<true>" in syms
