@@ -100,3 +100,34 @@ def test_cuda_path_matches_the_real_smm_jl(case, mode, smm):
     assert_trace_parity(got, want)
     np.testing.assert_allclose(s, sigma, rtol=1e-12)
     np.testing.assert_allclose(a, acc, rtol=1e-12)
+
+
+def test_stream_files_as_the_harness_indexes_them(oracle, monkeypatch):
+    """The harness reads the dumped arrays column-major with the dimensions reversed and indexes them 1-based as
+    ZPROP[k, attempt, iter, chain], UACC[iter, chain], PAIRS[1:2, t, iter], ZSIM[s, k].  Here the numpy restatement of the
+    algorithm runs on the FILES through exactly those index expressions (Fortran-order views, 1-based arithmetic) and
+    must reproduce the oracle's trace: a dimension or off-by-one mistake in the dump or in the harness's indexing shows
+    up here, without Julia."""
+    from oracle import oracle_np as onp
+    case = "mvnormal_8chains"
+    cfg, _ = dump_streams.cases()[case]
+    d = os.path.join(GOLDEN, case)
+    meta = julia_trace.read_meta(os.path.join(d, "meta.txt"))
+    N, P, S, I, A, NS = (int(meta[k]) for k in ("n_chains", "n_params", "n_sim", "n_iter", "n_attempts", "n_pairs"))
+    ZSIM = np.fromfile(os.path.join(d, "zsim.f64")).reshape((S, P), order="F")
+    ZPROP = np.fromfile(os.path.join(d, "zprop.f64")).reshape((P, A, I, N), order="F")
+    UACC = np.fromfile(os.path.join(d, "uacc.f64")).reshape((I, N), order="F")
+    PAIRS = np.fromfile(os.path.join(d, "pairs.i32"), dtype=np.int32).reshape((2, NS, I), order="F")
+    j = lambda i: i - 1                                   # Julia's 1-based index -> numpy
+    monkeypatch.setattr(onp, "prop_normal", lambda seed, c, it, a, k: float(ZPROP[j(k + 1), j(a + 1), j(it), j(c + 1)]))
+    monkeypatch.setattr(onp, "acc_uniform", lambda seed, c, it: float(UACC[j(it), j(c + 1)]))
+    monkeypatch.setattr(onp, "pair_sample", lambda seed, it, n: [(int(PAIRS[0, t, j(it)]) - 1, int(PAIRS[1, t, j(it)]) - 1) for t in range(NS)])
+    monkeypatch.setattr(onp, "sim_normals", lambda seed, k, s, *a, **kw: ZSIM[:, j(k + 1)].copy())
+    n = 40
+    r = onp.run(cfg, n)
+    ref = oracle.run(cfg, n)
+    for f in ("accepted", "status", "exchanged", "best_id"):
+        assert np.array_equal(np.asarray(r[f]), getattr(ref.trace, f)), f
+    assert np.array_equal(np.asarray(r["params"]), ref.trace.params)
+    np.testing.assert_allclose(np.asarray(r["value"]), ref.trace.value, rtol=1e-9)
+    np.testing.assert_allclose(r["sigma"], ref.sigma, rtol=1e-12)
